@@ -1,0 +1,77 @@
+// Shared host/device definitions of the dcb200 engine: model constants, HBM image
+// layouts and kernel parameter blocks.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace dcb {
+
+// ------------------------------------------------------------------ model geometry
+// The released DeepConsensus transformers all use hidden_size=280, 2 heads
+// (model_configs.py:84,139); the engine fixes these at compile time and validates
+// params.json against them in dcb_create().  Everything else (max_passes,
+// max_length, layers, filter_size, ReZero vs LayerNorm, ccs_bq, band) is runtime.
+constexpr int kTileM = 128;     // tokens per tile == UMMA M == TMEM lanes
+constexpr int kD = 280;         // hidden_size
+constexpr int kDP = 288;        // hidden_size padded to a multiple of 16 (UMMA K / N granularity)
+constexpr int kHeads = 2;
+constexpr int kDH = 140;        // size per head
+constexpr int kDHP = 144;       // padded per-head size (multiple of 16)
+constexpr int kQKVN = 3 * kHeads * kDHP;  // 864: [q_h0|q_h1|k_h0|k_h1|v_h0|v_h1]
+constexpr int kNC = 144;        // UMMA N per instruction for the d-wide GEMMs (288 = 2 x 144)
+constexpr int kVocab = 5;       // ' ATCG' (dc_constants.py:39-42)
+constexpr int kFFChunk = 128;   // filter_size is processed in chunks of 128 hidden units
+
+// ------------------------------------------------------------------ HBM images
+// bf16 activation image ("A operand image"): [tile][K/8][128][8]  -> 16 B per (chunk,row)
+// fp32 residual image:                        [tile][288/4][128][4] -> 16 B per (chunk,row)
+// Both make a warp's accesses (lane == row) 512 B contiguous.
+constexpr int kXChunks = kDP / 4;  // 72
+__host__ __device__ inline size_t act_image_elems(int k) { return (size_t)kTileM * k; }
+__host__ __device__ inline size_t x_image_elems() { return (size_t)kTileM * kDP; }
+
+// ------------------------------------------------------------------ embed descriptor
+// One entry per column e of the concatenated embedding (networks.py:457-506).
+struct EmbedCol {
+  int16_t src_row;    // input row r
+  int16_t width;      // embedding width of that row's table
+  int16_t col;        // column within the embedding vector
+  int16_t shift;      // +1 for the ccs_bq row (networks.py:495)
+  int32_t table_off;  // element offset of the table in the packed bf16 table blob
+  int32_t vocab;      // rows of the table
+  float clip_hi;      // > 0: clip value to [0, clip_hi] first (data_providers.py:151-162)
+};
+
+// ------------------------------------------------------------------ row epilogue
+// Shared tail of every d-wide GEMM: x_new = acc (+ x_old) (+ bias) (+ pos-enc);
+// write x_new (fp32 image) and the next sub-layer's bf16 operand image
+// (identity for ReZero, LayerNorm(eps=1e-6) otherwise).
+struct RowEpi {
+  float* x;              // fp32 residual image of the chunk (read when has_xold, always written)
+  __nv_bfloat16* xb;     // bf16 operand image for the next GEMM (may be null: skip)
+  const float* bias;     // [288] or null
+  const float* pe;       // [L][288] or null
+  const float* ln_g;     // [288] or null  (null => xb = bf16(x_new))
+  const float* ln_b;     // [288]
+  int has_xold;
+  int L;
+};
+
+struct HeadParams {
+  const float* x;        // fp32 residual image
+  const float* ln_g;     // final LayerNorm gamma/beta [288]
+  const float* ln_b;
+  const float* wfc;      // [280][5]
+  const float* bfc;      // [5]
+  uint8_t* bases;        // [M] ASCII ' ATCG'
+  uint8_t* quals;        // [M] Phred+33
+  float* probs;          // [M][5] or null
+  float* logits;         // [M][5] or null
+  int M;                 // valid tokens
+  int calib_enabled;
+  float calib_thr, calib_w, calib_b;
+  double calib_w64, calib_b64, calib_thr64;
+  float max_q;
+};
+
+}  // namespace dcb

@@ -1,0 +1,595 @@
+// dcb200 engine: C-ABI implementation (include/dcb200.h) -- configuration, weight packing into
+// the device operand images, workspace management and the per-chunk launch sequence.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dcb200.h"
+#include "kernels.h"
+
+using namespace dcb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct LayerDev {
+  __nv_bfloat16* wqkv = nullptr;  // 2 groups x [36][432][8]
+  __nv_bfloat16* wo = nullptr;    // [36][288][8]
+  uint8_t* wffn = nullptr;        // per ff chunk: [36][128][8] then [16][288][8]
+  float* b1 = nullptr;            // [ff]
+  float* b2 = nullptr;            // [288] (gain folded)
+  float* ln_g[2] = {nullptr, nullptr};  // pre-norm gamma/beta of the attention / FFN sub-layer
+  float* ln_b[2] = {nullptr, nullptr};
+};
+
+}  // namespace
+
+struct dcb_engine {
+  dcb_config cfg{};
+  std::string err;
+  int R = 0, L = 0, E = 0, Epad = 0, echunks = 0;
+  int chunk_tiles = 0, chunk_windows = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool weights_loaded = false;
+  bool debug = false;
+  float last_ms = 0.f;
+  int last_launches = 0;
+  int last_chunk_tokens = 0;
+  // model
+  EmbedCol* d_cols = nullptr;
+  __nv_bfloat16* d_tables = nullptr;
+  __nv_bfloat16* d_wc = nullptr;
+  float* d_pe = nullptr;
+  std::vector<LayerDev> layers;
+  float *d_fln_g = nullptr, *d_fln_b = nullptr, *d_wfc = nullptr, *d_bfc = nullptr;
+  // workspace
+  float* d_rows = nullptr;
+  __nv_bfloat16* d_embqkv = nullptr;
+  float* d_x = nullptr;
+  __nv_bfloat16* d_xb = nullptr;
+  __nv_bfloat16* d_att = nullptr;
+  uint8_t *d_bases = nullptr, *d_quals = nullptr;
+  float *d_probs = nullptr, *d_logits = nullptr;
+  int* d_status = nullptr;
+  float* d_dbg = nullptr;  // [stages][chunk_tiles * x_image]
+  std::vector<void*> owned;
+};
+
+namespace {
+
+int fail(dcb_engine* e, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(e, call)                                                                     \
+  do {                                                                                  \
+    cudaError_t _st = (call);                                                           \
+    if (_st != cudaSuccess)                                                             \
+      return fail(e, DCB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), \
+                  __FILE__, __LINE__);                                                  \
+  } while (0)
+
+template <typename T>
+int dev_alloc(dcb_engine* e, T** p, size_t n) {
+  CU(e, cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  CU(e, cudaMemset(*p, 0, n * sizeof(T)));
+  e->owned.push_back(*p);
+  return DCB_OK;
+}
+
+template <typename T>
+int upload(dcb_engine* e, T** p, const std::vector<T>& h) {
+  int rc = dev_alloc(e, p, h.size());
+  if (rc) return rc;
+  CU(e, cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return DCB_OK;
+}
+
+// B-operand image [K/8][N][8] bf16 from a getter W(k, n) (zero outside the real extents).
+std::vector<__nv_bfloat16> pack_b(int kpad, int n, const std::function<float(int, int)>& w) {
+  std::vector<__nv_bfloat16> img((size_t)kpad * n);
+  for (int kc = 0; kc < kpad / 8; ++kc)
+    for (int r = 0; r < n; ++r)
+      for (int j = 0; j < 8; ++j)
+        img[((size_t)kc * n + r) * 8 + j] = __float2bfloat16(w(kc * 8 + j, r));
+  return img;
+}
+
+struct TensorMap {
+  std::map<std::string, const dcb_tensor*> m;
+  dcb_engine* e;
+  const float* get(const std::string& name, std::initializer_list<int64_t> shape, int* rc) {
+    auto it = m.find(name);
+    if (it == m.end()) {
+      *rc = fail(e, DCB_ERR_WEIGHTS, "missing variable %s", name.c_str());
+      return nullptr;
+    }
+    const dcb_tensor* t = it->second;
+    bool ok = t->ndim == (int)shape.size() && t->data != nullptr;
+    int i = 0;
+    for (int64_t s : shape) { if (ok && t->shape[i] != s) ok = false; ++i; }
+    if (!ok) {
+      *rc = fail(e, DCB_ERR_WEIGHTS, "variable %s has the wrong shape/ndim", name.c_str());
+      return nullptr;
+    }
+    return t->data;
+  }
+};
+
+std::vector<float> pad288(const float* src, float scale = 1.f) {
+  std::vector<float> v(kDP, 0.f);
+  for (int i = 0; i < kD; ++i) v[i] = src[i] * scale;
+  return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dcb_version(void) { return "dcb200 0.1.0 (sm_100a)"; }
+
+const char* dcb_last_error(const dcb_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int dcb_create(const dcb_config* cfg, dcb_engine** out) {
+  if (!cfg || !out) return fail(nullptr, DCB_ERR_INVALID, "null argument");
+  if (cfg->struct_size != (int32_t)sizeof(dcb_config))
+    return fail(nullptr, DCB_ERR_INVALID, "dcb_config size mismatch: got %d, built with %zu",
+                cfg->struct_size, sizeof(dcb_config));
+  if (cfg->hidden_size != kD || cfg->num_heads != kHeads)
+    return fail(nullptr, DCB_ERR_INVALID, "unsupported model: hidden_size=%d num_heads=%d (engine is built for %d/%d)",
+                cfg->hidden_size, cfg->num_heads, kD, kHeads);
+  if (!cfg->condense_transformer_input)
+    return fail(nullptr, DCB_ERR_INVALID, "condense_transformer_input must be true");
+  if (cfg->filter_size <= 0 || cfg->filter_size % kFFChunk || cfg->filter_size > 2048)
+    return fail(nullptr, DCB_ERR_INVALID, "filter_size must be a multiple of %d and <= 2048", kFFChunk);
+  if (cfg->max_passes <= 0 || cfg->max_length <= 0 || cfg->max_length > 256 || cfg->num_hidden_layers <= 0 ||
+      cfg->max_batch <= 0)
+    return fail(nullptr, DCB_ERR_INVALID, "bad max_passes/max_length(<=256)/num_hidden_layers/max_batch");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, DCB_ERR_CUDA, "no CUDA device available (the dcb200 engine has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, DCB_ERR_INVALID, "bad device ordinal %d", cfg->device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+    return fail(nullptr, DCB_ERR_CUDA, "device %d is not an sm_100 GPU (compute capability %d.%d)", cfg->device,
+                prop.major, prop.minor);
+
+  dcb_engine* e = new dcb_engine();
+  e->cfg = *cfg;
+  e->num_sms = prop.multiProcessorCount;
+  e->L = cfg->max_length;
+  e->R = 4 * cfg->max_passes + (cfg->use_ccs_bq ? 6 : 5);  // data_providers.py:61-78
+  e->E = cfg->max_passes * (cfg->per_base_hidden_size + cfg->pw_hidden_size + cfg->ip_hidden_size +
+                            cfg->strand_hidden_size) +
+         cfg->per_base_hidden_size + (cfg->use_ccs_bq ? cfg->ccs_bq_hidden_size : 0) +
+         4 * cfg->sn_hidden_size;
+  e->Epad = (e->E + 15) / 16 * 16;
+  e->echunks = e->Epad / 8;
+  int ct = cfg->chunk_tiles;
+  if (const char* env = getenv("DCB_CHUNK_TILES")) ct = atoi(env);
+  if (ct <= 0) ct = 2 * e->num_sms;
+  const int max_tiles = (int)(((int64_t)cfg->max_batch * e->L + kTileM - 1) / kTileM);
+  e->chunk_windows = std::max(1, std::min(cfg->max_batch, ct * kTileM / e->L));
+  e->chunk_tiles = std::min(max_tiles, (e->chunk_windows * e->L + kTileM - 1) / kTileM);
+
+  auto bail = [&](int rc) { std::string m = e->err; dcb_destroy(e); g_create_error = m; return rc; };
+#define TRY(x) do { int _rc = (x); if (_rc) return bail(_rc); } while (0)
+#define CUC(call) do { cudaError_t _s = (call); if (_s != cudaSuccess) { fail(e, DCB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_s)); return bail(DCB_ERR_CUDA); } } while (0)
+  CUC(cudaSetDevice(cfg->device));
+  CUC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CUC(cudaEventCreate(&e->ev0));
+  CUC(cudaEventCreate(&e->ev1));
+  CUC(kernels_init());
+  const size_t T = e->chunk_tiles;
+  TRY(dev_alloc(e, &e->d_rows, (size_t)e->chunk_windows * e->R * e->L));
+  TRY(dev_alloc(e, &e->d_embqkv, T * kTileM * (size_t)std::max(e->Epad, kQKVN)));
+  TRY(dev_alloc(e, &e->d_x, T * x_image_elems()));
+  TRY(dev_alloc(e, &e->d_xb, T * act_image_elems(kDP)));
+  TRY(dev_alloc(e, &e->d_att, T * act_image_elems(kDP)));
+  const size_t mtok = (size_t)cfg->max_batch * e->L;
+  TRY(dev_alloc(e, &e->d_bases, mtok));
+  TRY(dev_alloc(e, &e->d_quals, mtok));
+  TRY(dev_alloc(e, &e->d_status, 1));
+#undef TRY
+#undef CUC
+  *out = e;
+  return DCB_OK;
+}
+
+void dcb_destroy(dcb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (void* p : e->owned) cudaFree(p);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
+  if (!e || !tensors) return fail(e, DCB_ERR_INVALID, "null argument");
+  CU(e, cudaSetDevice(e->cfg.device));
+  const dcb_config& c = e->cfg;
+  TensorMap tm;
+  tm.e = e;
+  for (int i = 0; i < n; ++i)
+    if (tensors[i].name) tm.m[tensors[i].name] = &tensors[i];
+  int rc = DCB_OK;
+
+  // ---- embedding tables (networks.py:375-421), pre-scaled by sqrt(width), row 0 zeroed
+  //      (ModifiedOnDeviceEmbedding, networks.py:42-63)
+  struct Tab { const char* layer; int vocab, width; int off; const float* data; };
+  std::vector<Tab> tabs = {
+      {"bases_embedding_layer", kVocab, c.per_base_hidden_size, 0, nullptr},
+      {"pw_embedding_layer", c.pw_max + 1, c.pw_hidden_size, 0, nullptr},
+      {"ip_embedding_layer", c.ip_max + 1, c.ip_hidden_size, 0, nullptr},
+      {"strand_embedding_layer", c.strand_max + 1, c.strand_hidden_size, 0, nullptr},
+      {"ccs_base_quality_scores_embedding_layer", c.ccs_bq_max, c.ccs_bq_hidden_size, 0, nullptr},
+      {"sn_embedding_layer", c.sn_max + 1, c.sn_hidden_size, 0, nullptr},
+  };
+  std::vector<__nv_bfloat16> blob;
+  for (size_t t = 0; t < tabs.size(); ++t) {
+    if (t == 4 && !c.use_ccs_bq) continue;
+    Tab& tb = tabs[t];
+    tb.data = tm.get(std::string("model/") + tb.layer + "/embeddings", {tb.vocab, tb.width}, &rc);
+    if (rc) return rc;
+    tb.off = (int)blob.size();
+    const float scale = sqrtf((float)tb.width);
+    for (int v = 0; v < tb.vocab; ++v)
+      for (int j = 0; j < tb.width; ++j)
+        blob.push_back(__float2bfloat16(v == 0 ? 0.f : tb.data[v * tb.width + j] * scale));
+  }
+  // ---- per-column gather descriptors in concat order (networks.py:457-506)
+  std::vector<EmbedCol> cols(e->Epad);
+  for (auto& cc : cols) { cc = EmbedCol{}; cc.src_row = -1; }
+  {
+    const int P = c.max_passes;
+    int eoff = 0;
+    auto add_rows = [&](int tab, int row0, int nrows, float clip, int shift) {
+      for (int r = 0; r < nrows; ++r)
+        for (int j = 0; j < tabs[tab].width; ++j) {
+          EmbedCol& cc = cols[eoff++];
+          cc.src_row = (int16_t)(row0 + r);
+          cc.width = (int16_t)tabs[tab].width;
+          cc.col = (int16_t)j;
+          cc.shift = (int16_t)shift;
+          cc.table_off = tabs[tab].off;
+          cc.vocab = tabs[tab].vocab;
+          cc.clip_hi = clip;
+        }
+    };
+    add_rows(0, 0, P, 0.f, 0);                                  // bases
+    add_rows(1, P, P, (float)c.pw_max, 0);                      // pw   (clip: data_providers.py:151-154)
+    add_rows(2, 2 * P, P, (float)c.ip_max, 0);                  // ip   (:155-158)
+    add_rows(3, 3 * P, P, 0.f, 0);                              // strand
+    add_rows(0, 4 * P, 1, 0.f, 0);                              // ccs shares the bases table (networks.py:485-489)
+    int next = 4 * P + 1;
+    if (c.use_ccs_bq) { add_rows(4, next, 1, 0.f, 1); ++next; }  // +1 shift (networks.py:495)
+    add_rows(5, next, 4, (float)c.sn_max, 0);                   // sn   (:159-162)
+    if (eoff != e->E) return fail(e, DCB_ERR_INVALID, "internal: embedding width %d != %d", eoff, e->E);
+  }
+  if ((rc = upload(e, &e->d_tables, blob))) return rc;
+  if ((rc = upload(e, &e->d_cols, cols))) return rc;
+
+  // ---- condenser (networks.py:426-434): B image [Epad/8][288][8]
+  {
+    const float* wc = tm.get("model/transformer_input_condenser/kernel", {e->E, kD}, &rc);
+    if (rc) return rc;
+    const int E = e->E;
+    auto img = pack_b(e->Epad, kDP, [&](int k, int nn) { return (k < E && nn < kD) ? wc[(size_t)k * kD + nn] : 0.f; });
+    if ((rc = upload(e, &e->d_wc, img))) return rc;
+  }
+  // ---- positional encoding table [L][288] (tf-models RelativePositionEmbedding; networks.py:301-323)
+  {
+    std::vector<float> pe((size_t)e->L * kDP, 0.f);
+    if (c.add_pos_encoding) {
+      const int nt = kD / 2;
+      const float inc = (float)(log(1e4 / 1.0) / (double)(nt - 1));
+      for (int l = 0; l < e->L; ++l)
+        for (int k = 0; k < nt; ++k) {
+          const float inv = expf((float)k * -inc);
+          const float sc = (float)l * inv;
+          pe[(size_t)l * kDP + k] = sinf(sc);
+          pe[(size_t)l * kDP + nt + k] = cosf(sc);
+        }
+    }
+    if ((rc = upload(e, &e->d_pe, pe))) return rc;
+  }
+  // ---- encoder layers
+  const int ff = c.filter_size;
+  e->layers.assign(c.num_hidden_layers, LayerDev());
+  for (int n_ = 0; n_ < c.num_hidden_layers; ++n_) {
+    LayerDev& ld = e->layers[n_];
+    char pre[128];
+    snprintf(pre, sizeof pre, "model/encoder_stack/layers/%d", n_);
+    const std::string P0 = std::string(pre) + "/0", P1 = std::string(pre) + "/1";
+    float alpha0 = 1.f, alpha1 = 1.f;
+    if (c.rezero) {
+      const float* a0 = tm.get(P0 + "/alpha", std::initializer_list<int64_t>{}, &rc); if (rc) return rc;
+      const float* a1 = tm.get(P1 + "/alpha", std::initializer_list<int64_t>{}, &rc); if (rc) return rc;
+      alpha0 = *a0; alpha1 = *a1;
+    } else {
+      for (int s = 0; s < 2; ++s) {
+        const std::string P = s ? P1 : P0;
+        const float* g = tm.get(P + "/layer_norm/gamma", {kD}, &rc); if (rc) return rc;
+        const float* b = tm.get(P + "/layer_norm/beta", {kD}, &rc); if (rc) return rc;
+        if ((rc = upload(e, &ld.ln_g[s], pad288(g)))) return rc;
+        if ((rc = upload(e, &ld.ln_b[s], pad288(b)))) return rc;
+      }
+    }
+    const float* wq = tm.get(P0 + "/layer/query_dense_layer/kernel", {kD, kHeads, kDH}, &rc); if (rc) return rc;
+    const float* wk = tm.get(P0 + "/layer/key_dense_layer/kernel", {kD, kHeads, kDH}, &rc); if (rc) return rc;
+    const float* wv = tm.get(P0 + "/layer/value_dense_layer/kernel", {kD, kHeads, kDH}, &rc); if (rc) return rc;
+    const float* wo = tm.get(P0 + "/layer/output_dense_layer/kernel", {kHeads, kDH, kD}, &rc); if (rc) return rc;
+    const float qscale = 1.0f / sqrtf((float)kDH);  // query *= depth**-0.5 (attention_layer.py:196-197)
+    {
+      // two n-groups of 432 columns: [q_h0 q_h1 k_h0 | k_h1 v_h0 v_h1], each slot 144 wide (140 + 4 zero)
+      std::vector<__nv_bfloat16> img;
+      for (int grp = 0; grp < 2; ++grp) {
+        auto part = pack_b(kDP, 3 * kNC, [&](int k, int nn) {
+          const int colg = grp * 3 * kNC + nn;
+          const int slot = colg / kDHP, dd = colg % kDHP;
+          if (k >= kD || dd >= kDH) return 0.f;
+          const int proj = slot / kHeads, head = slot % kHeads;
+          const float* w = proj == 0 ? wq : (proj == 1 ? wk : wv);
+          const float v = w[((size_t)k * kHeads + head) * kDH + dd];
+          return proj == 0 ? v * qscale : v;
+        });
+        img.insert(img.end(), part.begin(), part.end());
+      }
+      if ((rc = upload(e, &ld.wqkv, img))) return rc;
+    }
+    {
+      // out-proj: K index = head*144 + dd, N = e; ReZero alpha folded in (encoder_stack.py:88-90)
+      auto img = pack_b(kDP, kDP, [&](int k, int nn) {
+        const int head = k / kDHP, dd = k % kDHP;
+        if (dd >= kDH || nn >= kD) return 0.f;
+        return wo[((size_t)head * kDH + dd) * kD + nn] * alpha0;
+      });
+      if ((rc = upload(e, &ld.wo, img))) return rc;
+    }
+    const float* w1 = tm.get(P1 + "/layer/filter_dense_layer/kernel", {kD, ff}, &rc); if (rc) return rc;
+    const float* b1 = tm.get(P1 + "/layer/filter_dense_layer/bias", {ff}, &rc); if (rc) return rc;
+    const float* w2 = tm.get(P1 + "/layer/output_dense_layer/kernel", {ff, kD}, &rc); if (rc) return rc;
+    const float* b2 = tm.get(P1 + "/layer/output_dense_layer/bias", {kD}, &rc); if (rc) return rc;
+    {
+      std::vector<__nv_bfloat16> img;
+      img.reserve((size_t)ff * kDP * 2);
+      for (int ch = 0; ch < ff / kFFChunk; ++ch) {
+        auto p1 = pack_b(kDP, kFFChunk, [&](int k, int nn) {
+          return k < kD ? w1[(size_t)k * ff + ch * kFFChunk + nn] : 0.f;
+        });
+        auto p2 = pack_b(kFFChunk, kDP, [&](int k, int nn) {
+          return nn < kD ? w2[(size_t)(ch * kFFChunk + k) * kD + nn] * alpha1 : 0.f;
+        });
+        img.insert(img.end(), p1.begin(), p1.end());
+        img.insert(img.end(), p2.begin(), p2.end());
+      }
+      __nv_bfloat16* dptr = nullptr;
+      if ((rc = upload(e, &dptr, img))) return rc;
+      ld.wffn = reinterpret_cast<uint8_t*>(dptr);
+    }
+    if ((rc = upload(e, &ld.b1, std::vector<float>(b1, b1 + ff)))) return rc;
+    if ((rc = upload(e, &ld.b2, pad288(b2, alpha1)))) return rc;
+  }
+  // ---- head
+  {
+    const float* g = tm.get("model/encoder_stack/output_normalization/gamma", {kD}, &rc); if (rc) return rc;
+    const float* b = tm.get("model/encoder_stack/output_normalization/beta", {kD}, &rc); if (rc) return rc;
+    const float* w = tm.get("model/fc1/kernel", {kD, kVocab}, &rc); if (rc) return rc;
+    const float* bb = tm.get("model/fc1/bias", {kVocab}, &rc); if (rc) return rc;
+    if ((rc = upload(e, &e->d_fln_g, pad288(g)))) return rc;
+    if ((rc = upload(e, &e->d_fln_b, pad288(b)))) return rc;
+    if ((rc = upload(e, &e->d_wfc, std::vector<float>(w, w + kD * kVocab)))) return rc;
+    if ((rc = upload(e, &e->d_bfc, std::vector<float>(bb, bb + kVocab)))) return rc;
+  }
+  CU(e, cudaDeviceSynchronize());
+  e->weights_loaded = true;
+  return DCB_OK;
+}
+
+int dcb_set_debug(dcb_engine* e, int32_t enabled) {
+  if (!e) return DCB_ERR_INVALID;
+  e->debug = enabled != 0;
+  if (e->debug && !e->d_dbg) {
+    CU(e, cudaSetDevice(e->cfg.device));
+    const size_t stages = 1 + 2 * (size_t)e->cfg.num_hidden_layers;
+    int rc = dev_alloc(e, &e->d_dbg, stages * e->chunk_tiles * x_image_elems());
+    if (rc) return rc;
+  }
+  return DCB_OK;
+}
+
+int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, uint8_t* bases_out,
+                uint8_t* quals_out, float* probs_out, float* logits_out) {
+  if (!e) return DCB_ERR_INVALID;
+  if (!e->weights_loaded) return fail(e, DCB_ERR_STATE, "dcb_forward before dcb_load_weights");
+  if (batch < 0 || batch > e->cfg.max_batch) return fail(e, DCB_ERR_INVALID, "batch %d outside [0, max_batch=%d]", batch, e->cfg.max_batch);
+  if (batch == 0) { e->last_ms = 0.f; e->last_launches = 0; return DCB_OK; }
+  if (!rows || !bases_out || !quals_out) return fail(e, DCB_ERR_INVALID, "null rows / output buffer");
+  CU(e, cudaSetDevice(e->cfg.device));
+  const dcb_config& c = e->cfg;
+  const int L = e->L, R = e->R;
+  const size_t mtok = (size_t)c.max_batch * L;
+  if (probs_out && !e->d_probs) { int rc = dev_alloc(e, &e->d_probs, mtok * kVocab); if (rc) return rc; }
+  if (logits_out && !e->d_logits) { int rc = dev_alloc(e, &e->d_logits, mtok * kVocab); if (rc) return rc; }
+  const bool rows_dev = flags & DCB_ROWS_ON_DEVICE;
+  const bool out_dev = flags & DCB_OUT_ON_DEVICE;
+  cudaStream_t st = e->stream;
+  CU(e, cudaMemsetAsync(e->d_status, 0, sizeof(int), st));
+  CU(e, cudaEventRecord(e->ev0, st));
+  int launches = 0;
+  const size_t ximg = x_image_elems();
+  for (int w0 = 0; w0 < batch; w0 += e->chunk_windows) {
+    const int bw = std::min(e->chunk_windows, batch - w0);
+    const int M = bw * L;
+    const int T = (M + kTileM - 1) / kTileM;
+    const float* rows_chunk;
+    if (rows_dev) {
+      rows_chunk = rows + (size_t)w0 * R * L;
+    } else {
+      CU(e, cudaMemcpyAsync(e->d_rows, rows + (size_t)w0 * R * L, (size_t)bw * R * L * sizeof(float),
+                            cudaMemcpyHostToDevice, st));
+      rows_chunk = e->d_rows;
+    }
+    int stage = 0;
+    auto snap = [&]() {
+      if (e->debug) cudaMemcpyAsync(e->d_dbg + (size_t)stage * e->chunk_tiles * ximg, e->d_x, (size_t)T * ximg * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      ++stage;
+    };
+    launch_embed(rows_chunk, R, L, M, T, e->echunks, e->d_cols, e->d_tables, e->d_embqkv, e->d_status, st);
+    ++launches;
+    {
+      RowEpi epi{};
+      epi.x = e->d_x; epi.xb = e->d_xb; epi.bias = nullptr;
+      epi.pe = c.add_pos_encoding ? e->d_pe : nullptr;
+      epi.ln_g = c.rezero ? nullptr : e->layers[0].ln_g[0];
+      epi.ln_b = c.rezero ? nullptr : e->layers[0].ln_b[0];
+      epi.has_xold = 0; epi.L = L;
+      launch_gemm_row(e->d_embqkv, e->d_wc, e->Epad / 16, T, epi, st);
+      ++launches;
+      snap();
+    }
+    for (int n_ = 0; n_ < c.num_hidden_layers; ++n_) {
+      const LayerDev& ld = e->layers[n_];
+      const bool last = n_ + 1 == c.num_hidden_layers;
+      launch_gemm_qkv(e->d_xb, ld.wqkv, T, e->d_embqkv, st);
+      launch_attention(e->d_embqkv, e->d_att, L, c.attn_win_size, bw, st);
+      RowEpi ea{};
+      ea.x = e->d_x; ea.xb = e->d_xb; ea.bias = nullptr; ea.pe = nullptr;
+      ea.ln_g = c.rezero ? nullptr : ld.ln_g[1];
+      ea.ln_b = c.rezero ? nullptr : ld.ln_b[1];
+      ea.has_xold = 1; ea.L = L;
+      launch_gemm_row(e->d_att, ld.wo, kDP / 16, T, ea, st);
+      snap();
+      RowEpi ef{};
+      ef.x = e->d_x; ef.xb = last ? nullptr : e->d_xb; ef.bias = ld.b2; ef.pe = nullptr;
+      ef.ln_g = (c.rezero || last) ? nullptr : e->layers[n_ + 1].ln_g[0];
+      ef.ln_b = (c.rezero || last) ? nullptr : e->layers[n_ + 1].ln_b[0];
+      ef.has_xold = 1; ef.L = L;
+      launch_ffn(e->d_xb, ld.wffn, ld.b1, c.filter_size, T, ef, st);
+      snap();
+      launches += 4;
+    }
+    HeadParams hp{};
+    hp.x = e->d_x; hp.ln_g = e->d_fln_g; hp.ln_b = e->d_fln_b; hp.wfc = e->d_wfc; hp.bfc = e->d_bfc;
+    const size_t t0 = (size_t)w0 * L;
+    hp.bases = (out_dev ? bases_out : e->d_bases) + t0;
+    hp.quals = (out_dev ? quals_out : e->d_quals) + t0;
+    hp.probs = probs_out ? ((out_dev ? probs_out : e->d_probs) + t0 * kVocab) : nullptr;
+    hp.logits = logits_out ? ((out_dev ? logits_out : e->d_logits) + t0 * kVocab) : nullptr;
+    hp.M = M;
+    hp.calib_enabled = c.calibration_enabled;
+    hp.calib_thr = (float)c.calibration_threshold; hp.calib_w = (float)c.calibration_w; hp.calib_b = (float)c.calibration_b;
+    hp.calib_thr64 = c.calibration_threshold; hp.calib_w64 = c.calibration_w; hp.calib_b64 = c.calibration_b;
+    hp.max_q = (float)c.max_base_quality;
+    launch_head(hp, T, st);
+    ++launches;
+    e->last_chunk_tokens = M;
+  }
+  CU(e, cudaEventRecord(e->ev1, st));
+  if (!out_dev) {
+    const size_t ntok = (size_t)batch * L;
+    CU(e, cudaMemcpyAsync(bases_out, e->d_bases, ntok, cudaMemcpyDeviceToHost, st));
+    CU(e, cudaMemcpyAsync(quals_out, e->d_quals, ntok, cudaMemcpyDeviceToHost, st));
+    if (probs_out) CU(e, cudaMemcpyAsync(probs_out, e->d_probs, ntok * kVocab * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (logits_out) CU(e, cudaMemcpyAsync(logits_out, e->d_logits, ntok * kVocab * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  int status = 0;
+  CU(e, cudaMemcpyAsync(&status, e->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(e, cudaStreamSynchronize(st));
+  CU(e, cudaGetLastError());
+  CU(e, cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+  e->last_launches = launches;
+  if (status & 1) return fail(e, DCB_ERR_INPUT_RANGE, "embedding id out of range in the input rows (clamped)");
+  return DCB_OK;
+}
+
+int dcb_last_forward_ms(dcb_engine* e, float* ms) {
+  if (!e || !ms) return DCB_ERR_INVALID;
+  *ms = e->last_ms;
+  return DCB_OK;
+}
+
+int dcb_last_forward_launches(dcb_engine* e, int32_t* n) {
+  if (!e || !n) return DCB_ERR_INVALID;
+  *n = e->last_launches;
+  return DCB_OK;
+}
+
+int dcb_debug_residual(dcb_engine* e, int32_t stage, float* out, int64_t out_elems) {
+  if (!e || !out) return DCB_ERR_INVALID;
+  if (!e->debug || !e->d_dbg) return fail(e, DCB_ERR_STATE, "debug capture not enabled");
+  const int stages = 1 + 2 * e->cfg.num_hidden_layers;
+  if (stage < 0 || stage >= stages) return fail(e, DCB_ERR_INVALID, "stage %d outside [0,%d)", stage, stages);
+  const int M = e->last_chunk_tokens;
+  if (out_elems < (int64_t)M * kD) return fail(e, DCB_ERR_INVALID, "output too small: need %lld", (long long)M * kD);
+  CU(e, cudaSetDevice(e->cfg.device));
+  const int T = (M + kTileM - 1) / kTileM;
+  std::vector<float> img((size_t)T * x_image_elems());
+  CU(e, cudaMemcpy(img.data(), e->d_dbg + (size_t)stage * e->chunk_tiles * x_image_elems(), img.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  for (int t = 0; t < M; ++t) {
+    const int tile = t / kTileM, r = t % kTileM;
+    for (int col = 0; col < kD; ++col)
+      out[(size_t)t * kD + col] = img[(((size_t)tile * kXChunks + col / 4) * kTileM + r) * 4 + col % 4];
+  }
+  return DCB_OK;
+}
+
+int dcb_alloc_host(size_t bytes, void** out) {
+  if (!out) return DCB_ERR_INVALID;
+  return cudaMallocHost(out, bytes) == cudaSuccess ? DCB_OK : DCB_ERR_CUDA;
+}
+int dcb_free_host(void* p) { return cudaFreeHost(p) == cudaSuccess ? DCB_OK : DCB_ERR_CUDA; }
+
+int dcb_alloc_device(dcb_engine* e, size_t bytes, void** out) {
+  if (!e || !out) return DCB_ERR_INVALID;
+  CU(e, cudaSetDevice(e->cfg.device));
+  CU(e, cudaMalloc(out, bytes));
+  return DCB_OK;
+}
+int dcb_free_device(dcb_engine* e, void* p) {
+  if (!e) return DCB_ERR_INVALID;
+  CU(e, cudaSetDevice(e->cfg.device));
+  CU(e, cudaFree(p));
+  return DCB_OK;
+}
+int dcb_memcpy_h2d(dcb_engine* e, void* dst, const void* src, size_t bytes) {
+  if (!e) return DCB_ERR_INVALID;
+  CU(e, cudaSetDevice(e->cfg.device));
+  CU(e, cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return DCB_OK;
+}
+int dcb_memcpy_d2h(dcb_engine* e, void* dst, const void* src, size_t bytes) {
+  if (!e) return DCB_ERR_INVALID;
+  CU(e, cudaSetDevice(e->cfg.device));
+  CU(e, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return DCB_OK;
+}
+int dcb_synchronize(dcb_engine* e) {
+  if (!e) return DCB_ERR_INVALID;
+  CU(e, cudaSetDevice(e->cfg.device));
+  CU(e, cudaDeviceSynchronize());
+  return DCB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,872 @@
+// dcb200 device kernels (sm_100a).
+//
+//   embed_rows_kernel   rows f32 [B,R,L] -> concatenated embeddings, bf16 operand image
+//                       (format_rows clip + OnDeviceEmbedding gathers + concat + cast;
+//                        data_providers.py:151-162, networks.py:42-63,457-507)
+//   gemm_kernel         persistent, warp-specialised tcgen05 GEMM: bulk-copy (TMA) producer
+//                       warp, single-thread UMMA issuer, 4 epilogue warps reading TMEM.
+//                       Used for the condenser (+pos-enc), fused QKV, attention out-proj.
+//   band_attention_kernel  banded multi-head softmax attention (attention_layer.py:198-214)
+//   ffn_kernel          fused FFN: relu(x W1 + b1) W2 + b2 with the [128 x 2048] hidden
+//                       activation living only in TMEM/SMEM (ffn_layer.py:83-86)
+//   head_kernel         final LayerNorm -> fc1 -> softmax -> argmax -> Phred -> ASCII
+//                       (encoder_stack.py:197, networks.py:342,238, quick_inference.py:377-414)
+#include "kernels.h"
+
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "sm100.cuh"
+
+namespace dcb {
+
+// =====================================================================================
+// embed
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+embed_rows_kernel(const float* __restrict__ rows, int R, int L, int M, int echunks,
+                  const EmbedCol* __restrict__ cols, const __nv_bfloat16* __restrict__ tables,
+                  __nv_bfloat16* __restrict__ emb, int* __restrict__ status) {
+  const int tile = blockIdx.x;
+  const int total = echunks * kTileM;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int kc = idx / kTileM;
+    const int r = idx % kTileM;
+    const int tok = tile * kTileM + r;
+    uint32_t packed[4] = {0u, 0u, 0u, 0u};
+    if (tok < M) {
+      const int b = tok / L;
+      const int l = tok - b * L;
+      const float* win = rows + (size_t)b * R * L + l;
+      __nv_bfloat16 vals[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const EmbedCol c = cols[kc * 8 + j];
+        __nv_bfloat16 v = __float2bfloat16(0.f);
+        if (c.src_row >= 0) {
+          float f = __ldg(win + (size_t)c.src_row * L);
+          if (c.clip_hi > 0.f) f = fminf(fmaxf(f, 0.f), c.clip_hi);
+          f += (float)c.shift;
+          int id = (int)f;  // truncation toward zero == tf.cast(float32 -> int32)
+          if (id < 0 || id >= c.vocab) {
+            atomicOr(status, 1);  // TF's CPU gather raises here; flag and clamp
+            id = id < 0 ? 0 : c.vocab - 1;
+          }
+          v = tables[c.table_off + id * c.width + c.col];
+        }
+        vals[j] = v;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        packed[j] = (uint32_t)__bfloat16_as_ushort(vals[2 * j]) |
+                    ((uint32_t)__bfloat16_as_ushort(vals[2 * j + 1]) << 16);
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(emb + ((size_t)tile * echunks + kc) * kTileM * 8) + r;
+    *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  }
+}
+
+// =====================================================================================
+// row epilogue shared by the d-wide GEMMs (thread == token row)
+// =====================================================================================
+// acc is read from TMEM columns [tmem_row_base, +288) of this thread's lane.
+// Returns after the last TMEM read has completed (caller then releases the accumulator).
+template <bool kSecondPassOnly>
+__device__ __forceinline__ void row_epilogue_pass2(const RowEpi& e, int tile, int r, float mean,
+                                                   float rstd) {
+  // LayerNorm normalisation pass: re-read x_new (this thread's own writes) from global.
+  const float4* xrow = reinterpret_cast<const float4*>(e.x + (size_t)tile * x_image_elems()) + r;
+  uint4* xbrow = reinterpret_cast<uint4*>(e.xb + (size_t)tile * act_image_elems(kDP)) + r;
+#pragma unroll 1
+  for (int cb = 0; cb < kDP / 8; ++cb) {
+    float v[8];
+    const float4 a = xrow[(size_t)(cb * 2) * kTileM];
+    const float4 b = xrow[(size_t)(cb * 2 + 1) * kTileM];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = cb * 8 + j;
+      v[j] = col < kD ? (v[j] - mean) * rstd * __ldg(e.ln_g + col) + __ldg(e.ln_b + col) : 0.f;
+    }
+    xbrow[(size_t)cb * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+struct RowStats {
+  float mean, rstd;
+};
+
+__device__ __forceinline__ RowStats row_epilogue_pass1(const RowEpi& e, uint32_t tmem_row_base,
+                                                       int tile, int r) {
+  const int tok = tile * kTileM + r;
+  const int l = tok % e.L;
+  float4* xrow = reinterpret_cast<float4*>(e.x + (size_t)tile * x_image_elems()) + r;
+  uint4* xbrow = e.xb ? reinterpret_cast<uint4*>(e.xb + (size_t)tile * act_image_elems(kDP)) + r
+                      : nullptr;
+  const bool ln = e.ln_g != nullptr;
+  float s1 = 0.f, s2 = 0.f, shift = 0.f;
+#pragma unroll 1
+  for (int cb = 0; cb < kDP / 16; ++cb) {
+    uint32_t acc[16];
+    tmem_ld16(tmem_row_base + cb * 16, acc);
+    float v[16];
+    if (e.has_xold) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 t = xrow[(size_t)(cb * 4 + i) * kTileM];
+        v[4 * i + 0] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int col = cb * 16 + i;
+      float t = v[i] + __uint_as_float(acc[i]);
+      if (e.bias) t += __ldg(e.bias + col);
+      if (e.pe) t += __ldg(e.pe + (size_t)l * kDP + col);
+      v[i] = col < kD ? t : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      xrow[(size_t)(cb * 4 + i) * kTileM] =
+          make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    if (ln) {
+      if (cb == 0) shift = v[0];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float dlt = (cb * 16 + i < kD) ? v[i] - shift : 0.f;
+        s1 += dlt;
+        s2 += dlt * dlt;
+      }
+    } else if (xbrow) {
+      xbrow[(size_t)(cb * 2) * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                    pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      xbrow[(size_t)(cb * 2 + 1) * kTileM] =
+          make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                     pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+    }
+  }
+  RowStats st;
+  const float m1 = s1 * (1.f / kD);
+  const float var = fmaxf(s2 * (1.f / kD) - m1 * m1, 0.f);
+  st.mean = shift + m1;
+  st.rstd = rsqrtf(var + 1e-6f);
+  return st;
+}
+
+// =====================================================================================
+// generic persistent tcgen05 GEMM
+// =====================================================================================
+// D[128 x (NCH*144)] = A[128 x K] * B^T, A image [tile][K/8][128][8], B image per n-group
+// [K/8][NCH*144][8].  One work item = (tile, n-group).
+//
+// EPI_QKV : store bf16 into the qkv operand image (column offset group*NCH*144)
+// EPI_ROW : row epilogue (residual / bias / pos-enc / LayerNorm), NCH must be 2
+enum { EPI_QKV = 0, EPI_ROW = 1 };
+
+template <int NCH>
+struct GemmCfg {
+  static constexpr int kNItem = NCH * kNC;
+  static constexpr int kSK = 2;                                  // k-steps per stage
+  static constexpr int kABytesPerK = 2 * kTileM * 16;            // 4096
+  static constexpr int kBBytesPerK = 2 * kNItem * 16;
+  static constexpr int kStageBytes = kSK * (kABytesPerK + kBBytesPerK);
+  static constexpr int kStages = 4;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+};
+
+template <int NCH, int EPI>
+__global__ void __launch_bounds__(192, 1)
+gemm_kernel(const __nv_bfloat16* __restrict__ a_img, const __nv_bfloat16* __restrict__ b_img,
+            int ksteps, int ntiles, int ngroups, __nv_bfloat16* __restrict__ out_img,
+            int out_chunks, RowEpi epi) {
+  using Cfg = GemmCfg<NCH>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;                      // [kStages]
+  uint64_t* empty = bars + Cfg::kStages;      // [kStages]
+  uint64_t* acc_full = bars + 2 * Cfg::kStages;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int nitems = ntiles * ngroups;
+  const int kstages = (ksteps + Cfg::kSK - 1) / Cfg::kSK;
+  const size_t a_tile_bytes = (size_t)ksteps * Cfg::kABytesPerK;
+  const size_t b_group_bytes = (size_t)ksteps * Cfg::kBBytesPerK;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- producer
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int tile = item / ngroups, grp = item % ngroups;
+        const uint8_t* a_src = reinterpret_cast<const uint8_t*>(a_img) + tile * a_tile_bytes;
+        const uint8_t* b_src = reinterpret_cast<const uint8_t*>(b_img) + grp * b_group_bytes;
+        for (int s = 0; s < kstages; ++s) {
+          const int kh = min(Cfg::kSK, ksteps - s * Cfg::kSK);
+          mbar_wait(&empty[slot], phase ^ 1);
+          uint8_t* sa = stage_base + slot * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kSK * Cfg::kABytesPerK;
+          mbar_arrive_expect_tx(&full[slot], kh * (Cfg::kABytesPerK + Cfg::kBBytesPerK));
+          bulk_g2s(sa, a_src + (size_t)s * Cfg::kSK * Cfg::kABytesPerK, kh * Cfg::kABytesPerK,
+                   &full[slot]);
+          bulk_g2s(sb, b_src + (size_t)s * Cfg::kSK * Cfg::kBBytesPerK, kh * Cfg::kBBytesPerK,
+                   &full[slot]);
+          if (++slot == Cfg::kStages) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, kNC);
+      uint32_t slot = 0, phase = 0, it = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+        mbar_wait(acc_empty, (it & 1) ^ 1);
+        tc_fence_after();
+        for (int s = 0; s < kstages; ++s) {
+          const int kh = min(Cfg::kSK, ksteps - s * Cfg::kSK);
+          mbar_wait(&full[slot], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + slot * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kSK * Cfg::kABytesPerK;
+          for (int kk = 0; kk < kh; ++kk) {
+            const uint64_t adesc = make_kc16_desc(sa + kk * Cfg::kABytesPerK, kTileM * 16, 128);
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+              const uint64_t bdesc = make_kc16_desc(sb + kk * Cfg::kBBytesPerK + j * kNC * 16,
+                                                    Cfg::kNItem * 16, 128);
+              umma_bf16_ss(tmem_base + j * kNC, adesc, bdesc, idesc, (s | kk) != 0);
+            }
+          }
+          umma_commit(&empty[slot]);
+          if (++slot == Cfg::kStages) { slot = 0; phase ^= 1; }
+        }
+        umma_commit(acc_full);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------- epilogue (4 warps)
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;       // token row within the tile
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+      const int tile = item / ngroups, grp = item % ngroups;
+      mbar_wait(acc_full, it & 1);
+      tc_fence_after();
+      if constexpr (EPI == EPI_QKV) {
+        uint4* orow = reinterpret_cast<uint4*>(out_img + (size_t)tile * kTileM * out_chunks * 8) + r;
+#pragma unroll 1
+        for (int cb = 0; cb < Cfg::kNItem / 16; ++cb) {
+          uint32_t acc[16];
+          tmem_ld16(tmem_row + cb * 16, acc);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
+          const int kc = (grp * Cfg::kNItem + cb * 16) / 8;
+          orow[(size_t)kc * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                 pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          orow[(size_t)(kc + 1) * kTileM] =
+              make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                         pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty);
+      } else {
+        static_assert(EPI != EPI_ROW || NCH == 2, "row epilogue needs the full 288-wide row");
+        const RowStats st = row_epilogue_pass1(epi, tmem_row, tile, r);
+        tc_fence_before();
+        mbar_arrive(acc_empty);   // accumulator free: next item's MMAs overlap the LN pass
+        if (epi.ln_g && epi.xb) row_epilogue_pass2<false>(epi, tile, r, st.mean, st.rstd);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// =====================================================================================
+// fused FFN
+// =====================================================================================
+struct FfnCfg {
+  static constexpr int kABytes = (kDP / 8) * kTileM * 16;            // 73728: x operand tile
+  static constexpr int kHBytes = (kFFChunk / 8) * kTileM * 16;       // 32768: one hidden chunk
+  static constexpr int kSlotBytes = 12288;
+  static constexpr int kSlots = 6;
+  static constexpr int kW1StageK = 3;                                // k-steps per W1 stage
+  static constexpr int kW1StageBytes = kW1StageK * 2 * kFFChunk * 16;  // 12288
+  static constexpr int kW1Stages = (kDP / 16) / kW1StageK;           // 6
+  static constexpr int kW2StageBytes = 2 * kDP * 16;                 // 9216 (one k-step)
+  static constexpr int kW2Stages = kFFChunk / 16;                    // 8
+  static constexpr int kW1ChunkBytes = kW1Stages * kW1StageBytes;    // 73728
+  static constexpr int kW2ChunkBytes = kW2Stages * kW2StageBytes;    // 73728
+  static constexpr int kTmemY = 0;
+  static constexpr int kTmemH = kDP;                                 // 288
+  static constexpr int kTmemCols = 512;
+  static constexpr int kMaxFF = 2048;
+  static constexpr int kOffA = 0;
+  static constexpr int kOffH = kABytes;
+  static constexpr int kOffRing = kOffH + 2 * kHBytes;
+  static constexpr int kOffB1 = kOffRing + kSlots * kSlotBytes;
+  static constexpr int kOffBars = kOffB1 + kMaxFF * 4;
+  static constexpr int kSmemBytes = kOffBars + 256;
+};
+static_assert(FfnCfg::kSmemBytes <= 232448, "FFN shared memory budget");
+static_assert(FfnCfg::kW1StageBytes <= FfnCfg::kSlotBytes && FfnCfg::kW2StageBytes <= FfnCfg::kSlotBytes, "slot");
+
+// w_img: per ff-chunk c: [W1 chunk image 73728 B][W2 chunk image 73728 B].
+__global__ void __launch_bounds__(192, 1)
+ffn_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ w_img,
+           const float* __restrict__ b1, int ff, int ntiles, RowEpi epi) {
+  using C = FfnCfg;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem + C::kOffA;
+  uint8_t* sH = smem + C::kOffH;
+  uint8_t* sRing = smem + C::kOffRing;
+  float* sB1 = reinterpret_cast<float*>(smem + C::kOffB1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
+  uint64_t* full = bars;                   // [kSlots]
+  uint64_t* empty = bars + C::kSlots;      // [kSlots]
+  uint64_t* a_full = bars + 2 * C::kSlots;
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* h_full = a_full + 2;           // MMA -> epilogue: hidden chunk accumulator ready
+  uint64_t* h_free = a_full + 3;           // epilogue -> MMA: hidden TMEM columns drained
+  uint64_t* hs_full = a_full + 4;          // [2] epilogue -> MMA: bf16 hidden chunk in smem
+  uint64_t* hs_free = a_full + 6;          // [2] MMA -> epilogue: smem hidden chunk consumed
+  uint64_t* y_full = a_full + 8;
+  uint64_t* y_empty = a_full + 9;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 10);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nchunks = ff / kFFChunk;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::kSlots; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    mbar_init(h_full, 1);
+    mbar_init(h_free, 128);
+    mbar_init(&hs_full[0], 128);
+    mbar_init(&hs_full[1], 128);
+    mbar_init(&hs_free[0], 1);
+    mbar_init(&hs_free[1], 1);
+    mbar_init(y_full, 1);
+    mbar_init(y_empty, 128);
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < ff; i += blockDim.x) sB1[i] = b1[i];
+  if (warp == 1) tmem_alloc(tmem_holder, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- producer
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0, ti = 0;
+      auto push = [&](const uint8_t* src, uint32_t bytes) {
+        mbar_wait(&empty[slot], phase ^ 1);
+        mbar_arrive_expect_tx(&full[slot], bytes);
+        bulk_g2s(sRing + slot * C::kSlotBytes, src, bytes, &full[slot]);
+        if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+      };
+      auto push_w1 = [&](int c) {
+        const uint8_t* src = w_img + (size_t)c * (C::kW1ChunkBytes + C::kW2ChunkBytes);
+        for (int s = 0; s < C::kW1Stages; ++s) push(src + s * C::kW1StageBytes, C::kW1StageBytes);
+      };
+      auto push_w2 = [&](int c) {
+        const uint8_t* src =
+            w_img + (size_t)c * (C::kW1ChunkBytes + C::kW2ChunkBytes) + C::kW1ChunkBytes;
+        for (int s = 0; s < C::kW2Stages; ++s) push(src + s * C::kW2StageBytes, C::kW2StageBytes);
+      };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+        mbar_wait(a_empty, (ti & 1) ^ 1);
+        mbar_arrive_expect_tx(a_full, C::kABytes);
+        bulk_g2s(sA, reinterpret_cast<const uint8_t*>(a_img) + (size_t)tile * C::kABytes,
+                 C::kABytes, a_full);
+        // same order as the MMA warp consumes: W1(0), then W1(c+1), W2(c) ...
+        push_w1(0);
+        for (int c = 0; c < nchunks; ++c) {
+          if (c + 1 < nchunks) push_w1(c + 1);
+          push_w2(c);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_h = make_idesc_bf16(kTileM, kFFChunk);
+      constexpr uint32_t idesc_y = make_idesc_bf16(kTileM, kNC);
+      const uint32_t a_addr = smem_u32(sA);
+      uint32_t slot = 0, phase = 0, ti = 0, n = 0;  // n: global hidden-chunk counter
+      auto gemm1 = [&](uint32_t nn) {
+        // H[128 x 128] = X[128 x 288] * W1chunk^T
+        mbar_wait(h_free, (nn & 1) ^ 1);
+        tc_fence_after();
+        for (int s = 0; s < C::kW1Stages; ++s) {
+          mbar_wait(&full[slot], phase);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(sRing + slot * C::kSlotBytes);
+#pragma unroll
+          for (int kk = 0; kk < C::kW1StageK; ++kk) {
+            const int kstep = s * C::kW1StageK + kk;
+            const uint64_t adesc = make_kc16_desc(a_addr + kstep * 4096, kTileM * 16, 128);
+            const uint64_t bdesc = make_kc16_desc(sb + kk * (2 * kFFChunk * 16), kFFChunk * 16, 128);
+            umma_bf16_ss(tmem_base + C::kTmemH, adesc, bdesc, idesc_h, kstep != 0);
+          }
+          umma_commit(&empty[slot]);
+          if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+        }
+        umma_commit(h_full);
+      };
+      auto gemm2 = [&](uint32_t nn, int c) {
+        // Y[128 x 288] += Hc[128 x 128] * W2chunk^T
+        const uint32_t b = nn & 1;
+        mbar_wait(&hs_full[b], (nn >> 1) & 1);
+        tc_fence_after();
+        const uint32_t h_addr = smem_u32(sH + b * C::kHBytes);
+        for (int s = 0; s < C::kW2Stages; ++s) {
+          mbar_wait(&full[slot], phase);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(sRing + slot * C::kSlotBytes);
+          const uint64_t adesc = make_kc16_desc(h_addr + s * 4096, kTileM * 16, 128);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint64_t bdesc = make_kc16_desc(sb + j * kNC * 16, kDP * 16, 128);
+            umma_bf16_ss(tmem_base + C::kTmemY + j * kNC, adesc, bdesc, idesc_y, (c | s) != 0);
+          }
+          umma_commit(&empty[slot]);
+          if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+        }
+        umma_commit(&hs_free[b]);
+      };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+        mbar_wait(a_full, ti & 1);
+        tc_fence_after();
+        gemm1(n);
+        for (int c = 0; c < nchunks; ++c) {
+          if (c + 1 < nchunks) {
+            gemm1(n + c + 1);
+          } else {
+            umma_commit(a_empty);          // all GEMM1s of this tile issued: x tile reusable
+          }
+          if (c == 0) {
+            mbar_wait(y_empty, (ti & 1) ^ 1);  // previous tile's Y drained by the epilogue
+            tc_fence_after();
+          }
+          gemm2(n + c, c);
+        }
+        umma_commit(y_full);
+        n += nchunks;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------- epilogue (4 warps)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t ti = 0, n = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      for (int c = 0; c < nchunks; ++c, ++n) {
+        const uint32_t b = n & 1;
+        mbar_wait(h_full, n & 1);
+        tc_fence_after();
+        mbar_wait(&hs_free[b], ((n >> 1) & 1) ^ 1);
+        uint4* hrow = reinterpret_cast<uint4*>(sH + b * C::kHBytes) + r;
+        const float* bias = sB1 + c * kFFChunk;
+#pragma unroll 2
+        for (int cb = 0; cb < kFFChunk / 16; ++cb) {
+          uint32_t acc[16];
+          tmem_ld16(tmem_row + C::kTmemH + cb * 16, acc);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(acc[i]) + bias[cb * 16 + i], 0.f);
+          hrow[(size_t)(cb * 2) * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                       pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          hrow[(size_t)(cb * 2 + 1) * kTileM] =
+              make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                         pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        }
+        tc_fence_before();
+        mbar_arrive(h_free);
+        fence_proxy_async_smem();
+        mbar_arrive(&hs_full[b]);
+      }
+      mbar_wait(y_full, ti & 1);
+      tc_fence_after();
+      const RowStats st = row_epilogue_pass1(epi, tmem_row + C::kTmemY, tile, r);
+      tc_fence_before();
+      mbar_arrive(y_empty);
+      if (epi.ln_g && epi.xb) row_epilogue_pass2<false>(epi, tile, r, st.mean, st.rstd);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// =====================================================================================
+// banded attention (mma.sync m16n8k16 bf16, online softmax over 16-key tiles)
+// =====================================================================================
+// One CTA per (window, head).  K and V rows of the window are staged in shared memory
+// (row stride 152 bf16 = 304 B: conflict-free for the 32-bit K-fragment loads and for
+// ldmatrix.trans on V); Q fragments are read straight from the global operand image.
+// FLOP share of this kernel is ~1-4 % of the model, so the legacy warp-level MMA path
+// is used here on purpose ("Window/tile alignment for attention").
+constexpr int kAttStride = 152;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
+               : "=r"(r0), "=r"(r1)
+               : "r"(addr));
+}
+
+// element (token, col) of a bf16 operand image with `chunks` 8-wide chunks per row
+__device__ __forceinline__ size_t img_off(int tok, int col, int chunks) {
+  const int tile = tok / kTileM, r = tok % kTileM;
+  return (((size_t)tile * chunks + (col >> 3)) * kTileM + r) * 8 + (col & 7);
+}
+
+__global__ void __launch_bounds__(128)
+band_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ att,
+                      int L, int win, int nwindows) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int w = blockIdx.x >> 1;
+  const int head = blockIdx.x & 1;
+  if (w >= nwindows) return;
+  const int Lp = (L + 15) & ~15;  // key rows padded to a multiple of 16 (zero filled)
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sV = sK + (size_t)Lp * kAttStride;
+  constexpr int qkv_chunks = kQKVN / 8;  // 108
+  const int kcol = (2 + head) * kDHP, vcol = (4 + head) * kDHP, qcol = head * kDHP;
+  const int tok0 = w * L;
+
+  // stage K, V: 16-byte chunks, (row, chunk) -> smem[row*304 + chunk*16]
+  for (int idx = threadIdx.x; idx < Lp * (kDHP / 8) * 2; idx += blockDim.x) {
+    const int which = idx / (Lp * (kDHP / 8));
+    const int rem = idx - which * (Lp * (kDHP / 8));
+    const int ch = rem / Lp, row = rem - ch * Lp;  // row fastest: coalesced 16 B chunks
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (row < L)
+      val = *reinterpret_cast<const uint4*>(
+          qkv + img_off(tok0 + row, (which ? vcol : kcol) + ch * 8, qkv_chunks));
+    *reinterpret_cast<uint4*>((which ? sV : sK) + (size_t)row * kAttStride + ch * 8) = val;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int band = win > 0 ? win : L;  // attn_win_size None/0 => full attention
+  constexpr float kLog2e = 1.4426950408889634f;
+
+  for (int qb = warp; qb * 16 < L; qb += 4) {
+    const int i0 = qb * 16;
+    // Q fragments for 9 k-steps: rows i0+g, i0+g+8 (zero beyond L)
+    uint32_t qa[kDHP / 16][4];
+    const int r0 = i0 + g, r1 = i0 + g + 8;
+#pragma unroll
+    for (int ks = 0; ks < kDHP / 16; ++ks) {
+      const int c0 = qcol + ks * 16 + 2 * t;
+      qa[ks][0] = r0 < L ? *reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r0, c0, qkv_chunks)) : 0u;
+      qa[ks][1] = r1 < L ? *reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r1, c0, qkv_chunks)) : 0u;
+      qa[ks][2] = r0 < L ? *reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r0, c0 + 8, qkv_chunks)) : 0u;
+      qa[ks][3] = r1 < L ? *reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r1, c0 + 8, qkv_chunks)) : 0u;
+    }
+    float o[kDHP / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < kDHP / 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    int jlo = i0 - band; if (jlo < 0) jlo = 0; jlo &= ~15;
+    int jhi = i0 + 15 + band + 1; if (jhi > L) jhi = L;
+    for (int j0 = jlo; j0 < jhi; j0 += 16) {
+      // S tile 16 x 16 = two n-tiles of 8 keys
+      float s[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        const __nv_bfloat16* krow = sK + (size_t)(j0 + nt * 8 + g) * kAttStride + 2 * t;
+#pragma unroll
+        for (int ks = 0; ks < kDHP / 16; ++ks) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks * 16);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 8);
+          mma_bf16_16816(s[nt], qa[ks], b0, b1);
+        }
+      }
+      // mask: |i - j| <= band and j < L  (tf.where(mask, logits, -1e9): exp underflows to 0)
+      float tmax0 = -INFINITY, tmax1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = (e < 2) ? r0 : r1;
+          const int j = j0 + nt * 8 + 2 * t + (e & 1);
+          const int dlt = i - j;
+          const bool ok = (j < L) && (dlt <= band) && (dlt >= -band);
+          s[nt][e] = ok ? s[nt][e] : -INFINITY;
+        }
+        tmax0 = fmaxf(tmax0, fmaxf(s[nt][0], s[nt][1]));
+        tmax1 = fmaxf(tmax1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      tmax0 = fmaxf(tmax0, __shfl_xor_sync(0xffffffffu, tmax0, 1));
+      tmax0 = fmaxf(tmax0, __shfl_xor_sync(0xffffffffu, tmax0, 2));
+      tmax1 = fmaxf(tmax1, __shfl_xor_sync(0xffffffffu, tmax1, 1));
+      tmax1 = fmaxf(tmax1, __shfl_xor_sync(0xffffffffu, tmax1, 2));
+      const float mn0 = fmaxf(m0, tmax0), mn1 = fmaxf(m1, tmax1);
+      // rows with no valid key yet keep m = -inf; use 0 as the subtraction base there
+      const float base0 = mn0 == -INFINITY ? 0.f : mn0, base1 = mn1 == -INFINITY ? 0.f : mn1;
+      const float sc0 = exp2f((m0 - base0) * kLog2e), sc1 = exp2f((m1 - base1) * kLog2e);
+      m0 = mn0; m1 = mn1;
+      float ps0 = 0.f, ps1 = 0.f;
+      uint32_t pa[4];
+      {
+        float p[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          p[nt][0] = exp2f((s[nt][0] - base0) * kLog2e);
+          p[nt][1] = exp2f((s[nt][1] - base0) * kLog2e);
+          p[nt][2] = exp2f((s[nt][2] - base1) * kLog2e);
+          p[nt][3] = exp2f((s[nt][3] - base1) * kLog2e);
+          ps0 += p[nt][0] + p[nt][1];
+          ps1 += p[nt][2] + p[nt][3];
+        }
+        // C fragments of the two n-tiles form the A fragment of one 16-key k-step
+        pa[0] = pack_bf16x2(p[0][0], p[0][1]);
+        pa[1] = pack_bf16x2(p[0][2], p[0][3]);
+        pa[2] = pack_bf16x2(p[1][0], p[1][1]);
+        pa[3] = pack_bf16x2(p[1][2], p[1][3]);
+      }
+      l0 = l0 * sc0 + ps0;
+      l1 = l1 * sc1 + ps1;
+      // O = O * scale + P V
+      const uint32_t vbase = smem_u32(sV + (size_t)(j0 + (lane & 15)) * kAttStride);
+#pragma unroll
+      for (int nt = 0; nt < kDHP / 8; ++nt) {
+        o[nt][0] *= sc0; o[nt][1] *= sc0; o[nt][2] *= sc1; o[nt][3] *= sc1;
+        uint32_t b0, b1;
+        ldmatrix_x2_trans(b0, b1, vbase + nt * 16);
+        mma_bf16_16816(o[nt], pa, b0, b1);
+      }
+    }
+    // normalise (row sums live in the quad) and store bf16 to the attention operand image
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+#pragma unroll
+    for (int nt = 0; nt < kDHP / 8; ++nt) {
+      const int col = head * kDHP + nt * 8 + 2 * t;
+      if (r0 < L)
+        *reinterpret_cast<uint32_t*>(att + img_off(tok0 + r0, col, kDP / 8)) =
+            pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
+      if (r1 < L)
+        *reinterpret_cast<uint32_t*>(att + img_off(tok0 + r1, col, kDP / 8)) =
+            pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
+    }
+  }
+}
+
+// =====================================================================================
+// head: final LayerNorm -> fc1 -> softmax -> argmax / Phred / ASCII
+// =====================================================================================
+__global__ void __launch_bounds__(128)
+head_kernel(HeadParams p) {
+  __shared__ float sW[kD * kVocab];
+  __shared__ float sG[kD], sBt[kD];
+  for (int i = threadIdx.x; i < kD * kVocab; i += blockDim.x) sW[i] = p.wfc[i];
+  for (int i = threadIdx.x; i < kD; i += blockDim.x) { sG[i] = p.ln_g[i]; sBt[i] = p.ln_b[i]; }
+  __syncthreads();
+  const int tile = blockIdx.x, r = threadIdx.x;
+  const int tok = tile * kTileM + r;
+  if (tok >= p.M) return;
+  const float4* xrow = reinterpret_cast<const float4*>(p.x + (size_t)tile * x_image_elems()) + r;
+  // pass 1: mean / variance (biased, eps = 1e-6: encoder_stack.py:131-133)
+  float s1 = 0.f, s2 = 0.f;
+  const float shift = xrow[0].x;
+  for (int ch = 0; ch < kD / 4; ++ch) {
+    const float4 v = xrow[(size_t)ch * kTileM];
+    const float a = v.x - shift, b = v.y - shift, c = v.z - shift, d = v.w - shift;
+    s1 += (a + b) + (c + d);
+    s2 += (a * a + b * b) + (c * c + d * d);
+  }
+  const float m1 = s1 * (1.f / kD);
+  const float mean = shift + m1;
+  const float rstd = rsqrtf(fmaxf(s2 * (1.f / kD) - m1 * m1, 0.f) + 1e-6f);
+  // pass 2: logits = LN(x) Wfc + b (networks.py:342)
+  float lg[kVocab];
+#pragma unroll
+  for (int j = 0; j < kVocab; ++j) lg[j] = 0.f;
+  for (int ch = 0; ch < kD / 4; ++ch) {
+    const float4 v = xrow[(size_t)ch * kTileM];
+    const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = ch * 4 + i;
+      const float z = (xs[i] - mean) * rstd * sG[col] + sBt[col];
+#pragma unroll
+      for (int j = 0; j < kVocab; ++j) lg[j] = fmaf(z, sW[col * kVocab + j], lg[j]);
+    }
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kVocab; ++j) { lg[j] += p.bfc[j]; mx = fmaxf(mx, lg[j]); }
+  // softmax (networks.py:238), float32
+  float ex[kVocab], sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kVocab; ++j) { ex[j] = expf(lg[j] - mx); sum += ex[j]; }
+  float pr[kVocab], pmax = -1.f;
+  int arg = 0;
+#pragma unroll
+  for (int j = 0; j < kVocab; ++j) {
+    pr[j] = ex[j] / sum;
+    if (pr[j] > pmax) { pmax = pr[j]; arg = j; }  // first maximum wins (np.argmax)
+  }
+  // quick_inference.py:378-389
+  const float err = 1.f - pmax;
+  float qf = -10.f * log10f(err);  // err == 0 -> +inf
+  int qi;
+  if (p.calib_enabled && p.calib_thr != 0.f) {
+    // np.where branch of calibrate_quality_scores promotes to float64 (calibration_lib.py:93-99)
+    const double qd = (double)qf;
+    const bool above = qd > p.calib_thr64;
+    const double qc = qd * (above ? p.calib_w64 : 1.0) + (above ? p.calib_b64 : 0.0);
+    qi = (int)rint(fmin(qc, (double)p.max_q));
+  } else {
+    if (p.calib_enabled) qf = qf * p.calib_w + p.calib_b;    // float32 path (threshold == 0)
+    qi = (int)rintf(fminf(qf, p.max_q));                     // np.round: half to even
+  }
+  qi = qi < 0 ? 0 : qi;
+  const char vocab[kVocab] = {' ', 'A', 'T', 'C', 'G'};
+  p.bases[tok] = (uint8_t)vocab[arg];
+  p.quals[tok] = (uint8_t)(qi + 33);
+  if (p.probs) {
+#pragma unroll
+    for (int j = 0; j < kVocab; ++j) p.probs[(size_t)tok * kVocab + j] = pr[j];
+  }
+  if (p.logits) {
+#pragma unroll
+    for (int j = 0; j < kVocab; ++j) p.logits[(size_t)tok * kVocab + j] = lg[j];
+  }
+}
+
+// =====================================================================================
+// launchers
+// =====================================================================================
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+cudaError_t kernels_init() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(gemm_kernel<3, EPI_QKV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           GemmCfg<3>::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_kernel<2, EPI_ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           GemmCfg<2>::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           FfnCfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(band_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           2 * 256 * kAttStride * 2);
+  return e;
+}
+
+void launch_embed(const float* rows, int R, int L, int M, int ntiles, int echunks,
+                  const EmbedCol* cols, const __nv_bfloat16* tables, __nv_bfloat16* emb,
+                  int* status, cudaStream_t st) {
+  embed_rows_kernel<<<ntiles, 256, 0, st>>>(rows, R, L, M, echunks, cols, tables, emb, status);
+}
+
+void launch_gemm_row(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int ksteps, int ntiles,
+                     const RowEpi& epi, cudaStream_t st) {
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  gemm_kernel<2, EPI_ROW><<<grid, 192, GemmCfg<2>::kSmemBytes, st>>>(a_img, b_img, ksteps, ntiles, 1,
+                                                                     nullptr, 0, epi);
+}
+
+void launch_gemm_qkv(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int ntiles,
+                     __nv_bfloat16* qkv_img, cudaStream_t st) {
+  const int items = ntiles * 2;
+  const int grid = items < num_sms() ? items : num_sms();
+  RowEpi none{};
+  gemm_kernel<3, EPI_QKV><<<grid, 192, GemmCfg<3>::kSmemBytes, st>>>(a_img, b_img, kDP / 16, ntiles, 2,
+                                                                     qkv_img, kQKVN / 8, none);
+}
+
+void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int win, int nwindows,
+                      cudaStream_t st) {
+  const int Lp = (L + 15) & ~15;
+  const size_t smem = (size_t)2 * Lp * kAttStride * 2;
+  band_attention_kernel<<<nwindows * 2, 128, smem, st>>>(qkv, att, L, win, nwindows);
+}
+
+void launch_ffn(const __nv_bfloat16* a_img, const uint8_t* w_img, const float* b1, int ff, int ntiles,
+                const RowEpi& epi, cudaStream_t st) {
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  ffn_kernel<<<grid, 192, FfnCfg::kSmemBytes, st>>>(a_img, w_img, b1, ff, ntiles, epi);
+}
+
+void launch_head(const HeadParams& p, int ntiles, cudaStream_t st) {
+  head_kernel<<<ntiles, 128, 0, st>>>(p);
+}
+
+}  // namespace dcb

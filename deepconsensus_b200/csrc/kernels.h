@@ -1,0 +1,26 @@
+// Launchers of the dcb200 device kernels (definitions in kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace dcb {
+
+cudaError_t kernels_init();
+
+void launch_embed(const float* rows, int R, int L, int M, int ntiles, int echunks,
+                  const EmbedCol* cols, const __nv_bfloat16* tables, __nv_bfloat16* emb,
+                  int* status, cudaStream_t st);
+// D = A * B^T with the 288-wide row epilogue (condenser + pos-enc, attention out-proj).
+void launch_gemm_row(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int ksteps, int ntiles,
+                     const RowEpi& epi, cudaStream_t st);
+// fused q/k/v projection: A [tile][36][128][8] -> qkv image [tile][108][128][8]
+void launch_gemm_qkv(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int ntiles,
+                     __nv_bfloat16* qkv_img, cudaStream_t st);
+void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int win, int nwindows,
+                      cudaStream_t st);
+void launch_ffn(const __nv_bfloat16* a_img, const uint8_t* w_img, const float* b1, int ff, int ntiles,
+                const RowEpi& epi, cudaStream_t st);
+void launch_head(const HeadParams& p, int ntiles, cudaStream_t st);
+
+}  // namespace dcb

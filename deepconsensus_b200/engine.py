@@ -1,0 +1,311 @@
+"""ctypes binding of the dcb200 C-ABI (include/dcb200.h) and the model object built on it.
+
+`B200Model` stands where the reference's `tf.keras.Model` stands in
+`quick_inference.run_model_on_examples` (quick_inference.py:341-415):
+
+  * `model.predict(rows)` -> object with `.numpy()` giving softmax output [B, L, 5]
+    (the contract quick_inference.py:368-370 relies on), and
+  * `model.forward(rows)` -> base / quality characters straight from the device epilogue
+    (what quick_inference.py:377-414 computes on the host).
+
+There is no CPU fallback: if the CUDA library is missing or no sm_100 GPU is present,
+construction raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from deepconsensus_b200 import calibration as calibration_lib
+from deepconsensus_b200 import params as params_lib
+from deepconsensus_b200 import weights as weights_lib
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libdcb200.so")
+_lib = None
+
+DCB_ROWS_ON_DEVICE = 1
+DCB_OUT_ON_DEVICE = 2
+
+
+class DcbError(RuntimeError):
+  def __init__(self, code: int, message: str):
+    super().__init__("dcb200 error %d: %s" % (code, message))
+    self.code = code
+
+
+class DcbConfig(ctypes.Structure):
+  _fields_ = [
+      ("struct_size", ctypes.c_int32), ("device", ctypes.c_int32),
+      ("max_passes", ctypes.c_int32), ("max_length", ctypes.c_int32),
+      ("use_ccs_bq", ctypes.c_int32),
+      ("hidden_size", ctypes.c_int32), ("num_heads", ctypes.c_int32),
+      ("num_hidden_layers", ctypes.c_int32), ("filter_size", ctypes.c_int32),
+      ("attn_win_size", ctypes.c_int32), ("rezero", ctypes.c_int32),
+      ("add_pos_encoding", ctypes.c_int32), ("condense_transformer_input", ctypes.c_int32),
+      ("per_base_hidden_size", ctypes.c_int32), ("pw_hidden_size", ctypes.c_int32),
+      ("ip_hidden_size", ctypes.c_int32), ("strand_hidden_size", ctypes.c_int32),
+      ("ccs_bq_hidden_size", ctypes.c_int32), ("sn_hidden_size", ctypes.c_int32),
+      ("pw_max", ctypes.c_int32), ("ip_max", ctypes.c_int32), ("sn_max", ctypes.c_int32),
+      ("ccs_bq_max", ctypes.c_int32), ("strand_max", ctypes.c_int32),
+      ("max_base_quality", ctypes.c_int32), ("calibration_enabled", ctypes.c_int32),
+      ("calibration_threshold", ctypes.c_double), ("calibration_w", ctypes.c_double),
+      ("calibration_b", ctypes.c_double),
+      ("max_batch", ctypes.c_int32), ("chunk_tiles", ctypes.c_int32),
+      ("reserved", ctypes.c_int32 * 6),
+  ]
+
+
+class DcbTensor(ctypes.Structure):
+  _fields_ = [("name", ctypes.c_char_p), ("data", ctypes.POINTER(ctypes.c_float)),
+              ("ndim", ctypes.c_int32), ("shape", ctypes.c_int64 * 4)]
+
+
+# Every symbol include/dcb200.h declares; tests check the built library exports all of them.
+ABI_SYMBOLS = (
+    "dcb_create", "dcb_load_weights", "dcb_forward", "dcb_last_forward_ms",
+    "dcb_last_forward_launches", "dcb_set_debug", "dcb_debug_residual", "dcb_alloc_host",
+    "dcb_free_host", "dcb_alloc_device", "dcb_free_device", "dcb_memcpy_h2d", "dcb_memcpy_d2h",
+    "dcb_synchronize", "dcb_last_error", "dcb_version", "dcb_destroy",
+)
+
+
+def library_path() -> str:
+  return _LIB_PATH
+
+
+def load_library() -> ctypes.CDLL:
+  """Loads libdcb200.so (built in-tree by `__graft_entry__.build()` / csrc/build.sh)."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(_LIB_PATH):
+    raise FileNotFoundError(
+        "%s not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
+        "g.build()'); the dcb200 engine has no CPU fallback" % _LIB_PATH)
+  lib = ctypes.CDLL(_LIB_PATH)
+  vp, i32, u32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint32
+  lib.dcb_create.argtypes = [ctypes.POINTER(DcbConfig), ctypes.POINTER(vp)]
+  lib.dcb_load_weights.argtypes = [vp, ctypes.POINTER(DcbTensor), i32]
+  lib.dcb_forward.argtypes = [vp, vp, i32, u32, vp, vp, vp, vp]
+  lib.dcb_last_forward_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+  lib.dcb_last_forward_launches.argtypes = [vp, ctypes.POINTER(i32)]
+  lib.dcb_set_debug.argtypes = [vp, i32]
+  lib.dcb_debug_residual.argtypes = [vp, i32, vp, ctypes.c_int64]
+  lib.dcb_alloc_host.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+  lib.dcb_free_host.argtypes = [vp]
+  lib.dcb_alloc_device.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp)]
+  lib.dcb_free_device.argtypes = [vp, vp]
+  lib.dcb_memcpy_h2d.argtypes = [vp, vp, vp, ctypes.c_size_t]
+  lib.dcb_memcpy_d2h.argtypes = [vp, vp, vp, ctypes.c_size_t]
+  lib.dcb_synchronize.argtypes = [vp]
+  lib.dcb_last_error.argtypes = [vp]
+  lib.dcb_last_error.restype = ctypes.c_char_p
+  lib.dcb_version.restype = ctypes.c_char_p
+  lib.dcb_destroy.argtypes = [vp]
+  lib.dcb_destroy.restype = None
+  _lib = lib
+  return lib
+
+
+def make_config(params: params_lib.Params, max_batch: int, device: int = 0,
+                max_base_quality: int = 93,
+                calibration: Optional[calibration_lib.QualityCalibrationValues] = None,
+                chunk_tiles: int = 0) -> DcbConfig:
+  """params (params.json surface) + InferenceOptions fields -> dcb_config."""
+  c = DcbConfig()
+  c.struct_size = ctypes.sizeof(DcbConfig)
+  c.device = device
+  c.max_passes, c.max_length = int(params.max_passes), int(params.max_length)
+  c.use_ccs_bq = int(bool(params.use_ccs_bq))
+  c.hidden_size, c.num_heads = int(params.hidden_size), int(params.num_heads)
+  c.num_hidden_layers, c.filter_size = int(params.num_hidden_layers), int(params.filter_size)
+  c.attn_win_size = int(params.attn_win_size or 0)
+  c.rezero = int(bool(params.rezero))
+  c.add_pos_encoding = int(bool(params.add_pos_encoding))
+  c.condense_transformer_input = int(bool(params.condense_transformer_input))
+  for f in ("per_base", "pw", "ip", "strand", "ccs_bq", "sn"):
+    setattr(c, f + "_hidden_size", int(params[f + "_hidden_size"]))
+  c.pw_max, c.ip_max, c.sn_max = int(params.PW_MAX), int(params.IP_MAX), int(params.SN_MAX)
+  c.ccs_bq_max, c.strand_max = int(params.CCS_BQ_MAX), int(params.STRAND_MAX)
+  c.max_base_quality = int(max_base_quality)
+  if calibration is not None and calibration.enabled:
+    c.calibration_enabled = 1
+    c.calibration_threshold = float(calibration.threshold)
+    c.calibration_w, c.calibration_b = float(calibration.w), float(calibration.b)
+  c.max_batch = int(max_batch)
+  c.chunk_tiles = int(chunk_tiles)
+  for need in ("use_bases", "use_pw", "use_ip", "use_strand", "use_ccs", "use_sn"):
+    if not params.get(need, True):
+      raise DcbError(-1, "params.%s=False is not supported by the dcb200 engine" % need)
+  return c
+
+
+class _Prediction:
+  """Stand-in for the EagerTensor `model.predict` returns (quick_inference.py:368-370)."""
+
+  def __init__(self, array: np.ndarray):
+    self._array = array
+
+  def numpy(self) -> np.ndarray:
+    return self._array
+
+
+class B200Model:
+  """The encoder-only learned-values transformer on one B200, behind the C-ABI."""
+
+  def __init__(self, params: params_lib.Params, weights: weights_lib.Weights, max_batch: int = 1024,
+               device: int = 0, max_base_quality: int = 93,
+               calibration: Optional[calibration_lib.QualityCalibrationValues] = None,
+               chunk_tiles: int = 0):
+    self._lib = load_library()
+    self._handle = ctypes.c_void_p()
+    self.params = params
+    self.max_batch = max_batch
+    self.max_length = int(params.max_length)
+    self.total_rows = params_lib.get_total_rows(params.max_passes, params.use_ccs_bq)
+    cfg = make_config(params, max_batch, device, max_base_quality, calibration, chunk_tiles)
+    rc = self._lib.dcb_create(ctypes.byref(cfg), ctypes.byref(self._handle))
+    if rc:
+      msg = self._lib.dcb_last_error(None).decode()
+      self._handle = ctypes.c_void_p()
+      raise DcbError(rc, msg)
+    self.load_weights(weights)
+
+  # -- lifecycle ---------------------------------------------------------------------------
+  def close(self) -> None:
+    if getattr(self, "_handle", None) and self._handle.value:
+      self._lib.dcb_destroy(self._handle)
+      self._handle = ctypes.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # interpreter shutdown
+      pass
+
+  def _check(self, rc: int, tolerate: Tuple[int, ...] = ()) -> int:
+    if rc and rc not in tolerate:
+      raise DcbError(rc, self._lib.dcb_last_error(self._handle).decode())
+    return rc
+
+  def load_weights(self, weights: weights_lib.Weights) -> None:
+    weights_lib.check_weights(self.params, weights)
+    keep, tensors = [], (DcbTensor * len(weights))()
+    for i, (name, arr) in enumerate(weights.items()):
+      a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32))
+      keep.append(a)
+      tensors[i].name = name.encode()
+      tensors[i].data = a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+      tensors[i].ndim = a.ndim
+      for d in range(a.ndim):
+        tensors[i].shape[d] = a.shape[d]
+    self._check(self._lib.dcb_load_weights(self._handle, tensors, len(weights)))
+
+  # -- the hot path ------------------------------------------------------------------------
+  def _rows3(self, rows: np.ndarray) -> np.ndarray:
+    rows = np.asarray(rows)
+    if rows.ndim == 4:
+      if rows.shape[-1] != 1:
+        raise ValueError("rows must be [B, R, L, 1]")
+      rows = rows[..., 0]
+    if rows.ndim != 3 or rows.shape[1] != self.total_rows or rows.shape[2] != self.max_length:
+      raise ValueError("rows must be [B, %d, %d(, 1)], got %s" %
+                       (self.total_rows, self.max_length, rows.shape))
+    return np.ascontiguousarray(rows, dtype=np.float32)
+
+  def forward(self, rows: np.ndarray, want_probs: bool = False, want_logits: bool = False,
+              strict_input: bool = True) -> Dict[str, np.ndarray]:
+    """rows float32 [B, R, L(,1)] -> dict(bases u8 [B,L], quals u8 [B,L], [probs], [logits]).
+
+    Batches larger than `max_batch` are split, like `batch_examples` does with
+    `options.batch_size` (quick_inference.py:304-338).
+    """
+    rows = self._rows3(rows)
+    B, L = rows.shape[0], self.max_length
+    out = dict(bases=np.empty((B, L), np.uint8), quals=np.empty((B, L), np.uint8))
+    if want_probs:
+      out["probs"] = np.empty((B, L, 5), np.float32)
+    if want_logits:
+      out["logits"] = np.empty((B, L, 5), np.float32)
+    ms, launches = 0.0, 0
+    for b0 in range(0, B, self.max_batch):
+      b1 = min(B, b0 + self.max_batch)
+      ptr = lambda k: out[k][b0:b1].ctypes.data_as(ctypes.c_void_p) if k in out else None
+      rc = self._lib.dcb_forward(self._handle, rows[b0:b1].ctypes.data_as(ctypes.c_void_p), b1 - b0, 0,
+                                 ptr("bases"), ptr("quals"), ptr("probs"), ptr("logits"))
+      self._check(rc, tolerate=() if strict_input else (-5,))
+      ms += self.last_forward_ms()
+      launches += self.last_forward_launches()
+    self.last_ms, self.last_launches = ms, launches
+    return out
+
+  def predict(self, rows: np.ndarray) -> _Prediction:
+    """Softmax output [B, L, 5], shaped like `EncoderOnlyTransformer.predict` (networks.py:357-365)."""
+    return _Prediction(self.forward(rows, want_probs=True)["probs"])
+
+  # -- introspection -----------------------------------------------------------------------
+  def last_forward_ms(self) -> float:
+    v = ctypes.c_float()
+    self._check(self._lib.dcb_last_forward_ms(self._handle, ctypes.byref(v)))
+    return float(v.value)
+
+  def last_forward_launches(self) -> int:
+    v = ctypes.c_int32()
+    self._check(self._lib.dcb_last_forward_launches(self._handle, ctypes.byref(v)))
+    return int(v.value)
+
+  def set_debug(self, enabled: bool = True) -> None:
+    self._check(self._lib.dcb_set_debug(self._handle, int(enabled)))
+
+  def debug_residual(self, stage: int, tokens: int) -> np.ndarray:
+    out = np.empty((tokens, 280), np.float32)
+    self._check(self._lib.dcb_debug_residual(self._handle, stage, out.ctypes.data_as(ctypes.c_void_p),
+                                             out.size))
+    return out
+
+  # -- raw device / pinned buffers (bench, multi-GPU driver) ----------------------------------
+  def alloc_device(self, nbytes: int) -> int:
+    p = ctypes.c_void_p()
+    self._check(self._lib.dcb_alloc_device(self._handle, nbytes, ctypes.byref(p)))
+    return p.value
+
+  def free_device(self, ptr: int) -> None:
+    self._check(self._lib.dcb_free_device(self._handle, ctypes.c_void_p(ptr)))
+
+  def memcpy_h2d(self, dst: int, src: np.ndarray) -> None:
+    src = np.ascontiguousarray(src)
+    self._check(self._lib.dcb_memcpy_h2d(self._handle, ctypes.c_void_p(dst),
+                                         src.ctypes.data_as(ctypes.c_void_p), src.nbytes))
+
+  def memcpy_d2h(self, dst: np.ndarray, src: int) -> None:
+    self._check(self._lib.dcb_memcpy_d2h(self._handle, dst.ctypes.data_as(ctypes.c_void_p),
+                                         ctypes.c_void_p(src), dst.nbytes))
+
+  def forward_raw(self, rows_ptr: int, batch: int, flags: int, bases_ptr: int, quals_ptr: int,
+                  probs_ptr: int = 0, logits_ptr: int = 0) -> None:
+    """dcb_forward on caller-managed pointers (host or device per `flags`)."""
+    self._check(self._lib.dcb_forward(self._handle, ctypes.c_void_p(rows_ptr), batch, flags,
+                                      ctypes.c_void_p(bases_ptr), ctypes.c_void_p(quals_ptr),
+                                      ctypes.c_void_p(probs_ptr) if probs_ptr else None,
+                                      ctypes.c_void_p(logits_ptr) if logits_ptr else None))
+
+  def synchronize(self) -> None:
+    self._check(self._lib.dcb_synchronize(self._handle))
+
+
+def alloc_pinned(nbytes: int) -> Tuple[int, np.ndarray]:
+  """Pinned host buffer as (address, uint8 ndarray view). Free with free_pinned(address)."""
+  lib = load_library()
+  p = ctypes.c_void_p()
+  rc = lib.dcb_alloc_host(nbytes, ctypes.byref(p))
+  if rc:
+    raise DcbError(rc, "cudaMallocHost failed")
+  arr = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(nbytes,))
+  return p.value, arr
+
+
+def free_pinned(addr: int) -> None:
+  load_library().dcb_free_host(ctypes.c_void_p(addr))

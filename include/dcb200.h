@@ -1,0 +1,129 @@
+/* dcb200 -- C ABI of the B200-native DeepConsensus model path.
+ *
+ * This is the drop-in boundary for the one hot path of google/deepconsensus (v1.2.0):
+ *
+ *   quick_inference.initialize_model()          deepconsensus/inference/quick_inference.py:485-532
+ *   quick_inference.run_model_on_examples()     deepconsensus/inference/quick_inference.py:341-415
+ *     -> model.predict(rows)                    deepconsensus/models/networks.py:357-365 (:221-345, :436-520)
+ *     -> argmax / Phred / calibration / clip    quick_inference.py:377-389, quality_calibration/calibration_lib.py:77-99
+ *     -> per-window base + quality strings      quick_inference.py:390-414, utils/utils.py:60-62
+ *
+ * The reference has no FFI (it is pure Python on TensorFlow); the binding a maintainer adds
+ * is a ctypes stub -- see INTEGRATION.md and deepconsensus_b200/engine.py.
+ *
+ * Conventions: plain C, no exceptions across the boundary.  Every function returns
+ * DCB_OK (0) or a negative error code; dcb_last_error() gives the message.  All buffers are
+ * caller-owned and caller-sized.  One engine per device, not re-entrant (the reference
+ * touches the model from its main thread only).  Results are deterministic (no atomics in
+ * any reduction).
+ */
+#ifndef DCB200_H_
+#define DCB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCB_OK 0
+#define DCB_ERR_INVALID (-1)     /* bad argument / unsupported configuration */
+#define DCB_ERR_CUDA (-2)        /* CUDA runtime error (message has the detail) */
+#define DCB_ERR_WEIGHTS (-3)     /* missing / mis-shaped variable */
+#define DCB_ERR_STATE (-4)       /* call order (e.g. forward before load_weights) */
+#define DCB_ERR_INPUT_RANGE (-5) /* an embedding id was out of range (TF would raise); output still produced with clamped ids */
+
+typedef struct dcb_engine dcb_engine;
+
+/* Model + inference options.  Field names follow params.json / InferenceOptions
+ * (models/model_configs.py:76-139,272-338; quick_inference.py:238-275). */
+typedef struct dcb_config {
+  int32_t struct_size;        /* sizeof(dcb_config), for ABI checking */
+  int32_t device;             /* CUDA device ordinal */
+  /* input geometry (data_providers.py:61-113) */
+  int32_t max_passes;
+  int32_t max_length;
+  int32_t use_ccs_bq;
+  /* transformer (transformer_basic_params.py:33-67 merged under model_configs.py) */
+  int32_t hidden_size;        /* must be 280 */
+  int32_t num_heads;          /* must be 2 */
+  int32_t num_hidden_layers;
+  int32_t filter_size;        /* multiple of 128, <= 2048 */
+  int32_t attn_win_size;      /* 0 => full attention (params.attn_win_size None) */
+  int32_t rezero;             /* 1: x + alpha*f(x); 0: x + f(LayerNorm(x)) (encoder_stack.py:72-93) */
+  int32_t add_pos_encoding;
+  int32_t condense_transformer_input; /* must be 1 (transformer_input_size == hidden_size) */
+  /* embedding widths and vocabularies (networks.py:375-421) */
+  int32_t per_base_hidden_size, pw_hidden_size, ip_hidden_size, strand_hidden_size,
+      ccs_bq_hidden_size, sn_hidden_size;
+  int32_t pw_max, ip_max, sn_max, ccs_bq_max, strand_max;
+  /* post-processing (quick_inference.py:377-389) */
+  int32_t max_base_quality;   /* 93 */
+  int32_t calibration_enabled;
+  double calibration_threshold, calibration_w, calibration_b;
+  /* engine sizing */
+  int32_t max_batch;          /* largest B a single dcb_forward call will see */
+  int32_t chunk_tiles;        /* 128-token tiles processed per pass through the layer stack; 0 = auto */
+  int32_t reserved[6];
+} dcb_config;
+
+/* A named host tensor in the reference checkpoint's layout, e.g.
+ * "model/encoder_stack/layers/0/0/layer/query_dense_layer/kernel" float32 [280,2,140]. */
+typedef struct dcb_tensor {
+  const char* name;
+  const float* data;   /* host pointer, C-contiguous float32 */
+  int32_t ndim;
+  int64_t shape[4];
+} dcb_tensor;
+
+/* flags for dcb_forward */
+#define DCB_ROWS_ON_DEVICE 1u   /* `rows` is a device pointer (already resident in HBM) */
+#define DCB_OUT_ON_DEVICE 2u    /* output pointers are device pointers */
+
+/* Create an engine on cfg->device.  Replaces model construction in initialize_model
+ * (quick_inference.py:515-526). */
+int dcb_create(const dcb_config* cfg, dcb_engine** out);
+
+/* Load all variables (host fp32, reference shapes); the engine pads, folds (query scale,
+ * ReZero alpha) and casts into its device layouts.  Replaces checkpoint.restore(...)
+ * (quick_inference.py:527-529).  Unknown names are ignored (expect_partial); every variable
+ * the configured model needs must be present. */
+int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n);
+
+/* The hot path: rows float32 [B, total_rows, max_length] (the [B,R,L,1] tensor of
+ * quick_inference.py:363 with the channel axis dropped; NOT pre-clipped -- format_rows'
+ * clipping happens on the device) -> per position base character (' ', 'A', 'T', 'C', 'G')
+ * and Phred+33 quality character.  probs_out / logits_out ([B, L, 5] float32) may be NULL. */
+int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
+                uint8_t* bases_out, uint8_t* quals_out, float* probs_out, float* logits_out);
+
+/* Device time of the last dcb_forward (milliseconds, CUDA events on the engine's stream). */
+int dcb_last_forward_ms(dcb_engine* e, float* ms);
+/* Number of engine kernels launched by the last dcb_forward. */
+int dcb_last_forward_launches(dcb_engine* e, int32_t* n);
+
+/* Debug/test hook: copy the fp32 residual stream after stage `stage` of the LAST chunk of the
+ * last forward into out [tokens, 280] (row-major).  stage 0 = condenser+pos-enc,
+ * 1+2n = attention sub-layer n, 2+2n = FFN sub-layer n.  Requires dcb_set_debug(e, 1). */
+int dcb_set_debug(dcb_engine* e, int32_t enabled);
+int dcb_debug_residual(dcb_engine* e, int32_t stage, float* out, int64_t out_elems);
+
+/* Pinned host memory helpers (for callers that want async H2D/D2H). */
+int dcb_alloc_host(size_t bytes, void** out);
+int dcb_free_host(void* p);
+/* Device memory helpers so a host language can keep inputs resident (bench `value`). */
+int dcb_alloc_device(dcb_engine* e, size_t bytes, void** out);
+int dcb_free_device(dcb_engine* e, void* p);
+int dcb_memcpy_h2d(dcb_engine* e, void* dst_dev, const void* src_host, size_t bytes);
+int dcb_memcpy_d2h(dcb_engine* e, void* dst_host, const void* src_dev, size_t bytes);
+int dcb_synchronize(dcb_engine* e);
+
+const char* dcb_last_error(const dcb_engine* e); /* e may be NULL: last create() error */
+const char* dcb_version(void);
+void dcb_destroy(dcb_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCB200_H_ */
