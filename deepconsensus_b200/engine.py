@@ -195,13 +195,14 @@ class B200Model:
     weights_lib.check_weights(self.params, weights)
     keep, tensors = [], (DcbTensor * len(weights))()
     for i, (name, arr) in enumerate(weights.items()):
-      a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32))
+      shape = np.shape(arr)                      # 0-d for the ReZero alphas
+      a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32)).reshape(-1)
       keep.append(a)
       tensors[i].name = name.encode()
       tensors[i].data = a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
-      tensors[i].ndim = a.ndim
-      for d in range(a.ndim):
-        tensors[i].shape[d] = a.shape[d]
+      tensors[i].ndim = len(shape)
+      for d, s in enumerate(shape):
+        tensors[i].shape[d] = s
     self._check(self._lib.dcb_load_weights(self._handle, tensors, len(weights)))
 
   # -- the hot path ------------------------------------------------------------------------
