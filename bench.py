@@ -1,0 +1,296 @@
+"""bench.py -- ZMW windows/sec of the DeepConsensus model path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus 1 --steps K --warmup W            # the dcb200 engine
+  python bench.py --impl reference --gpus 1 --steps K ...   # reference algorithm on host cores
+
+A "step" is one pass of the hot path over one batch of synthetic pileup windows
+(BASELINE.json configs[1]: 20 subreads x 120 bp, d_model 280, 6 layers, batch 1024 per GPU).
+Multi-GPU (torchrun, one rank per GPU): windows are independent units, every rank scores its
+own shard -- no data-path collective; NCCL carries only the barrier and the max-over-ranks
+time reduction ("scaling": "weak").
+
+value  : whole-job windows/s with the input rows already resident in HBM.
+e2e    : the same metric through the reference-facing call (B200Model.forward: C-ABI
+         dcb_forward with HOST buffers) -- pinned-host rows are copied H2D and the base /
+         quality characters copied D2H inside the timed region.
+roofline: tensor-core roofline of the dominant kernel (fused FFN), timed with CUDA events on
+         the engine's stream during the timed region.
+cpu_baseline / --impl reference: the oracle (torch-CPU fp32 restatement of the reference
+         model, oracle/model.py) on the box's host cores.  This is the only place bench.py
+         executes oracle/ -- as the baseline being reported, never as the product.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from deepconsensus_b200 import calibration as calibration_lib  # noqa: E402
+from deepconsensus_b200 import params as params_lib            # noqa: E402
+from deepconsensus_b200 import synthetic                       # noqa: E402
+from deepconsensus_b200 import weights as weights_lib          # noqa: E402
+
+METRIC = "zmw_windows_per_sec"
+UNIT = "windows/s"
+WORKLOAD = dict(workload="synthetic pileup windows (BASELINE configs[1])", max_passes=20,
+                window=120, d_model=280, layers=6, heads=2, filter_size=2048, attn_win_size=12,
+                batch_per_gpu=1024)
+CALIBRATION = "0,1.197654,-0.99781"   # the fixture params.json's dc_calibration
+
+
+def model_params():
+  return params_lib.synthetic_params(max_passes=WORKLOAD["max_passes"], max_length=WORKLOAD["window"],
+                                     num_hidden_layers=WORKLOAD["layers"])
+
+
+def flops_per_window(p) -> float:
+  """Algorithmic (un-padded, banded) FLOPs per window -- SURVEY.md section 8(d)."""
+  L, d, ff, w = p.max_length, p.hidden_size, p.filter_size, p.attn_win_size
+  E = params_lib.embedded_width(p)
+  pairs = L * (2 * w + 1) - w * (w + 1)
+  return 2 * L * E * d + p.num_hidden_layers * (8 * L * d * d + 4 * pairs * d + 4 * L * d * ff) + 2 * L * d * 5
+
+
+def measured_peaks():
+  path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(path):
+    with open(path) as f:
+      pk = json.load(f)
+    return dict(bf16_tflops=pk["bf16_tflops"], bf16_tflops_sustained=pk.get("bf16_tflops_sustained"),
+                hbm_gbs=pk["hbm_gbs"], source="MEASURED_PEAKS.json")
+  return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0,
+              source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+  """Samples nvidia-smi SM clock + throttle reasons for one GPU during the timed region."""
+
+  def __init__(self, index: int):
+    super().__init__(daemon=True)
+    self.index, self.samples, self.stop_flag = index, [], threading.Event()
+    self.max_mhz = None
+
+  def run(self):
+    q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    while not self.stop_flag.is_set():
+      try:
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                             timeout=5).stdout.strip().split(",")
+        self.samples.append((float(out[0]), [o.strip() for o in out[2:]]))
+        self.max_mhz = float(out[1])
+      except Exception:
+        pass
+      self.stop_flag.wait(0.2)
+
+  def summary(self):
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    if not self.samples:
+      return dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=[], samples=0)
+    reasons = sorted({names[i] for _, fl in self.samples for i, v in enumerate(fl) if v.lower().startswith("active")})
+    return dict(sm_mhz=float(np.median([s[0] for s in self.samples])), sm_max_mhz=self.max_mhz,
+                reasons=reasons, samples=len(self.samples))
+
+
+def cpu_reference_windows_per_sec(p, w, sample_windows: int, reps: int, threads: int):
+  """Times the oracle (reference algorithm restated on torch-CPU fp32) incl. argmax/QV."""
+  import torch
+  from oracle import model as omodel, postprocess as opost
+  torch.set_num_threads(threads)
+  rows = synthetic.make_rows(p, sample_windows, seed=99)
+  cal = calibration_lib.parse_calibration_string(CALIBRATION)
+  ts = []
+  for _ in range(reps + 1):
+    t = time.perf_counter()
+    out = omodel.forward(rows, p, w)
+    opost.quality_from_probs(out["probs"], 93, (cal.threshold, cal.w, cal.b))
+    ts.append(time.perf_counter() - t)
+  best = float(np.median(ts[1:])) if reps > 1 else ts[-1]
+  return sample_windows / best, best
+
+
+def run_reference(args, rank, world):
+  """--impl reference: the reference's CPU path of the same workload (rank 0 only)."""
+  if rank != 0:
+    return
+  p = model_params()
+  w = weights_lib.init_weights(p, seed=1)
+  cores = os.cpu_count() or 1
+  sample = 128
+  import torch
+  from oracle import model as omodel, postprocess as opost
+  torch.set_num_threads(cores)
+  rows = synthetic.make_rows(p, sample, seed=99)
+  cal = calibration_lib.parse_calibration_string(CALIBRATION)
+
+  def step():
+    out = omodel.forward(rows, p, w)
+    opost.quality_from_probs(out["probs"], 93, (cal.threshold, cal.w, cal.b))
+  for _ in range(args.warmup):
+    step()
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    step()
+  dt = time.perf_counter() - t0
+  value = sample * args.steps / dt
+  desc = dict(value=value, unit=UNIT, cores=cores, kind="port",
+              sample="%d synthetic windows per step (of the 1024-window batch), torch-CPU fp32 oracle" % sample)
+  print(json.dumps(dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus,
+                        steps=args.steps, warmup=args.warmup, ms_per_step=dt / args.steps * 1e3,
+                        higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                        data="synthetic", config=dict(WORKLOAD), cpu_baseline=desc,
+                        e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--warmup", type=int, default=5)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--batch", type=int, default=WORKLOAD["batch_per_gpu"])
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3)
+
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if args.impl == "reference":
+    run_reference(args, rank, world)
+    return
+
+  import torch
+  import torch.distributed as dist
+  from deepconsensus_b200 import engine as engine_lib
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py: no CUDA device (the dcb200 engine has no CPU fallback)")
+  torch.cuda.set_device(local)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+  p = model_params()
+  w = weights_lib.init_weights(p, seed=1)
+  B, L, R = args.batch, p.max_length, p.total_rows
+  cal = calibration_lib.parse_calibration_string(CALIBRATION)
+  model = engine_lib.B200Model(p, w, max_batch=B, device=local, calibration=cal)
+
+  # ---- inputs: NBUF distinct batches rotate so a step's rows are never L2-resident
+  NBUF = 4
+  row_bytes = B * R * L * 4
+  host_rows = [synthetic.make_rows(p, B, seed=20240921 + 1 + rank * NBUF + i)[..., 0] for i in range(NBUF)]
+  dev_rows = [model.alloc_device(row_bytes) for _ in range(NBUF)]
+  for d, h in zip(dev_rows, host_rows):
+    model.memcpy_h2d(d, h)
+  dev_bases, dev_quals = model.alloc_device(B * L), model.alloc_device(B * L)
+  pin_addr, pin = [], []
+  for h in host_rows:
+    a, arr = engine_lib.alloc_pinned(row_bytes)
+    arr.view(np.float32)[:] = h.reshape(-1)
+    pin_addr.append(a)
+    pin.append(arr)
+  out_addr, out_pin = engine_lib.alloc_pinned(2 * B * L)
+  FL = engine_lib.DCB_ROWS_ON_DEVICE | engine_lib.DCB_OUT_ON_DEVICE
+
+  def step_resident(i):
+    model.forward_raw(dev_rows[i % NBUF], B, FL, dev_bases, dev_quals)
+
+  def step_e2e(i):
+    model.forward_raw(pin_addr[i % NBUF], B, 0, out_addr, out_addr + B * L)
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(fn, steps):
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for i in range(steps):
+      fn(i)
+      dev_ms += model.last_forward_ms()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+      t = torch.tensor([dt, dev_ms], device="cuda", dtype=torch.float64)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      dt, dev_ms = float(t[0]), float(t[1])
+    barrier()
+    return dt, dev_ms
+
+  for i in range(args.warmup):
+    step_resident(i)
+  sampler = ClockSampler(local)
+  sampler.start()
+  model.set_profile(True)
+  dt, dev_ms = timed(step_resident, args.steps)
+  prof = model.get_profile()
+  model.set_profile(False)
+  launches = model.last_forward_launches() * args.steps
+  sampler.stop_flag.set()
+  sampler.join(timeout=2)
+  for i in range(3):
+    step_e2e(i)
+  dt_e2e, _ = timed(step_e2e, args.steps)
+
+  total_windows = B * world * args.steps
+  value = total_windows / dt
+  e2e_value = total_windows / dt_e2e
+  F = flops_per_window(p)
+  peaks = measured_peaks()
+  # dominant kernel: fused FFN.  Algorithmic FLOPs per launch = tokens * 4*d*ff.
+  ffn_flops = prof["ffn_tokens"] * 4.0 * p.hidden_size * p.filter_size
+  ffn_tflops = ffn_flops / (prof["ffn_ms_total"] * 1e-3) / 1e12 if prof["ffn_ms_total"] > 0 else None
+  traffic = None
+  tpath = os.path.join(ROOT, "profiles", "ffn_dram_traffic.json")
+  if os.path.exists(tpath):
+    with open(tpath) as f:
+      traffic = json.load(f).get("dram_bytes_per_launch")
+  roof = dict(bound="tensor", kernel="ffn_kernel", achieved=ffn_tflops, peak=peaks["bf16_tflops"],
+              unit="TFLOP/s", frac=(ffn_tflops / peaks["bf16_tflops"]) if ffn_tflops else None,
+              traffic=traffic, peak_source=peaks["source"] + " (burst bf16)",
+              launches_timed=prof["ffn_launches"],
+              avg_launch_ms=prof["ffn_ms_total"] / max(prof["ffn_launches"], 1),
+              model_tflops_whole_step=value / world * F / 1e12,
+              model_frac_of_peak=value / world * F / 1e12 / peaks["bf16_tflops"])
+  line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+              ms_per_step=dt / args.steps * 1e3, device_ms_per_step=dev_ms / args.steps,
+              higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+              data="synthetic",
+              config=dict(WORKLOAD, global_batch=B * world, parallelism="dp%d (independent shards)" % world,
+                          l2="inputs rotate over %d resident batches (%.0f MB > L2)" % (NBUF, NBUF * row_bytes / 1e6),
+                          gflop_per_window=F / 1e9),
+              e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=row_bytes * world,
+                       d2h_bytes_per_step=2 * B * L * world, ms_per_step=dt_e2e / args.steps * 1e3),
+              gpu_launches=launches, roofline=roof, clocks=sampler.summary())
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    cores = os.cpu_count() or 1
+    v, secs = cpu_reference_windows_per_sec(p, w, sample_windows=128, reps=2, threads=cores)
+    line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=cores, kind="port",
+                                sample="128 synthetic windows of the same workload, torch-CPU fp32 oracle (%.1f s/pass)" % secs)
+  if rank == 0:
+    print(json.dumps(line))
+  for d in dev_rows + [dev_bases, dev_quals]:
+    model.free_device(d)
+  for a in pin_addr + [out_addr]:
+    engine_lib.free_pinned(a)
+  model.close()
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

@@ -44,6 +44,12 @@ struct dcb_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool weights_loaded = false;
   bool debug = false;
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // around every ffn_kernel launch
+  size_t prof_used = 0;
+  float prof_ffn_ms = 0.f;
+  int prof_ffn_launches = 0;
+  long long prof_ffn_tokens = 0;
   float last_ms = 0.f;
   int last_launches = 0;
   int last_chunk_tokens = 0;
@@ -219,6 +225,7 @@ void dcb_destroy(dcb_engine* e) {
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void* p : e->owned) cudaFree(p);
+  for (auto& pr : e->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -486,7 +493,21 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
       ef.ln_g = (c.rezero || last) ? nullptr : e->layers[n_ + 1].ln_g[0];
       ef.ln_b = (c.rezero || last) ? nullptr : e->layers[n_ + 1].ln_b[0];
       ef.has_xold = 1; ef.L = L;
+      if (e->profile) {
+        if (e->prof_used == e->prof_events.size()) {
+          cudaEvent_t a, b;
+          CU(e, cudaEventCreate(&a));
+          CU(e, cudaEventCreate(&b));
+          e->prof_events.emplace_back(a, b);
+        }
+        CU(e, cudaEventRecord(e->prof_events[e->prof_used].first, st));
+      }
       launch_ffn(e->d_xb, ld.wffn, ld.b1, c.filter_size, T, ef, st);
+      if (e->profile) {
+        CU(e, cudaEventRecord(e->prof_events[e->prof_used].second, st));
+        ++e->prof_used;
+        e->prof_ffn_tokens += M;
+      }
       snap();
       launches += 4;
     }
@@ -520,6 +541,15 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
   CU(e, cudaGetLastError());
   CU(e, cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
   e->last_launches = launches;
+  if (e->profile) {
+    for (size_t i = 0; i < e->prof_used; ++i) {
+      float ms = 0.f;
+      CU(e, cudaEventElapsedTime(&ms, e->prof_events[i].first, e->prof_events[i].second));
+      e->prof_ffn_ms += ms;
+      ++e->prof_ffn_launches;
+    }
+    e->prof_used = 0;
+  }
   if (status & 1) return fail(e, DCB_ERR_INPUT_RANGE, "embedding id out of range in the input rows (clamped)");
   return DCB_OK;
 }
@@ -533,6 +563,24 @@ int dcb_last_forward_ms(dcb_engine* e, float* ms) {
 int dcb_last_forward_launches(dcb_engine* e, int32_t* n) {
   if (!e || !n) return DCB_ERR_INVALID;
   *n = e->last_launches;
+  return DCB_OK;
+}
+
+int dcb_set_profile(dcb_engine* e, int32_t enabled) {
+  if (!e) return DCB_ERR_INVALID;
+  e->profile = enabled != 0;
+  e->prof_ffn_ms = 0.f;
+  e->prof_ffn_launches = 0;
+  e->prof_ffn_tokens = 0;
+  e->prof_used = 0;
+  return DCB_OK;
+}
+
+int dcb_get_profile(dcb_engine* e, float* ffn_ms_total, int32_t* ffn_launches, int64_t* ffn_tokens) {
+  if (!e || !ffn_ms_total || !ffn_launches || !ffn_tokens) return DCB_ERR_INVALID;
+  *ffn_ms_total = e->prof_ffn_ms;
+  *ffn_launches = e->prof_ffn_launches;
+  *ffn_tokens = e->prof_ffn_tokens;
   return DCB_OK;
 }
 

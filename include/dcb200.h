@@ -103,6 +103,12 @@ int dcb_last_forward_ms(dcb_engine* e, float* ms);
 /* Number of engine kernels launched by the last dcb_forward. */
 int dcb_last_forward_launches(dcb_engine* e, int32_t* n);
 
+/* Per-kernel timing of the dominant kernel (the fused FFN): when enabled, every ffn_kernel
+ * launch is bracketed by CUDA events on the engine's stream; dcb_get_profile returns the
+ * accumulated device time, launch count and tokens processed since dcb_set_profile. */
+int dcb_set_profile(dcb_engine* e, int32_t enabled);
+int dcb_get_profile(dcb_engine* e, float* ffn_ms_total, int32_t* ffn_launches, int64_t* ffn_tokens);
+
 /* Debug/test hook: copy the fp32 residual stream after stage `stage` of the LAST chunk of the
  * last forward into out [tokens, 280] (row-major).  stage 0 = condenser+pos-enc,
  * 1+2n = attention sub-layer n, 2+2n = FFN sub-layer n.  Requires dcb_set_debug(e, 1). */
