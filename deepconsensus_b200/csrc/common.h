@@ -42,6 +42,13 @@ struct EmbedCol {
   float clip_hi;      // > 0: clip value to [0, clip_hi] first (data_providers.py:151-162)
 };
 
+// Per input row: how a raw value becomes a table id.
+struct EmbedRow {
+  float clip_hi;   // > 0: clip to [0, clip_hi] (format_rows)
+  int32_t shift;   // +1 for ccs_bq
+  int32_t vocab;   // table rows
+};
+
 // ------------------------------------------------------------------ row epilogue
 // Shared tail of every d-wide GEMM: x_new = acc (+ x_old) (+ bias) (+ pos-enc);
 // write x_new (fp32 image) and the next sub-layer's bf16 operand image

@@ -55,6 +55,8 @@ struct dcb_engine {
   int last_chunk_tokens = 0;
   // model
   EmbedCol* d_cols = nullptr;
+  EmbedRow* d_rowmeta = nullptr;
+  int table_elems = 0;
   __nv_bfloat16* d_tables = nullptr;
   __nv_bfloat16* d_wc = nullptr;
   float* d_pe = nullptr;
@@ -191,7 +193,7 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   e->echunks = e->Epad / 8;
   int ct = cfg->chunk_tiles;
   if (const char* env = getenv("DCB_CHUNK_TILES")) ct = atoi(env);
-  if (ct <= 0) ct = 2 * e->num_sms;
+  if (ct <= 0) ct = 8 * e->num_sms;   // measured: larger chunks win (kernels are not DRAM-bound)
   const int max_tiles = (int)(((int64_t)cfg->max_batch * e->L + kTileM - 1) / kTileM);
   e->chunk_windows = std::max(1, std::min(cfg->max_batch, ct * kTileM / e->L));
   e->chunk_tiles = std::min(max_tiles, (e->chunk_windows * e->L + kTileM - 1) / kTileM);
@@ -293,6 +295,15 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
     if (c.use_ccs_bq) { add_rows(4, next, 1, 0.f, 1); ++next; }  // +1 shift (networks.py:495)
     add_rows(5, next, 4, (float)c.sn_max, 0);                   // sn   (:159-162)
     if (eoff != e->E) return fail(e, DCB_ERR_INVALID, "internal: embedding width %d != %d", eoff, e->E);
+  }
+  {
+    std::vector<EmbedRow> meta(e->R, EmbedRow{0.f, 0, 1});
+    for (const EmbedCol& cc : cols)
+      if (cc.src_row >= 0) meta[cc.src_row] = EmbedRow{cc.clip_hi, cc.shift, cc.vocab};
+    if ((rc = upload(e, &e->d_rowmeta, meta))) return rc;
+    e->table_elems = (int)blob.size();
+    if (embed_smem_bytes(e->R, e->echunks, e->table_elems) > 160 * 1024)
+      return fail(e, DCB_ERR_INVALID, "embedding tables + ids do not fit the embed kernel's shared memory");
   }
   if ((rc = upload(e, &e->d_tables, blob))) return rc;
   if ((rc = upload(e, &e->d_cols, cols))) return rc;
@@ -463,7 +474,7 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
       if (e->debug) cudaMemcpyAsync(e->d_dbg + (size_t)stage * e->chunk_tiles * ximg, e->d_x, (size_t)T * ximg * sizeof(float), cudaMemcpyDeviceToDevice, st);
       ++stage;
     };
-    launch_embed(rows_chunk, R, L, M, T, e->echunks, e->d_cols, e->d_tables, e->d_embqkv, e->d_status, st);
+    launch_embed(rows_chunk, R, L, M, T, e->echunks, e->d_cols, e->d_rowmeta, e->d_tables, e->table_elems, e->d_embqkv, e->d_status, st);
     ++launches;
     {
       RowEpi epi{};
@@ -601,6 +612,10 @@ int dcb_debug_residual(dcb_engine* e, int32_t stage, float* out, int64_t out_ele
       out[(size_t)t * kD + col] = img[(((size_t)tile * kXChunks + col / 4) * kTileM + r) * 4 + col % 4];
   }
   return DCB_OK;
+}
+
+int dcb_debug_trace(uint64_t* out, int32_t n) {
+  return read_ffn_trace(reinterpret_cast<unsigned long long*>(out), n) ? DCB_ERR_CUDA : DCB_OK;
 }
 
 int dcb_alloc_host(size_t bytes, void** out) {

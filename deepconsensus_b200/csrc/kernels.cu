@@ -15,6 +15,8 @@
 
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "sm100.cuh"
 
@@ -23,44 +25,61 @@ namespace dcb {
 // =====================================================================================
 // embed
 // =====================================================================================
+// One CTA per 128-token tile.  Phase 1 turns the tile's R x 128 input values into table ids
+// (clip -> shift -> truncate -> range check) in shared memory with coalesced loads along L;
+// phase 2 assembles 16-byte K-chunks of the operand image from the shared-memory tables.
 __global__ void __launch_bounds__(256)
 embed_rows_kernel(const float* __restrict__ rows, int R, int L, int M, int echunks,
-                  const EmbedCol* __restrict__ cols, const __nv_bfloat16* __restrict__ tables,
+                  const EmbedCol* __restrict__ cols, const EmbedRow* __restrict__ rowmeta,
+                  const __nv_bfloat16* __restrict__ tables, int table_elems,
                   __nv_bfloat16* __restrict__ emb, int* __restrict__ status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __nv_bfloat16* s_tab = reinterpret_cast<__nv_bfloat16*>(smem);
+  const int tab_bytes = (table_elems * 2 + 15) & ~15;
+  EmbedCol* s_cols = reinterpret_cast<EmbedCol*>(smem + tab_bytes);
+  const int cols_bytes = (echunks * 8 * (int)sizeof(EmbedCol) + 15) & ~15;
+  uint16_t* s_ids = reinterpret_cast<uint16_t*>(smem + tab_bytes + cols_bytes);  // [R][128]
   const int tile = blockIdx.x;
+  for (int i = threadIdx.x; i < table_elems; i += blockDim.x) s_tab[i] = tables[i];
+  for (int i = threadIdx.x; i < echunks * 8; i += blockDim.x) s_cols[i] = cols[i];
+  for (int idx = threadIdx.x; idx < R * kTileM; idx += blockDim.x) {
+    const int rr = idx / kTileM, r = idx % kTileM;
+    const int tok = tile * kTileM + r;
+    int id = 0;
+    if (tok < M) {
+      const int b = tok / L, l = tok - b * L;
+      const EmbedRow m = rowmeta[rr];
+      float f = __ldg(rows + ((size_t)b * R + rr) * L + l);
+      if (m.clip_hi > 0.f) f = fminf(fmaxf(f, 0.f), m.clip_hi);  // format_rows (data_providers.py:151-162)
+      f += (float)m.shift;                                         // networks.py:495
+      id = (int)f;  // truncation toward zero == tf.cast(float32 -> int32)
+      if (id < 0 || id >= m.vocab) {
+        atomicOr(status, 1);  // TF's CPU gather raises here; flag and clamp
+        id = id < 0 ? 0 : m.vocab - 1;
+      }
+    }
+    s_ids[idx] = (uint16_t)id;
+  }
+  __syncthreads();
   const int total = echunks * kTileM;
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int kc = idx / kTileM;
     const int r = idx % kTileM;
-    const int tok = tile * kTileM + r;
-    uint32_t packed[4] = {0u, 0u, 0u, 0u};
-    if (tok < M) {
-      const int b = tok / L;
-      const int l = tok - b * L;
-      const float* win = rows + (size_t)b * R * L + l;
-      __nv_bfloat16 vals[8];
+    uint32_t packed[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const EmbedCol c = cols[kc * 8 + j];
-        __nv_bfloat16 v = __float2bfloat16(0.f);
+    for (int j = 0; j < 4; ++j) {
+      uint32_t pr = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const EmbedCol c = s_cols[kc * 8 + 2 * j + h];
+        uint32_t bits = 0;
         if (c.src_row >= 0) {
-          float f = __ldg(win + (size_t)c.src_row * L);
-          if (c.clip_hi > 0.f) f = fminf(fmaxf(f, 0.f), c.clip_hi);
-          f += (float)c.shift;
-          int id = (int)f;  // truncation toward zero == tf.cast(float32 -> int32)
-          if (id < 0 || id >= c.vocab) {
-            atomicOr(status, 1);  // TF's CPU gather raises here; flag and clamp
-            id = id < 0 ? 0 : c.vocab - 1;
-          }
-          v = tables[c.table_off + id * c.width + c.col];
+          const int id = s_ids[c.src_row * kTileM + r];
+          bits = __bfloat16_as_ushort(s_tab[c.table_off + id * c.width + c.col]);
         }
-        vals[j] = v;
+        pr |= bits << (16 * h);
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        packed[j] = (uint32_t)__bfloat16_as_ushort(vals[2 * j]) |
-                    ((uint32_t)__bfloat16_as_ushort(vals[2 * j + 1]) << 16);
-      }
+      packed[j] = pr;
     }
     uint4* dst = reinterpret_cast<uint4*>(emb + ((size_t)tile * echunks + kc) * kTileM * 8) + r;
     *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -99,8 +118,29 @@ struct RowStats {
   float mean, rstd;
 };
 
+// x_old prefetch for the row epilogue: kRowPF column blocks of 16 floats in flight per thread.
+constexpr int kRowPF = 4;
+struct RowPrefetch {
+  float4 buf[kRowPF][4];
+};
+
+__device__ __forceinline__ void row_prefetch_issue(const RowEpi& e, int tile, int r, int cb,
+                                                   float4 (&dst)[4]) {
+  const float4* xrow = reinterpret_cast<const float4*>(e.x + (size_t)tile * x_image_elems()) + r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dst[i] = xrow[(size_t)(cb * 4 + i) * kTileM];
+}
+
+// Issue the first kRowPF blocks (call before waiting for the accumulator).
+__device__ __forceinline__ void row_prefetch_start(const RowEpi& e, int tile, int r, RowPrefetch& pf) {
+  if (e.has_xold) {
+#pragma unroll
+    for (int k = 0; k < kRowPF; ++k) row_prefetch_issue(e, tile, r, k, pf.buf[k]);
+  }
+}
+
 __device__ __forceinline__ RowStats row_epilogue_pass1(const RowEpi& e, uint32_t tmem_row_base,
-                                                       int tile, int r) {
+                                                       int tile, int r, RowPrefetch& pf) {
   const int tok = tile * kTileM + r;
   const int l = tok % e.L;
   float4* xrow = reinterpret_cast<float4*>(e.x + (size_t)tile * x_image_elems()) + r;
@@ -108,7 +148,7 @@ __device__ __forceinline__ RowStats row_epilogue_pass1(const RowEpi& e, uint32_t
                       : nullptr;
   const bool ln = e.ln_g != nullptr;
   float s1 = 0.f, s2 = 0.f, shift = 0.f;
-#pragma unroll 1
+#pragma unroll
   for (int cb = 0; cb < kDP / 16; ++cb) {
     uint32_t acc[16];
     tmem_ld16(tmem_row_base + cb * 16, acc);
@@ -116,9 +156,10 @@ __device__ __forceinline__ RowStats row_epilogue_pass1(const RowEpi& e, uint32_t
     if (e.has_xold) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 t = xrow[(size_t)(cb * 4 + i) * kTileM];
+        const float4 t = pf.buf[cb % kRowPF][i];
         v[4 * i + 0] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
       }
+      if (cb + kRowPF < kDP / 16) row_prefetch_issue(e, tile, r, cb + kRowPF, pf.buf[cb % kRowPF]);
     } else {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = 0.f;
@@ -279,6 +320,8 @@ gemm_kernel(const __nv_bfloat16* __restrict__ a_img, const __nv_bfloat16* __rest
     uint32_t it = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
       const int tile = item / ngroups, grp = item % ngroups;
+      RowPrefetch pf;
+      if constexpr (EPI == EPI_ROW) row_prefetch_start(epi, tile, r, pf);
       mbar_wait(acc_full, it & 1);
       tc_fence_after();
       if constexpr (EPI == EPI_QKV) {
@@ -302,7 +345,7 @@ gemm_kernel(const __nv_bfloat16* __restrict__ a_img, const __nv_bfloat16* __rest
         mbar_arrive(acc_empty);
       } else {
         static_assert(EPI != EPI_ROW || NCH == 2, "row epilogue needs the full 288-wide row");
-        const RowStats st = row_epilogue_pass1(epi, tmem_row, tile, r);
+        const RowStats st = row_epilogue_pass1(epi, tmem_row, tile, r, pf);
         tc_fence_before();
         mbar_arrive(acc_empty);   // accumulator free: next item's MMAs overlap the LN pass
         if (epi.ln_g && epi.xb) row_epilogue_pass2<false>(epi, tile, r, st.mean, st.rstd);
@@ -323,13 +366,14 @@ gemm_kernel(const __nv_bfloat16* __restrict__ a_img, const __nv_bfloat16* __rest
 struct FfnCfg {
   static constexpr int kABytes = (kDP / 8) * kTileM * 16;            // 73728: x operand tile
   static constexpr int kHBytes = (kFFChunk / 8) * kTileM * 16;       // 32768: one hidden chunk
-  static constexpr int kSlotBytes = 12288;
-  static constexpr int kSlots = 6;
-  static constexpr int kW1StageK = 3;                                // k-steps per W1 stage
-  static constexpr int kW1StageBytes = kW1StageK * 2 * kFFChunk * 16;  // 12288
-  static constexpr int kW1Stages = (kDP / 16) / kW1StageK;           // 6
-  static constexpr int kW2StageBytes = 2 * kDP * 16;                 // 9216 (one k-step)
-  static constexpr int kW2Stages = kFFChunk / 16;                    // 8
+  static constexpr int kSlotBytes = 24576;
+  static constexpr int kSlots = 3;
+  static constexpr int kW1StageK = 6;                                // k-steps per W1 stage
+  static constexpr int kW1StageBytes = kW1StageK * 2 * kFFChunk * 16;  // 24576
+  static constexpr int kW1Stages = (kDP / 16) / kW1StageK;           // 3
+  static constexpr int kW2StageK = 2;                                // k-steps per W2 stage
+  static constexpr int kW2StageBytes = kW2StageK * 2 * kDP * 16;     // 18432
+  static constexpr int kW2Stages = (kFFChunk / 16) / kW2StageK;      // 4
   static constexpr int kW1ChunkBytes = kW1Stages * kW1StageBytes;    // 73728
   static constexpr int kW2ChunkBytes = kW2Stages * kW2StageBytes;    // 73728
   static constexpr int kTmemY = 0;
@@ -347,7 +391,35 @@ static_assert(FfnCfg::kSmemBytes <= 232448, "FFN shared memory budget");
 static_assert(FfnCfg::kW1StageBytes <= FfnCfg::kSlotBytes && FfnCfg::kW2StageBytes <= FfnCfg::kSlotBytes, "slot");
 
 // w_img: per ff-chunk c: [W1 chunk image 73728 B][W2 chunk image 73728 B].
-__global__ void __launch_bounds__(192, 1)
+//
+// CS = thread-block cluster size.  The CS CTAs of a cluster walk their tiles in lock step and
+// share every weight stage: CTA `rank` fetches 1/CS of the stage and multicasts it into the
+// same ring slot of all CS CTAs (cp.async.bulk ... .multicast::cluster), which divides the
+// L2 -> SM weight traffic by CS (an un-clustered CTA streams all 2.36 MB of layer weights per
+// 128-token tile, which saturates L2 bandwidth long before the tensor pipe).  A ring slot is
+// recycled when the MMAs of ALL CS CTAs that read it have completed (multicast tcgen05.commit
+// onto every CTA's `empty` barrier, count = CS).
+//
+// Four warpgroups: WG0 = {bulk-copy producer, UMMA issuer (+TMEM alloc), 2 idle warps};
+// WG1+WG2 = hidden-chunk epilogue (two warps share each TMEM lane quarter and split the chunk's
+// columns, halving the G1 -> epilogue -> G1 dependency chain); WG3 = row epilogue of the finished
+// tile, which thereby overlaps the next tile's GEMMs (its residual loads are software-prefetched).
+// setmaxnreg moves registers from WG0-2 to WG3, whose fully unrolled prefetching loop needs ~200.
+constexpr int kFfnThreads = 512;
+
+// Optional cycle trace (build with -DDCB_TRACE): per CTA, cycles the MMA thread and one
+// hidden-epilogue warp spend in each wait.  Read back with dcb_debug_trace().
+__device__ unsigned long long g_ffn_trace[256 * 16];
+#ifdef DCB_TRACE
+#define TRACE_T0() long long _t0 = clock64()
+#define TRACE_ADD(var) do { long long _t1 = clock64(); (var) += _t1 - _t0; _t0 = _t1; } while (0)
+#else
+#define TRACE_T0() do {} while (0)
+#define TRACE_ADD(var) do {} while (0)
+#endif
+
+template <int CS>
+__global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ w_img,
            const float* __restrict__ b1, int ff, int ntiles, RowEpi epi) {
   using C = FfnCfg;
@@ -372,18 +444,23 @@ ffn_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nchunks = ff / kFFChunk;
+  const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
+  // every CTA of a cluster runs the same number of rounds; a CTA whose tile index falls past the
+  // end recomputes the last tile and drops the result, so the shared weight pipeline stays uniform
+  const int rounds = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::kSlots; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], CS);
     }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
     mbar_init(h_full, 1);
-    mbar_init(h_free, 128);
-    mbar_init(&hs_full[0], 128);
-    mbar_init(&hs_full[1], 128);
+    mbar_init(h_free, 256);
+    mbar_init(&hs_full[0], 256);
+    mbar_init(&hs_full[1], 256);
     mbar_init(&hs_free[0], 1);
     mbar_init(&hs_free[1], 1);
     mbar_init(y_full, 1);
@@ -394,17 +471,26 @@ ffn_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ 
   if (warp == 1) tmem_alloc(tmem_holder, C::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 0) {
+  if (warp < 4) {
+   setmaxnreg_dec<64>();
+   if (warp == 0) {
     // ------------------------------------------------------------- producer
     if (lane == 0) {
-      uint32_t slot = 0, phase = 0, ti = 0;
+      uint32_t slot = 0, phase = 0;
       auto push = [&](const uint8_t* src, uint32_t bytes) {
         mbar_wait(&empty[slot], phase ^ 1);
         mbar_arrive_expect_tx(&full[slot], bytes);
-        bulk_g2s(sRing + slot * C::kSlotBytes, src, bytes, &full[slot]);
+        if (CS == 1) {
+          bulk_g2s(sRing + slot * C::kSlotBytes, src, bytes, &full[slot]);
+        } else {
+          const uint32_t part = bytes / CS;
+          bulk_g2s_multicast(sRing + slot * C::kSlotBytes + rank * part, src + rank * part, part,
+                             &full[slot], kMask);
+        }
         if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
       };
       auto push_w1 = [&](int c) {
@@ -416,7 +502,8 @@ ffn_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ 
             w_img + (size_t)c * (C::kW1ChunkBytes + C::kW2ChunkBytes) + C::kW1ChunkBytes;
         for (int s = 0; s < C::kW2Stages; ++s) push(src + s * C::kW2StageBytes, C::kW2StageBytes);
       };
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      for (int ti = 0; ti < rounds; ++ti) {
+        const int tile = min(ti * (int)gridDim.x + (int)blockIdx.x, ntiles - 1);
         mbar_wait(a_empty, (ti & 1) ^ 1);
         mbar_arrive_expect_tx(a_full, C::kABytes);
         bulk_g2s(sA, reinterpret_cast<const uint8_t*>(a_img) + (size_t)tile * C::kABytes,
@@ -435,13 +522,21 @@ ffn_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ 
       constexpr uint32_t idesc_h = make_idesc_bf16(kTileM, kFFChunk);
       constexpr uint32_t idesc_y = make_idesc_bf16(kTileM, kNC);
       const uint32_t a_addr = smem_u32(sA);
-      uint32_t slot = 0, phase = 0, ti = 0, n = 0;  // n: global hidden-chunk counter
+      uint32_t slot = 0, phase = 0, n = 0;  // n: global hidden-chunk counter
+      long long t_hfree = 0, t_full = 0, t_hsfull = 0, t_issue = 0, t_afull = 0, t_yempty = 0;
+      const long long t_begin = clock64();
+      auto release = [&](uint64_t* bar) {
+        if (CS == 1) umma_commit(bar); else umma_commit_multicast(bar, kMask);
+      };
       auto gemm1 = [&](uint32_t nn) {
         // H[128 x 128] = X[128 x 288] * W1chunk^T
+        TRACE_T0();
         mbar_wait(h_free, (nn & 1) ^ 1);
+        TRACE_ADD(t_hfree);
         tc_fence_after();
         for (int s = 0; s < C::kW1Stages; ++s) {
           mbar_wait(&full[slot], phase);
+          TRACE_ADD(t_full);
           tc_fence_after();
           const uint32_t sb = smem_u32(sRing + slot * C::kSlotBytes);
 #pragma unroll
@@ -451,34 +546,43 @@ ffn_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ 
             const uint64_t bdesc = make_kc16_desc(sb + kk * (2 * kFFChunk * 16), kFFChunk * 16, 128);
             umma_bf16_ss(tmem_base + C::kTmemH, adesc, bdesc, idesc_h, kstep != 0);
           }
-          umma_commit(&empty[slot]);
+          release(&empty[slot]);
           if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+          TRACE_ADD(t_issue);
         }
         umma_commit(h_full);
       };
       auto gemm2 = [&](uint32_t nn, int c) {
         // Y[128 x 288] += Hc[128 x 128] * W2chunk^T
         const uint32_t b = nn & 1;
+        TRACE_T0();
         mbar_wait(&hs_full[b], (nn >> 1) & 1);
+        TRACE_ADD(t_hsfull);
         tc_fence_after();
         const uint32_t h_addr = smem_u32(sH + b * C::kHBytes);
         for (int s = 0; s < C::kW2Stages; ++s) {
           mbar_wait(&full[slot], phase);
+          TRACE_ADD(t_full);
           tc_fence_after();
           const uint32_t sb = smem_u32(sRing + slot * C::kSlotBytes);
-          const uint64_t adesc = make_kc16_desc(h_addr + s * 4096, kTileM * 16, 128);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint64_t bdesc = make_kc16_desc(sb + j * kNC * 16, kDP * 16, 128);
-            umma_bf16_ss(tmem_base + C::kTmemY + j * kNC, adesc, bdesc, idesc_y, (c | s) != 0);
+          for (int kk = 0; kk < C::kW2StageK; ++kk) {
+            const int kstep = s * C::kW2StageK + kk;
+            const uint64_t adesc = make_kc16_desc(h_addr + kstep * 4096, kTileM * 16, 128);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t bdesc =
+                  make_kc16_desc(sb + kk * (2 * kDP * 16) + j * kNC * 16, kDP * 16, 128);
+              umma_bf16_ss(tmem_base + C::kTmemY + j * kNC, adesc, bdesc, idesc_y, (c | kstep) != 0);
+            }
           }
-          umma_commit(&empty[slot]);
+          release(&empty[slot]);
           if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
         }
         umma_commit(&hs_free[b]);
       };
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
-        mbar_wait(a_full, ti & 1);
+      for (int ti = 0; ti < rounds; ++ti) {
+        { TRACE_T0(); mbar_wait(a_full, ti & 1); TRACE_ADD(t_afull); }
         tc_fence_after();
         gemm1(n);
         for (int c = 0; c < nchunks; ++c) {
@@ -488,7 +592,9 @@ ffn_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ 
             umma_commit(a_empty);          // all GEMM1s of this tile issued: x tile reusable
           }
           if (c == 0) {
+            TRACE_T0();
             mbar_wait(y_empty, (ti & 1) ^ 1);  // previous tile's Y drained by the epilogue
+            TRACE_ADD(t_yempty);
             tc_fence_after();
           }
           gemm2(n + c, c);
@@ -496,50 +602,100 @@ ffn_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ 
         umma_commit(y_full);
         n += nchunks;
       }
+#ifdef DCB_TRACE
+      if (blockIdx.x < 256) {
+        unsigned long long* tr = g_ffn_trace + blockIdx.x * 16;
+        tr[0] = clock64() - t_begin; tr[1] = t_hfree; tr[2] = t_full; tr[3] = t_hsfull;
+        tr[4] = t_issue; tr[5] = t_afull; tr[6] = t_yempty; tr[7] = rounds;
+      }
+#endif
     }
+   }
   } else {
-    // ------------------------------------------------------------- epilogue (4 warps)
-    const int q = warp & 3;
+    // ------------------------------------------------------------- epilogue warps
+    const int q = warp & 3;            // TMEM lane quarter
     const int r = q * 32 + lane;
     const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t ti = 0, n = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
-      for (int c = 0; c < nchunks; ++c, ++n) {
-        const uint32_t b = n & 1;
-        mbar_wait(h_full, n & 1);
-        tc_fence_after();
-        mbar_wait(&hs_free[b], ((n >> 1) & 1) ^ 1);
-        uint4* hrow = reinterpret_cast<uint4*>(sH + b * C::kHBytes) + r;
-        const float* bias = sB1 + c * kFFChunk;
-#pragma unroll 2
-        for (int cb = 0; cb < kFFChunk / 16; ++cb) {
-          uint32_t acc[16];
-          tmem_ld16(tmem_row + C::kTmemH + cb * 16, acc);
-          tmem_ld_wait();
-          float v[16];
+    if (warp < 12) {
+      setmaxnreg_dec<96>();
+      // hidden-chunk epilogue: TMEM -> +b1, relu -> bf16 -> smem operand of GEMM2
+      const int half = (warp - 4) >> 2;  // which 64 columns of the hidden chunk
+      uint32_t n = 0;
+      long long t_hfull = 0, t_hsfree = 0, t_body = 0;
+      for (int ti = 0; ti < rounds; ++ti) {
+        for (int c = 0; c < nchunks; ++c, ++n) {
+          const uint32_t b = n & 1;
+          TRACE_T0();
+          mbar_wait(h_full, n & 1);
+          TRACE_ADD(t_hfull);
+          tc_fence_after();
+          mbar_wait(&hs_free[b], ((n >> 1) & 1) ^ 1);
+          TRACE_ADD(t_hsfree);
+          uint4* hrow = reinterpret_cast<uint4*>(sH + b * C::kHBytes) + r;
+          const float* bias = sB1 + c * kFFChunk;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(acc[i]) + bias[cb * 16 + i], 0.f);
-          hrow[(size_t)(cb * 2) * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                       pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          hrow[(size_t)(cb * 2 + 1) * kTileM] =
-              make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
-                         pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+          for (int cc = 0; cc < kFFChunk / 32; ++cc) {
+            const int cb = half * (kFFChunk / 32) + cc;
+            uint32_t acc[16];
+            tmem_ld16(tmem_row + C::kTmemH + cb * 16, acc);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(acc[i]) + bias[cb * 16 + i], 0.f);
+            hrow[(size_t)(cb * 2) * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                         pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            hrow[(size_t)(cb * 2 + 1) * kTileM] =
+                make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                           pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+          }
+          tc_fence_before();
+          mbar_arrive(h_free);
+          fence_proxy_async_smem();
+          mbar_arrive(&hs_full[b]);
+          TRACE_ADD(t_body);
         }
-        tc_fence_before();
-        mbar_arrive(h_free);
-        fence_proxy_async_smem();
-        mbar_arrive(&hs_full[b]);
       }
-      mbar_wait(y_full, ti & 1);
-      tc_fence_after();
-      const RowStats st = row_epilogue_pass1(epi, tmem_row + C::kTmemY, tile, r);
-      tc_fence_before();
-      mbar_arrive(y_empty);
-      if (epi.ln_g && epi.xb) row_epilogue_pass2<false>(epi, tile, r, st.mean, st.rstd);
+#ifdef DCB_TRACE
+      if (warp == 4 && lane == 0 && blockIdx.x < 256) {
+        unsigned long long* tr = g_ffn_trace + blockIdx.x * 16;
+        tr[8] = t_hfull; tr[9] = t_hsfree; tr[10] = t_body;
+      }
+#endif
+    } else {
+      setmaxnreg_inc<216>();
+      // row epilogue of each finished tile (overlaps the next tile's GEMMs)
+      long long t_yfull = 0, t_row = 0;
+      for (int ti = 0; ti < rounds; ++ti) {
+        const int tile_raw = ti * (int)gridDim.x + (int)blockIdx.x;
+        const bool valid = tile_raw < ntiles;
+        RowPrefetch pf;
+        if (valid) row_prefetch_start(epi, tile_raw, r, pf);
+        TRACE_T0();
+        mbar_wait(y_full, ti & 1);
+        TRACE_ADD(t_yfull);
+        tc_fence_after();
+        if (valid) {
+          const RowStats st = row_epilogue_pass1(epi, tmem_row + C::kTmemY, tile_raw, r, pf);
+          tc_fence_before();
+          mbar_arrive(y_empty);
+          if (epi.ln_g && epi.xb) row_epilogue_pass2<false>(epi, tile_raw, r, st.mean, st.rstd);
+        } else {
+          tc_fence_before();
+          mbar_arrive(y_empty);
+        }
+        TRACE_ADD(t_row);
+      }
+#ifdef DCB_TRACE
+      if (warp == 12 && lane == 0 && blockIdx.x < 256) {
+        unsigned long long* tr = g_ffn_trace + blockIdx.x * 16;
+        tr[11] = t_yfull; tr[12] = t_row;
+      }
+#endif
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
@@ -591,37 +747,48 @@ band_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
   const int kcol = (2 + head) * kDHP, vcol = (4 + head) * kDHP, qcol = head * kDHP;
   const int tok0 = w * L;
 
-  // stage K, V: 16-byte chunks, (row, chunk) -> smem[row*304 + chunk*16]
+  // stage K, V with cp.async (all copies in flight at once): 16-byte chunks,
+  // (row, chunk) -> smem[row*304 + chunk*16]; rows >= L are zero filled.
   for (int idx = threadIdx.x; idx < Lp * (kDHP / 8) * 2; idx += blockDim.x) {
     const int which = idx / (Lp * (kDHP / 8));
     const int rem = idx - which * (Lp * (kDHP / 8));
     const int ch = rem / Lp, row = rem - ch * Lp;  // row fastest: coalesced 16 B chunks
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (row < L)
-      val = *reinterpret_cast<const uint4*>(
-          qkv + img_off(tok0 + row, (which ? vcol : kcol) + ch * 8, qkv_chunks));
-    *reinterpret_cast<uint4*>((which ? sV : sK) + (size_t)row * kAttStride + ch * 8) = val;
+    __nv_bfloat16* dst = (which ? sV : sK) + (size_t)row * kAttStride + ch * 8;
+    if (row < L) {
+      const __nv_bfloat16* src = qkv + img_off(tok0 + row, (which ? vcol : kcol) + ch * 8, qkv_chunks);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
   }
-  __syncthreads();
+  asm volatile("cp.async.commit_group;" ::: "memory");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int band = win > 0 ? win : L;  // attn_win_size None/0 => full attention
   constexpr float kLog2e = 1.4426950408889634f;
 
-  for (int qb = warp; qb * 16 < L; qb += 4) {
-    const int i0 = qb * 16;
-    // Q fragments for 9 k-steps: rows i0+g, i0+g+8 (zero beyond L)
-    uint32_t qa[kDHP / 16][4];
-    const int r0 = i0 + g, r1 = i0 + g + 8;
+  // Q fragments for 9 k-steps: rows i0+g, i0+g+8 (zero beyond L), straight from global
+  uint32_t qa[kDHP / 16][4];
+  auto load_q = [&](int qb) {
+    const int r0 = qb * 16 + g, r1 = r0 + 8;
 #pragma unroll
     for (int ks = 0; ks < kDHP / 16; ++ks) {
       const int c0 = qcol + ks * 16 + 2 * t;
-      qa[ks][0] = r0 < L ? *reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r0, c0, qkv_chunks)) : 0u;
-      qa[ks][1] = r1 < L ? *reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r1, c0, qkv_chunks)) : 0u;
-      qa[ks][2] = r0 < L ? *reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r0, c0 + 8, qkv_chunks)) : 0u;
-      qa[ks][3] = r1 < L ? *reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r1, c0 + 8, qkv_chunks)) : 0u;
+      qa[ks][0] = r0 < L ? __ldg(reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r0, c0, qkv_chunks))) : 0u;
+      qa[ks][1] = r1 < L ? __ldg(reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r1, c0, qkv_chunks))) : 0u;
+      qa[ks][2] = r0 < L ? __ldg(reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r0, c0 + 8, qkv_chunks))) : 0u;
+      qa[ks][3] = r1 < L ? __ldg(reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r1, c0 + 8, qkv_chunks))) : 0u;
     }
+  };
+  if (warp * 16 < L) load_q(warp);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  for (int qb = warp; qb * 16 < L; qb += 4) {
+    const int i0 = qb * 16;
+    const int r0 = i0 + g, r1 = i0 + g + 8;
+    if (qb != warp) load_q(qb);
     float o[kDHP / 8][4];
 #pragma unroll
     for (int nt = 0; nt < kDHP / 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
@@ -822,18 +989,29 @@ cudaError_t kernels_init() {
   e = cudaFuncSetAttribute(gemm_kernel<2, EPI_ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            GemmCfg<2>::kSmemBytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           FfnCfg::kSmemBytes);
+  e = cudaFuncSetAttribute(ffn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(ffn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(ffn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(embed_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(band_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            2 * 256 * kAttStride * 2);
   return e;
 }
 
+size_t embed_smem_bytes(int R, int echunks, int table_elems) {
+  return (size_t)((table_elems * 2 + 15) & ~15) + ((echunks * 8 * sizeof(EmbedCol) + 15) & ~(size_t)15) +
+         (size_t)R * kTileM * 2;
+}
+
 void launch_embed(const float* rows, int R, int L, int M, int ntiles, int echunks,
-                  const EmbedCol* cols, const __nv_bfloat16* tables, __nv_bfloat16* emb,
-                  int* status, cudaStream_t st) {
-  embed_rows_kernel<<<ntiles, 256, 0, st>>>(rows, R, L, M, echunks, cols, tables, emb, status);
+                  const EmbedCol* cols, const EmbedRow* rowmeta, const __nv_bfloat16* tables,
+                  int table_elems, __nv_bfloat16* emb, int* status, cudaStream_t st) {
+  embed_rows_kernel<<<ntiles, 256, embed_smem_bytes(R, echunks, table_elems), st>>>(
+      rows, R, L, M, echunks, cols, rowmeta, tables, table_elems, emb, status);
 }
 
 void launch_gemm_row(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int ksteps, int ntiles,
@@ -859,10 +1037,54 @@ void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int w
   band_attention_kernel<<<nwindows * 2, 128, smem, st>>>(qkv, att, L, win, nwindows);
 }
 
+static int g_ffn_cluster = 0;
+
+template <int CS>
+static void launch_ffn_cs(const __nv_bfloat16* a_img, const uint8_t* w_img, const float* b1, int ff,
+                          int ntiles, const RowEpi& epi, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kFfnThreads);
+  cfg.dynamicSmemBytes = FfnCfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // persistent grid = as many clusters as can be co-resident (GPC sizes strand a few SMs for CS=4)
+  static int max_clusters = 0;
+  if (!max_clusters) {
+    cfg.gridDim = dim3(num_sms() / CS * CS);
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, ffn_kernel<CS>, &cfg) != cudaSuccess || nc <= 0) nc = num_sms() / CS;
+    max_clusters = nc;
+    if (getenv("DCB_VERBOSE")) fprintf(stderr, "[dcb200] ffn cluster size %d: %d co-resident clusters\n", CS, nc);
+  }
+  int clusters = (ntiles + CS - 1) / CS;
+  if (clusters > max_clusters) clusters = max_clusters;
+  cfg.gridDim = dim3(clusters * CS);
+  cudaLaunchKernelEx(&cfg, ffn_kernel<CS>, a_img, w_img, b1, ff, ntiles, epi);
+}
+
 void launch_ffn(const __nv_bfloat16* a_img, const uint8_t* w_img, const float* b1, int ff, int ntiles,
                 const RowEpi& epi, cudaStream_t st) {
-  const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  ffn_kernel<<<grid, 192, FfnCfg::kSmemBytes, st>>>(a_img, w_img, b1, ff, ntiles, epi);
+  if (!g_ffn_cluster) {
+    const char* env = getenv("DCB_FFN_CLUSTER");
+    g_ffn_cluster = env ? atoi(env) : 1;   // measured: multicast does not pay here (smem-bound, not L2-bound)
+    if (g_ffn_cluster != 1 && g_ffn_cluster != 2 && g_ffn_cluster != 4) g_ffn_cluster = 1;
+  }
+  switch (g_ffn_cluster) {
+    case 1: launch_ffn_cs<1>(a_img, w_img, b1, ff, ntiles, epi, st); break;
+    case 2: launch_ffn_cs<2>(a_img, w_img, b1, ff, ntiles, epi, st); break;
+    default: launch_ffn_cs<4>(a_img, w_img, b1, ff, ntiles, epi, st); break;
+  }
+}
+
+int read_ffn_trace(unsigned long long* out, int n) {
+  if (n > 256 * 16) n = 256 * 16;
+  return cudaMemcpyFromSymbol(out, g_ffn_trace, (size_t)n * sizeof(unsigned long long)) == cudaSuccess ? 0 : -1;
 }
 
 void launch_head(const HeadParams& p, int ntiles, cudaStream_t st) {

@@ -8,9 +8,10 @@ namespace dcb {
 
 cudaError_t kernels_init();
 
+size_t embed_smem_bytes(int R, int echunks, int table_elems);
 void launch_embed(const float* rows, int R, int L, int M, int ntiles, int echunks,
-                  const EmbedCol* cols, const __nv_bfloat16* tables, __nv_bfloat16* emb,
-                  int* status, cudaStream_t st);
+                  const EmbedCol* cols, const EmbedRow* rowmeta, const __nv_bfloat16* tables,
+                  int table_elems, __nv_bfloat16* emb, int* status, cudaStream_t st);
 // D = A * B^T with the 288-wide row epilogue (condenser + pos-enc, attention out-proj).
 void launch_gemm_row(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int ksteps, int ntiles,
                      const RowEpi& epi, cudaStream_t st);
@@ -21,6 +22,7 @@ void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int w
                       cudaStream_t st);
 void launch_ffn(const __nv_bfloat16* a_img, const uint8_t* w_img, const float* b1, int ff, int ntiles,
                 const RowEpi& epi, cudaStream_t st);
+int read_ffn_trace(unsigned long long* out, int n);
 void launch_head(const HeadParams& p, int ntiles, cudaStream_t st);
 
 }  // namespace dcb

@@ -66,7 +66,7 @@ class DcbTensor(ctypes.Structure):
 # Every symbol include/dcb200.h declares; tests check the built library exports all of them.
 ABI_SYMBOLS = (
     "dcb_create", "dcb_load_weights", "dcb_forward", "dcb_last_forward_ms",
-    "dcb_last_forward_launches", "dcb_set_profile", "dcb_get_profile", "dcb_set_debug", "dcb_debug_residual", "dcb_alloc_host",
+    "dcb_last_forward_launches", "dcb_set_profile", "dcb_get_profile", "dcb_set_debug", "dcb_debug_residual", "dcb_debug_trace", "dcb_alloc_host",
     "dcb_free_host", "dcb_alloc_device", "dcb_free_device", "dcb_memcpy_h2d", "dcb_memcpy_d2h",
     "dcb_synchronize", "dcb_last_error", "dcb_version", "dcb_destroy",
 )

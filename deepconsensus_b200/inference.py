@@ -1,0 +1,120 @@
+"""Host driver pieces of `deepconsensus run` that touch the model (mirror of the hot-path part of
+`deepconsensus/inference/quick_inference.py`).
+
+  InferenceOptions        quick_inference.py:238-275 (same field names)
+  batch_examples          quick_inference.py:304-338
+  run_model_on_examples   quick_inference.py:341-415   <- the drop-in: same signature, same return
+  initialize_model        quick_inference.py:485-532   (weights come from an .npz / dict instead of a
+                                                         TF checkpoint)
+
+`run_model_on_examples` hands the stacked rows to the CUDA engine, which returns the per-position
+base and quality characters directly (the device epilogue does argmax / Phred / calibration /
+clip / round, quick_inference.py:377-389); the host only slices bytes into `DCModelOutput`s.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Any, Dict, Iterable, Iterator, List, Optional, Tuple, Union
+
+import numpy as np
+
+from deepconsensus_b200 import calibration as calibration_lib
+from deepconsensus_b200 import constants
+from deepconsensus_b200 import engine as engine_lib
+from deepconsensus_b200 import params as params_lib
+from deepconsensus_b200 import stitch_utils
+from deepconsensus_b200 import weights as weights_lib
+
+
+@dataclasses.dataclass
+class InferenceOptions:
+  """Options used across the inference stages (quick_inference.py:238-275)."""
+  max_length: int
+  example_height: int
+  max_passes: int
+  min_quality: int
+  min_length: int
+  batch_size: int
+  use_ccs_bq: bool
+  cpus: int
+  skip_windows_above: int
+  use_saved_model: bool
+  max_base_quality: int
+  dc_calibration_values: calibration_lib.QualityCalibrationValues
+  ccs_calibration_values: calibration_lib.QualityCalibrationValues
+
+
+def format_rows(subreads: np.ndarray, params: params_lib.Params) -> np.ndarray:
+  """Shape check only: the PW/IP/SN clipping of data_providers.format_rows (:128-184) runs on the
+  device inside the embedding kernel, so rows are passed through unmodified."""
+  rows = np.asarray(subreads, dtype=constants.NP_DATA_TYPE)
+  if rows.ndim == 2:
+    rows = rows[..., None]
+  if rows.shape != (params.total_rows, params.max_length, 1):
+    raise ValueError("expected subreads of shape %s, got %s" %
+                     ((params.total_rows, params.max_length, 1), rows.shape))
+  return rows
+
+
+def process_feature_dict(features: Dict[str, Any], params: params_lib.Params) -> Dict[str, Any]:
+  """data_providers.process_feature_dict (:187-223) without TensorFlow."""
+  return {
+      "rows": format_rows(features["subreads"], params),
+      "label": np.array([]),
+      "num_passes": features["subreads/num_passes"],
+      "window_pos": features["window_pos"],
+      "name": features["name"],
+      "ccs_base_quality_scores": features["ccs_base_quality_scores"],
+      "ec": features["ec"],
+      "np_num_passes": features["np_num_passes"],
+      "rq": features["rq"],
+      "rg": features["rg"],
+  }
+
+
+def batch_examples(feature_dicts: List[Dict[str, Any]], model_params: params_lib.Params,
+                   options: InferenceOptions) -> Iterator[Dict[str, Any]]:
+  """Stack values for each feature, `options.batch_size` windows at a time (quick_inference.py:304-338)."""
+  processed = [process_feature_dict(fd, model_params) for fd in feature_dicts]
+  for i in range(0, len(processed), options.batch_size):
+    one_batch = processed[i:i + options.batch_size]
+    yield {key: np.stack([x[key] for x in one_batch]) for key in constants.DC_FEATURES}
+
+
+def run_model_on_examples(feature_dicts: List[Dict[str, Any]], model: engine_lib.B200Model,
+                          model_params: params_lib.Params,
+                          options: InferenceOptions) -> List[stitch_utils.DCModelOutput]:
+  """Runs the model over windows and returns one DCModelOutput per window (quick_inference.py:341-415)."""
+  predictions: List[stitch_utils.DCModelOutput] = []
+  for data in batch_examples(feature_dicts, model_params, options):
+    out = model.forward(data["rows"])
+    bases, quals = out["bases"], out["quals"]
+    for i in range(bases.shape[0]):
+      predictions.append(stitch_utils.DCModelOutput(
+          window_pos=data["window_pos"][i], molecule_name=data["name"][i], ec=data["ec"][i],
+          np_num_passes=data["np_num_passes"][i], rq=data["rq"][i], rg=data["rg"][i],
+          sequence=bases[i].tobytes().decode("ascii"),
+          quality_string=quals[i].tobytes().decode("ascii")))
+  return predictions
+
+
+def load_weights_npz(path: str) -> weights_lib.Weights:
+  """Variables exported as an .npz keyed by the checkpoint variable names."""
+  with np.load(path) as z:
+    return {k: z[k] for k in z.files}
+
+
+def initialize_model(checkpoint_path: str, params: params_lib.Params, options: InferenceOptions,
+                     weights: Optional[weights_lib.Weights] = None, device: int = 0
+                     ) -> Tuple[engine_lib.B200Model, params_lib.Params]:
+  """Builds the engine for `params` and loads variables (quick_inference.py:485-532).
+
+  `checkpoint_path` may point at an .npz export of the checkpoint's variables; `weights` overrides it.
+  """
+  params_lib.modify_params(params, max_length=options.max_length, is_training=False)
+  if weights is None:
+    weights = load_weights_npz(checkpoint_path)
+  model = engine_lib.B200Model(params, weights, max_batch=options.batch_size, device=device,
+                               max_base_quality=options.max_base_quality,
+                               calibration=options.dc_calibration_values)
+  return model, params

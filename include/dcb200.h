@@ -115,6 +115,10 @@ int dcb_get_profile(dcb_engine* e, float* ffn_ms_total, int32_t* ffn_launches, i
 int dcb_set_debug(dcb_engine* e, int32_t enabled);
 int dcb_debug_residual(dcb_engine* e, int32_t stage, float* out, int64_t out_elems);
 
+/* Developer hook: cycle counters of the last ffn_kernel launch (only meaningful in a -DDCB_TRACE
+ * build; 16 uint64 per CTA). */
+int dcb_debug_trace(uint64_t* out, int32_t n);
+
 /* Pinned host memory helpers (for callers that want async H2D/D2H). */
 int dcb_alloc_host(size_t bytes, void** out);
 int dcb_free_host(void* p);
