@@ -94,7 +94,8 @@ def test_ragged_batches_chunks_and_determinism(engine_mod):
   w = weights_lib.init_weights(p, seed=10)
   rows = synthetic.make_rows(p, 37, seed=11)
   whole = _check(engine_mod, p, w, rows)
-  model = engine_mod.B200Model(p, w, max_batch=16, chunk_tiles=3)     # 3 engine calls, several chunks each
+  model = engine_mod.B200Model(p, w, max_batch=16, chunk_tiles=3,     # 3 engine calls, several chunks each
+                               calibration=calibration.parse_calibration_string(CAL))
   split = model.forward(rows, want_logits=True, strict_input=False)
   again = model.forward(rows, want_logits=True, strict_input=False)
   one = model.forward(rows[:1], want_logits=True, strict_input=False)
