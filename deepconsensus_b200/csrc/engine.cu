@@ -26,6 +26,7 @@ struct LayerDev {
   __nv_bfloat16* wqkv = nullptr;  // 2 groups x [36][432][8]
   __nv_bfloat16* wo = nullptr;    // [36][288][8]
   uint8_t* wffn = nullptr;        // per ff chunk: [36][128][8] then [16][288][8]
+  uint8_t* wffn2 = nullptr;       // CTA-pair image: per (chunk, rank): [36][64][8] then [16][144][8]
   float* b1 = nullptr;            // [ff]
   float* b2 = nullptr;            // [288] (gain folded)
   float* ln_g[2] = {nullptr, nullptr};  // pre-norm gamma/beta of the attention / FFN sub-layer
@@ -44,6 +45,7 @@ struct dcb_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool weights_loaded = false;
   bool debug = false;
+  bool ffn_pair = true;
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // around every ffn_kernel launch
   size_t prof_used = 0;
@@ -191,6 +193,7 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
          4 * cfg->sn_hidden_size;
   e->Epad = (e->E + 15) / 16 * 16;
   e->echunks = e->Epad / 8;
+  if (const char* env = getenv("DCB_FFN_PAIR")) e->ffn_pair = atoi(env) != 0;
   int ct = cfg->chunk_tiles;
   if (const char* env = getenv("DCB_CHUNK_TILES")) ct = atoi(env);
   if (ct <= 0) ct = 8 * e->num_sms;   // measured: larger chunks win (kernels are not DRAM-bound)
@@ -261,6 +264,7 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
     Tab& tb = tabs[t];
     tb.data = tm.get(std::string("model/") + tb.layer + "/embeddings", {tb.vocab, tb.width}, &rc);
     if (rc) return rc;
+    while (blob.size() % 8) blob.push_back(__float2bfloat16(0.f));   // 16-byte aligned table rows (width-8 fast path)
     tb.off = (int)blob.size();
     const float scale = sqrtf((float)tb.width);
     for (int v = 0; v < tb.vocab; ++v)
@@ -406,6 +410,27 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
       if ((rc = upload(e, &dptr, img))) return rc;
       ld.wffn = reinterpret_cast<uint8_t*>(dptr);
     }
+    {
+      // CTA-pair image: rank r holds hidden units c*128 + r*64 + [0,64) of W1 and, for each 144-wide
+      // N chunk j of W2, output rows j*144 + r*72 + [0,72)
+      std::vector<__nv_bfloat16> img;
+      img.reserve((size_t)ff * kDP * 2);
+      for (int ch = 0; ch < ff / kFFChunk; ++ch)
+        for (int rk = 0; rk < 2; ++rk) {
+          auto p1 = pack_b(kDP, kFFChunk / 2, [&](int k, int nn) {
+            return k < kD ? w1[(size_t)k * ff + ch * kFFChunk + rk * (kFFChunk / 2) + nn] : 0.f;
+          });
+          auto p2 = pack_b(kFFChunk, kDP / 2, [&](int k, int nn) {
+            const int col = (nn / (kNC / 2)) * kNC + rk * (kNC / 2) + nn % (kNC / 2);
+            return col < kD ? w2[(size_t)(ch * kFFChunk + k) * kD + col] * alpha1 : 0.f;
+          });
+          img.insert(img.end(), p1.begin(), p1.end());
+          img.insert(img.end(), p2.begin(), p2.end());
+        }
+      __nv_bfloat16* dptr = nullptr;
+      if ((rc = upload(e, &dptr, img))) return rc;
+      ld.wffn2 = reinterpret_cast<uint8_t*>(dptr);
+    }
     if ((rc = upload(e, &ld.b1, std::vector<float>(b1, b1 + ff)))) return rc;
     if ((rc = upload(e, &ld.b2, pad288(b2, alpha1)))) return rc;
   }
@@ -513,7 +538,8 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
         }
         CU(e, cudaEventRecord(e->prof_events[e->prof_used].first, st));
       }
-      launch_ffn(e->d_xb, ld.wffn, ld.b1, c.filter_size, T, ef, st);
+      if (e->ffn_pair) launch_ffn_pair(e->d_xb, ld.wffn2, ld.b1, c.filter_size, T, ef, st);
+      else launch_ffn(e->d_xb, ld.wffn, ld.b1, c.filter_size, T, ef, st);
       if (e->profile) {
         CU(e, cudaEventRecord(e->prof_events[e->prof_used].second, st));
         ++e->prof_used;

@@ -65,24 +65,33 @@ embed_rows_kernel(const float* __restrict__ rows, int R, int L, int M, int echun
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int kc = idx / kTileM;
     const int r = idx % kTileM;
-    uint32_t packed[4];
+    uint4 val;
+    const EmbedCol c0 = s_cols[kc * 8];
+    if (c0.width == 8 && c0.col == 0 && c0.src_row >= 0) {
+      // fast path: the whole 16-byte chunk is one width-8 embedding row (bases/pw/ip/ccs/bq/sn)
+      const int id = s_ids[c0.src_row * kTileM + r];
+      val = *reinterpret_cast<const uint4*>(s_tab + c0.table_off + id * 8);
+    } else {
+      uint32_t packed[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t pr = 0;
+      for (int j = 0; j < 4; ++j) {
+        uint32_t pr = 0;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const EmbedCol c = s_cols[kc * 8 + 2 * j + h];
-        uint32_t bits = 0;
-        if (c.src_row >= 0) {
-          const int id = s_ids[c.src_row * kTileM + r];
-          bits = __bfloat16_as_ushort(s_tab[c.table_off + id * c.width + c.col]);
+        for (int h = 0; h < 2; ++h) {
+          const EmbedCol c = s_cols[kc * 8 + 2 * j + h];
+          uint32_t bits = 0;
+          if (c.src_row >= 0) {
+            const int id = s_ids[c.src_row * kTileM + r];
+            bits = __bfloat16_as_ushort(s_tab[c.table_off + id * c.width + c.col]);
+          }
+          pr |= bits << (16 * h);
         }
-        pr |= bits << (16 * h);
+        packed[j] = pr;
       }
-      packed[j] = pr;
+      val = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
     uint4* dst = reinterpret_cast<uint4*>(emb + ((size_t)tile * echunks + kc) * kTileM * 8) + r;
-    *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    *dst = val;
   }
 }
 
@@ -140,7 +149,8 @@ __device__ __forceinline__ void row_prefetch_start(const RowEpi& e, int tile, in
 }
 
 __device__ __forceinline__ RowStats row_epilogue_pass1(const RowEpi& e, uint32_t tmem_row_base,
-                                                       int tile, int r, RowPrefetch& pf) {
+                                                       int tile, int r, RowPrefetch& pf,
+                                                       long long* t_ldtm = nullptr) {
   const int tok = tile * kTileM + r;
   const int l = tok % e.L;
   float4* xrow = reinterpret_cast<float4*>(e.x + (size_t)tile * x_image_elems()) + r;
@@ -151,6 +161,9 @@ __device__ __forceinline__ RowStats row_epilogue_pass1(const RowEpi& e, uint32_t
 #pragma unroll
   for (int cb = 0; cb < kDP / 16; ++cb) {
     uint32_t acc[16];
+#ifdef DCB_TRACE
+    const long long _tl0 = clock64();
+#endif
     tmem_ld16(tmem_row_base + cb * 16, acc);
     float v[16];
     if (e.has_xold) {
@@ -165,6 +178,9 @@ __device__ __forceinline__ RowStats row_epilogue_pass1(const RowEpi& e, uint32_t
       for (int i = 0; i < 16; ++i) v[i] = 0.f;
     }
     tmem_ld_wait();
+#ifdef DCB_TRACE
+    if (t_ldtm) *t_ldtm += clock64() - _tl0;
+#endif
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int col = cb * 16 + i;
@@ -703,6 +719,401 @@ ffn_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ 
 }
 
 // =====================================================================================
+// fused FFN, CTA-pair version (tcgen05 cta_group::2)
+// =====================================================================================
+// Two CTAs (a cluster of 2 = one TPC's SM pair) process two 128-token tiles together with M=256
+// UMMAs issued by the leader (cluster rank 0).  Each CTA keeps its own x tile, hidden chunk and
+// accumulators (rows of D split across the two TMEMs) but holds only HALF of every weight chunk
+// (N/2 rows of B), so per SM the weight bytes pulled from L2 and written to / re-read from shared
+// memory are halved and every MMA instruction carries twice the work.
+//
+// Per-rank weight image (w2img): for ff chunk c and rank r at offset (2c + r) * 73728 B:
+//   [W1 half: 36 k-chunks x 64 hidden rows x 16 B][W2 half: 16 k-chunks x 144 output rows x 16 B]
+// W1 half r holds hidden units c*128 + r*64 + [0,64); W2 half r holds, for each 144-wide N chunk j,
+// output rows j*144 + r*72 + [0,72).
+//
+// Cross-CTA protocol (leader L, peer P):
+//   full[slot] (L): local producer arrive.expect_tx + P's relay thread arrives remotely once P's own
+//                   copy of the stage has landed (count 2).      full[slot] (P): local only.
+//   empty[slot], a_empty, h_full, hs_free[2], y_full: tcgen05.commit multicast to both CTAs.
+//   a_full (L): local expect_tx + remote arrive from P's relay (count 2).
+//   h_free, hs_full[2], y_empty (L): one arrive per epilogue warp of BOTH CTAs (P's remotely).
+struct Ffn2Cfg {
+  static constexpr int kABytes = (kDP / 8) * kTileM * 16;            // 73728
+  static constexpr int kHBytes = (kFFChunk / 8) * kTileM * 16;       // 32768
+  static constexpr int kSlotBytes = 18432;
+  static constexpr int kSlots = 4;
+  static constexpr int kW1Rows = kFFChunk / 2;                       // 64 hidden rows per CTA
+  static constexpr int kW1StageK = 9;
+  static constexpr int kW1Stages = 2;
+  static constexpr int kW1StageBytes = kW1StageK * 2 * kW1Rows * 16; // 18432
+  static constexpr int kW2Rows = kDP / 2;                            // 144 output rows per CTA
+  static constexpr int kW2StageK = 4;
+  static constexpr int kW2Stages = 2;
+  static constexpr int kW2StageBytes = kW2StageK * 2 * kW2Rows * 16; // 18432
+  static constexpr int kHalfChunkBytes = kW1Stages * kW1StageBytes + kW2Stages * kW2StageBytes;  // 73728
+  static constexpr int kTmemY = 0;
+  static constexpr int kTmemH = kDP;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kMaxFF = 2048;
+  static constexpr int kOffA = 0;
+  static constexpr int kOffH = kABytes;
+  static constexpr int kOffRing = kOffH + 2 * kHBytes;
+  static constexpr int kOffB1 = kOffRing + kSlots * kSlotBytes;
+  static constexpr int kOffBars = kOffB1 + kMaxFF * 4;
+  static constexpr int kSmemBytes = kOffBars + 256;
+};
+static_assert(Ffn2Cfg::kSmemBytes <= 232448, "FFN pair shared memory budget");
+static_assert(Ffn2Cfg::kW1Stages * Ffn2Cfg::kW1StageK == kDP / 16 && Ffn2Cfg::kW2Stages * Ffn2Cfg::kW2StageK == kFFChunk / 16, "stages");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFfnThreads, 1)
+ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ w2img,
+                const float* __restrict__ b1, int ff, int ntiles, RowEpi epi, int stagger_cycles) {
+  using C = Ffn2Cfg;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem + C::kOffA;
+  uint8_t* sH = smem + C::kOffH;
+  uint8_t* sRing = smem + C::kOffRing;
+  float* sB1 = reinterpret_cast<float*>(smem + C::kOffB1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
+  uint64_t* full = bars;                   // [kSlots]
+  uint64_t* empty = bars + C::kSlots;      // [kSlots]
+  uint64_t* a_full = bars + 2 * C::kSlots;
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* h_full = a_full + 2;
+  uint64_t* h_free = a_full + 3;
+  uint64_t* hs_full = a_full + 4;          // [2]
+  uint64_t* hs_free = a_full + 6;          // [2]
+  uint64_t* y_full = a_full + 8;
+  uint64_t* y_empty = a_full + 9;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 10);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nchunks = ff / kFFChunk;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int npairs = (int)gridDim.x >> 1;
+  const int pair = (int)blockIdx.x >> 1;
+  const int tile_pairs = (ntiles + 1) >> 1;
+  const int rounds = (tile_pairs + npairs - 1) / npairs;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::kSlots; ++i) {
+      mbar_init(&full[i], leader ? 2 : 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(a_full, leader ? 2 : 1);
+    mbar_init(a_empty, 1);
+    mbar_init(h_full, 1);
+    mbar_init(h_free, 16);         // 8 hidden-epilogue warps x 2 CTAs (used in the leader only)
+    mbar_init(&hs_full[0], 16);
+    mbar_init(&hs_full[1], 16);
+    mbar_init(&hs_free[0], 1);
+    mbar_init(&hs_free[1], 1);
+    mbar_init(y_full, 1);
+    mbar_init(y_empty, 8);         // 4 row-epilogue warps x 2 CTAs (leader only)
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < ff; i += blockDim.x) sB1[i] = b1[i];
+  if (warp == 1) tmem_alloc_pair(tmem_holder, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  // a tile index for this CTA in round ti (clamped: an out-of-range CTA recomputes the last tile)
+  auto tile_of = [&](int ti) { return ((ti * npairs + pair) << 1) + (int)rank; };
+
+  // De-synchronise the pairs: in lock step every CTA hits its residual read / write burst at the
+  // same moment and HBM (not the tensor pipe) sets the pace; a start offset spreads the bursts.
+  if (stagger_cycles > 0) {
+    const long long t0 = clock64();
+    const long long wait = (long long)(pair & 7) * stagger_cycles;
+    while (clock64() - t0 < wait) {
+    }
+  }
+
+  if (warp < 4) {
+   setmaxnreg_dec<64>();
+   if (warp == 0) {
+    // ------------------------------------------------------------- producer (both CTAs, own halves)
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      auto push = [&](const uint8_t* src, uint32_t bytes) {
+        mbar_wait(&empty[slot], phase ^ 1);
+        mbar_arrive_expect_tx(&full[slot], bytes);
+        bulk_g2s(sRing + slot * C::kSlotBytes, src, bytes, &full[slot]);
+        if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+      };
+      auto half = [&](int c) { return w2img + ((size_t)c * 2 + rank) * C::kHalfChunkBytes; };
+      auto push_w1 = [&](int c) {
+        for (int s = 0; s < C::kW1Stages; ++s) push(half(c) + s * C::kW1StageBytes, C::kW1StageBytes);
+      };
+      auto push_w2 = [&](int c) {
+        const uint8_t* src = half(c) + C::kW1Stages * C::kW1StageBytes;
+        for (int s = 0; s < C::kW2Stages; ++s) push(src + s * C::kW2StageBytes, C::kW2StageBytes);
+      };
+      for (int ti = 0; ti < rounds; ++ti) {
+        const int tile = min(tile_of(ti), ntiles - 1);
+        mbar_wait(a_empty, (ti & 1) ^ 1);
+        mbar_arrive_expect_tx(a_full, C::kABytes);
+        bulk_g2s(sA, reinterpret_cast<const uint8_t*>(a_img) + (size_t)tile * C::kABytes, C::kABytes, a_full);
+        push_w1(0);
+        for (int c = 0; c < nchunks; ++c) {
+          if (c + 1 < nchunks) push_w1(c + 1);
+          push_w2(c);
+        }
+      }
+    }
+   } else if (warp == 1) {
+    if (lane == 0) {
+      if (leader) {
+        // ----------------------------------------------------------- UMMA issuer (leader only)
+        constexpr uint32_t idesc_h = make_idesc_bf16(2 * kTileM, kFFChunk);
+        constexpr uint32_t idesc_y = make_idesc_bf16(2 * kTileM, kNC);
+        constexpr uint16_t kBoth = 3;
+        const uint32_t a_addr = smem_u32(sA);
+        uint32_t slot = 0, phase = 0, n = 0;
+        long long t_hfree = 0, t_full = 0, t_hsfull = 0, t_issue = 0, t_afull = 0, t_yempty = 0;
+        const long long t_begin = clock64();
+        auto gemm1 = [&](uint32_t nn) {
+          TRACE_T0();
+          mbar_wait_cluster(h_free, (nn & 1) ^ 1);
+          TRACE_ADD(t_hfree);
+          tc_fence_after();
+          for (int s = 0; s < C::kW1Stages; ++s) {
+            mbar_wait_cluster(&full[slot], phase);
+            TRACE_ADD(t_full);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(sRing + slot * C::kSlotBytes);
+#pragma unroll
+            for (int kk = 0; kk < C::kW1StageK; ++kk) {
+              const int kstep = s * C::kW1StageK + kk;
+              const uint64_t adesc = make_kc16_desc(a_addr + kstep * 4096, kTileM * 16, 128);
+              const uint64_t bdesc = make_kc16_desc(sb + kk * (2 * C::kW1Rows * 16), C::kW1Rows * 16, 128);
+              umma_bf16_ss_pair(tmem_base + C::kTmemH, adesc, bdesc, idesc_h, kstep != 0);
+            }
+            umma_commit_pair(&empty[slot], kBoth);
+            if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+            TRACE_ADD(t_issue);
+          }
+          umma_commit_pair(h_full, kBoth);
+        };
+        auto gemm2 = [&](uint32_t nn, int c) {
+          const uint32_t b = nn & 1;
+          TRACE_T0();
+          mbar_wait_cluster(&hs_full[b], (nn >> 1) & 1);
+          TRACE_ADD(t_hsfull);
+          tc_fence_after();
+          const uint32_t h_addr = smem_u32(sH + b * C::kHBytes);
+          for (int s = 0; s < C::kW2Stages; ++s) {
+            mbar_wait_cluster(&full[slot], phase);
+            TRACE_ADD(t_full);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(sRing + slot * C::kSlotBytes);
+#pragma unroll
+            for (int kk = 0; kk < C::kW2StageK; ++kk) {
+              const int kstep = s * C::kW2StageK + kk;
+              const uint64_t adesc = make_kc16_desc(h_addr + kstep * 4096, kTileM * 16, 128);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint64_t bdesc = make_kc16_desc(sb + kk * (2 * C::kW2Rows * 16) + j * (kNC / 2) * 16,
+                                                      C::kW2Rows * 16, 128);
+                umma_bf16_ss_pair(tmem_base + C::kTmemY + j * kNC, adesc, bdesc, idesc_y, true);
+              }
+            }
+            umma_commit_pair(&empty[slot], kBoth);
+            if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+            TRACE_ADD(t_issue);
+          }
+          umma_commit_pair(&hs_free[b], kBoth);
+        };
+        for (int ti = 0; ti < rounds; ++ti) {
+          { TRACE_T0(); mbar_wait_cluster(a_full, ti & 1); TRACE_ADD(t_afull); }
+          tc_fence_after();
+          gemm1(n);
+          for (int c = 0; c < nchunks; ++c) {
+            if (c + 1 < nchunks) {
+              gemm1(n + c + 1);
+            } else {
+              umma_commit_pair(a_empty, kBoth);
+            }
+            if (c == 0) {
+              TRACE_T0();
+              mbar_wait_cluster(y_empty, ti & 1);   // "Y holds x_old": both CTAs' row warps initialised it
+              TRACE_ADD(t_yempty);
+              tc_fence_after();
+            }
+            gemm2(n + c, c);
+          }
+          umma_commit_pair(y_full, kBoth);
+          n += nchunks;
+        }
+#ifdef DCB_TRACE
+        if (blockIdx.x < 256) {
+          unsigned long long* tr = g_ffn_trace + blockIdx.x * 16;
+          tr[0] = clock64() - t_begin; tr[1] = t_hfree; tr[2] = t_full; tr[3] = t_hsfull;
+          tr[4] = t_issue; tr[5] = t_afull; tr[6] = t_yempty; tr[7] = rounds;
+        }
+#endif
+      } else {
+        // ----------------------------------------------------------- relay (peer): forward "my half
+        // of this stage / my x tile has landed" to the leader's barriers, in consumption order
+        uint32_t slot = 0, phase = 0;
+        auto relay_stages = [&](int count) {
+          for (int s = 0; s < count; ++s) {
+            mbar_wait(&full[slot], phase);
+            mbar_arrive_cluster(&full[slot], 0);
+            if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+          }
+        };
+        for (int ti = 0; ti < rounds; ++ti) {
+          mbar_wait(a_full, ti & 1);
+          mbar_arrive_cluster(a_full, 0);
+          relay_stages(C::kW1Stages);
+          for (int c = 0; c < nchunks; ++c) {
+            if (c + 1 < nchunks) relay_stages(C::kW1Stages);
+            relay_stages(C::kW2Stages);
+          }
+        }
+      }
+    }
+   }
+  } else {
+    // ------------------------------------------------------------- epilogue warps (both CTAs)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    auto arrive_leader = [&](uint64_t* bar) {   // one arrive per warp on the leader's barrier
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(bar); else mbar_arrive_cluster(bar, 0);
+      }
+    };
+    if (warp < 12) {
+      setmaxnreg_dec<96>();
+      const int half = (warp - 4) >> 2;
+      uint32_t n = 0;
+      long long t_hfull = 0, t_hsfree = 0, t_body = 0;
+      for (int ti = 0; ti < rounds; ++ti) {
+        for (int c = 0; c < nchunks; ++c, ++n) {
+          const uint32_t b = n & 1;
+          TRACE_T0();
+          mbar_wait(h_full, n & 1);
+          TRACE_ADD(t_hfull);
+          tc_fence_after();
+          mbar_wait(&hs_free[b], ((n >> 1) & 1) ^ 1);
+          TRACE_ADD(t_hsfree);
+          uint4* hrow = reinterpret_cast<uint4*>(sH + b * C::kHBytes) + r;
+          const float* bias = sB1 + c * kFFChunk + half * (kFFChunk / 2);
+          // all four 16-column TMEM loads in flight, one wait, then release the accumulator
+          // immediately so GEMM1 of the next chunk overlaps the math + smem stores below
+          uint32_t acc[kFFChunk / 32][16];
+#pragma unroll
+          for (int cc = 0; cc < kFFChunk / 32; ++cc)
+            tmem_ld16(tmem_row + C::kTmemH + (half * (kFFChunk / 32) + cc) * 16, acc[cc]);
+          tmem_ld_wait();
+          tc_fence_before();
+          arrive_leader(h_free);
+#pragma unroll
+          for (int cc = 0; cc < kFFChunk / 32; ++cc) {
+            const int cb = half * (kFFChunk / 32) + cc;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(acc[cc][i]) + bias[cc * 16 + i], 0.f);
+            hrow[(size_t)(cb * 2) * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                         pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            hrow[(size_t)(cb * 2 + 1) * kTileM] =
+                make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                           pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+          }
+          fence_proxy_async_smem();
+          arrive_leader(&hs_full[b]);
+          TRACE_ADD(t_body);
+        }
+      }
+#ifdef DCB_TRACE
+      if (warp == 4 && lane == 0 && blockIdx.x < 256) {
+        unsigned long long* tr = g_ffn_trace + blockIdx.x * 16;
+        tr[8] = t_hfull; tr[9] = t_hsfree; tr[10] = t_body;
+      }
+#endif
+    } else {
+      setmaxnreg_inc<216>();
+      long long t_yfull = 0, t_row1 = 0, t_ldtm = 0, t_phaseA = 0;
+      for (int ti = 0; ti < rounds; ++ti) {
+        const int tile_raw = tile_of(ti);
+        const bool valid = tile_raw < ntiles;
+#ifdef DCB_TRACE
+        const long long _ta0 = clock64();
+#endif
+        // phase A: residual-in-accumulator.  Y <- x_old (tcgen05.st) so GEMM2 accumulates on top of it
+        // and the drain below needs no global loads.  (Y is free: this warp drained it last round.)
+        {
+          // two batches of 9 column blocks: all 36 16-byte loads of a batch are in flight together
+          // (HBM latency ~2000 cycles: bytes in flight per SM set the pace of this phase)
+          const int tile_ld = min(tile_raw, ntiles - 1);
+          const float4* xrow = reinterpret_cast<const float4*>(epi.x + (size_t)tile_ld * x_image_elems()) + r;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float4 buf[9][4];
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) buf[k][i] = xrow[(size_t)((half * 9 + k) * 4 + i) * kTileM];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+              uint32_t v[16];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                v[4 * i + 0] = __float_as_uint(buf[k][i].x); v[4 * i + 1] = __float_as_uint(buf[k][i].y);
+                v[4 * i + 2] = __float_as_uint(buf[k][i].z); v[4 * i + 3] = __float_as_uint(buf[k][i].w);
+              }
+              tmem_st16(tmem_row + C::kTmemY + (half * 9 + k) * 16, v);
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          arrive_leader(y_empty);
+        }
+#ifdef DCB_TRACE
+        t_phaseA += clock64() - _ta0;
+#endif
+        // phase B: drain the finished tile
+        TRACE_T0();
+        mbar_wait(y_full, ti & 1);
+        TRACE_ADD(t_yfull);
+        tc_fence_after();
+        if (valid) {
+          RowEpi edr = epi;
+          edr.has_xold = 0;               // x_old is already inside the accumulator
+          RowPrefetch unused;
+          const RowStats st = row_epilogue_pass1(edr, tmem_row + C::kTmemY, tile_raw, r, unused, &t_ldtm);
+          TRACE_ADD(t_row1);
+          if (epi.ln_g && epi.xb) row_epilogue_pass2<false>(epi, tile_raw, r, st.mean, st.rstd);
+        }
+        tc_fence_before();
+      }
+#ifdef DCB_TRACE
+      if (warp == 12 && lane == 0 && blockIdx.x < 256) {
+        unsigned long long* tr = g_ffn_trace + blockIdx.x * 16;
+        tr[11] = t_yfull; tr[12] = t_row1; tr[13] = t_ldtm; tr[14] = t_phaseA;
+      }
+#endif
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, C::kTmemCols);
+  }
+}
+
+// =====================================================================================
 // banded attention (mma.sync m16n8k16 bf16, online softmax over 16-key tiles)
 // =====================================================================================
 // One CTA per (window, head).  K and V rows of the window are staged in shared memory
@@ -989,6 +1400,8 @@ cudaError_t kernels_init() {
   e = cudaFuncSetAttribute(gemm_kernel<2, EPI_ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            GemmCfg<2>::kSmemBytes);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(ffn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Ffn2Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(ffn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg::kSmemBytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(ffn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg::kSmemBytes);
@@ -1066,6 +1479,28 @@ static void launch_ffn_cs(const __nv_bfloat16* a_img, const uint8_t* w_img, cons
   if (clusters > max_clusters) clusters = max_clusters;
   cfg.gridDim = dim3(clusters * CS);
   cudaLaunchKernelEx(&cfg, ffn_kernel<CS>, a_img, w_img, b1, ff, ntiles, epi);
+}
+
+void launch_ffn_pair(const __nv_bfloat16* a_img, const uint8_t* w2img, const float* b1, int ff, int ntiles,
+                     const RowEpi& epi, cudaStream_t st) {
+  static int max_pairs = 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kFfnThreads);
+  cfg.dynamicSmemBytes = Ffn2Cfg::kSmemBytes;
+  cfg.stream = st;
+  if (!max_pairs) {
+    cfg.gridDim = dim3(num_sms() / 2 * 2);
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, ffn_pair_kernel, &cfg) != cudaSuccess || nc <= 0) nc = num_sms() / 2;
+    max_pairs = nc;
+    if (getenv("DCB_VERBOSE")) fprintf(stderr, "[dcb200] ffn pair kernel: %d co-resident CTA pairs\n", nc);
+  }
+  int pairs = (ntiles + 1) / 2;
+  if (pairs > max_pairs) pairs = max_pairs;
+  cfg.gridDim = dim3(pairs * 2);
+  static int stagger = -1;
+  if (stagger < 0) { const char* env = getenv("DCB_FFN_STAGGER"); stagger = env ? atoi(env) : 0; }
+  cudaLaunchKernelEx(&cfg, ffn_pair_kernel, a_img, w2img, b1, ff, ntiles, epi, stagger);
 }
 
 void launch_ffn(const __nv_bfloat16* a_img, const uint8_t* w_img, const float* b1, int ff, int ntiles,

@@ -20,6 +20,9 @@ void launch_gemm_qkv(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int
                      __nv_bfloat16* qkv_img, cudaStream_t st);
 void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int win, int nwindows,
                       cudaStream_t st);
+// CTA-pair (cta_group::2) version; w2img is the per-rank half-chunk weight image.
+void launch_ffn_pair(const __nv_bfloat16* a_img, const uint8_t* w2img, const float* b1, int ff, int ntiles,
+                     const RowEpi& epi, cudaStream_t st);
 void launch_ffn(const __nv_bfloat16* a_img, const uint8_t* w_img, const float* b1, int ff, int ntiles,
                 const RowEpi& epi, cudaStream_t st);
 int read_ffn_trace(unsigned long long* out, int n);

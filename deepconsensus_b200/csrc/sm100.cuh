@@ -55,6 +55,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait with cluster-scope acquire (for barriers that peers of the cluster arrive on).
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
 // ------------------------------------------------------------------- bulk async copy (TMA)
 // global -> shared, completion reported on an mbarrier as transaction bytes.
 // size % 16 == 0, both addresses 16-byte aligned.
@@ -163,6 +177,50 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
       : "memory");
 }
 
+// ----------------------------------------------------------------------------- CTA pairs (cta_group::2)
+// TMEM alloc / dealloc for a CTA pair: the same warp of BOTH CTAs executes it with the same smem offset.
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_holder)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// D[256 x N] (+)= A * B over the pair: each CTA supplies its 128 rows of A and N/2 rows of B from
+// its own shared memory (same offsets in both CTAs); rows 0-127 of D land in the leader's TMEM,
+// rows 128-255 in the peer's.  Issued by ONE thread of the leader CTA.
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                  uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
+      : "memory");
+}
+// Completion of all prior pair-MMAs -> arrive on the barrier at this offset in the CTAs of cta_mask.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+// Arrive on the mbarrier at the same shared-memory offset in CTA `target_cta` of the cluster.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t target_cta) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(target_cta));
+  // default semantics (.release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id) does: a
+  // cluster-scope release would make ptxas emit MEMBAR.ALL.GPU + ERRBAR in front of every arrive.
+  // What the leader's consumers need is covered elsewhere: TMEM reads by tcgen05.fence, shared-memory
+  // operand writes by fence.proxy.async (they are read by the tensor core's async proxy).
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+
 // ----------------------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -184,6 +242,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+// registers -> TMEM: this warp's 32 lanes x 16 consecutive 32-bit columns.
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
