@@ -27,6 +27,7 @@ struct LayerDev {
   __nv_bfloat16* wo = nullptr;    // [36][288][8]
   uint8_t* wffn = nullptr;        // per ff chunk: [36][128][8] then [16][288][8]
   uint8_t* wffn2 = nullptr;       // CTA-pair image: per (chunk, rank): [36][64][8] then [16][144][8]
+  uint8_t* wo2 = nullptr;         // CTA-pair out-proj image: per rank [36][144][8]
   float* b1 = nullptr;            // [ff]
   float* b2 = nullptr;            // [288] (gain folded)
   float* ln_g[2] = {nullptr, nullptr};  // pre-norm gamma/beta of the attention / FFN sub-layer
@@ -46,6 +47,8 @@ struct dcb_engine {
   bool weights_loaded = false;
   bool debug = false;
   bool ffn_pair = true;
+  bool fuse_oproj = true;
+  bool fused_last = false;
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // around every ffn_kernel launch
   size_t prof_used = 0;
@@ -194,6 +197,7 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   e->Epad = (e->E + 15) / 16 * 16;
   e->echunks = e->Epad / 8;
   if (const char* env = getenv("DCB_FFN_PAIR")) e->ffn_pair = atoi(env) != 0;
+  if (const char* env = getenv("DCB_FUSE_OPROJ")) e->fuse_oproj = atoi(env) != 0;
   int ct = cfg->chunk_tiles;
   if (const char* env = getenv("DCB_CHUNK_TILES")) ct = atoi(env);
   if (ct <= 0) ct = 8 * e->num_sms;   // measured: larger chunks win (kernels are not DRAM-bound)
@@ -388,6 +392,20 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
         return wo[((size_t)head * kDH + dd) * kD + nn] * alpha0;
       });
       if ((rc = upload(e, &ld.wo, img))) return rc;
+      // CTA-pair halves: rank r holds, for each 144-wide N chunk j, output rows j*144 + r*72 + [0,72)
+      std::vector<__nv_bfloat16> img2;
+      for (int rk = 0; rk < 2; ++rk) {
+        auto part = pack_b(kDP, kDP / 2, [&](int k, int nn) {
+          const int col = (nn / (kNC / 2)) * kNC + rk * (kNC / 2) + nn % (kNC / 2);
+          const int head = k / kDHP, dd = k % kDHP;
+          if (dd >= kDH || col >= kD) return 0.f;
+          return wo[((size_t)head * kDH + dd) * kD + col] * alpha0;
+        });
+        img2.insert(img2.end(), part.begin(), part.end());
+      }
+      __nv_bfloat16* dptr = nullptr;
+      if ((rc = upload(e, &dptr, img2))) return rc;
+      ld.wo2 = reinterpret_cast<uint8_t*>(dptr);
     }
     const float* w1 = tm.get(P1 + "/layer/filter_dense_layer/kernel", {kD, ff}, &rc); if (rc) return rc;
     const float* b1 = tm.get(P1 + "/layer/filter_dense_layer/bias", {ff}, &rc); if (rc) return rc;
@@ -517,19 +535,25 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
       const bool last = n_ + 1 == c.num_hidden_layers;
       launch_gemm_qkv(e->d_xb, ld.wqkv, T, e->d_embqkv, st);
       launch_attention(e->d_embqkv, e->d_att, L, c.attn_win_size, bw, st);
-      RowEpi ea{};
-      ea.x = e->d_x; ea.xb = e->d_xb; ea.bias = nullptr; ea.pe = nullptr;
-      ea.ln_g = c.rezero ? nullptr : ld.ln_g[1];
-      ea.ln_b = c.rezero ? nullptr : ld.ln_b[1];
-      ea.has_xold = 1; ea.L = L;
-      launch_gemm_row(e->d_att, ld.wo, kDP / 16, T, ea, st);
-      snap();
+      // attention out-proj + FFN: fused into one CTA-pair kernel unless debugging the intermediate
+      const bool fused = e->ffn_pair && e->fuse_oproj && !e->debug;
       RowEpi ef{};
       ef.x = e->d_x; ef.xb = last ? nullptr : e->d_xb; ef.bias = ld.b2; ef.pe = nullptr;
       ef.ln_g = (c.rezero || last) ? nullptr : e->layers[n_ + 1].ln_g[0];
       ef.ln_b = (c.rezero || last) ? nullptr : e->layers[n_ + 1].ln_b[0];
       ef.has_xold = 1; ef.L = L;
-      if (e->profile) {
+      if (!fused) {
+        RowEpi ea{};
+        ea.x = e->d_x; ea.xb = e->d_xb; ea.bias = nullptr; ea.pe = nullptr;
+        ea.ln_g = c.rezero ? nullptr : ld.ln_g[1];
+        ea.ln_b = c.rezero ? nullptr : ld.ln_b[1];
+        ea.has_xold = 1; ea.L = L;
+        launch_gemm_row(e->d_att, ld.wo, kDP / 16, T, ea, st);
+        ++launches;
+        snap();
+      }
+      const bool prof = e->profile;
+      if (prof) {
         if (e->prof_used == e->prof_events.size()) {
           cudaEvent_t a, b;
           CU(e, cudaEventCreate(&a));
@@ -538,15 +562,21 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
         }
         CU(e, cudaEventRecord(e->prof_events[e->prof_used].first, st));
       }
-      if (e->ffn_pair) launch_ffn_pair(e->d_xb, ld.wffn2, ld.b1, c.filter_size, T, ef, st);
-      else launch_ffn(e->d_xb, ld.wffn, ld.b1, c.filter_size, T, ef, st);
-      if (e->profile) {
+      if (fused)
+        launch_ffn_pair(e->d_att, ld.wffn2, ld.b1, c.filter_size, T, ef, st, ld.wo2,
+                        c.rezero ? nullptr : ld.ln_g[1], c.rezero ? nullptr : ld.ln_b[1]);
+      else if (e->ffn_pair)
+        launch_ffn_pair(e->d_xb, ld.wffn2, ld.b1, c.filter_size, T, ef, st);
+      else
+        launch_ffn(e->d_xb, ld.wffn, ld.b1, c.filter_size, T, ef, st);
+      if (prof) {
         CU(e, cudaEventRecord(e->prof_events[e->prof_used].second, st));
         ++e->prof_used;
         e->prof_ffn_tokens += M;
       }
-      snap();
-      launches += 4;
+      if (!fused) snap();
+      e->fused_last = fused;
+      launches += 3;
     }
     HeadParams hp{};
     hp.x = e->d_x; hp.ln_g = e->d_fln_g; hp.ln_b = e->d_fln_b; hp.wfc = e->d_wfc; hp.bfc = e->d_bfc;

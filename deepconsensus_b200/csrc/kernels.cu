@@ -752,6 +752,9 @@ struct Ffn2Cfg {
   static constexpr int kW2Stages = 2;
   static constexpr int kW2StageBytes = kW2StageK * 2 * kW2Rows * 16; // 18432
   static constexpr int kHalfChunkBytes = kW1Stages * kW1StageBytes + kW2Stages * kW2StageBytes;  // 73728
+  static constexpr int kWoStageK = 3;                                // attention out-proj: k-steps per stage
+  static constexpr int kWoStages = (kDP / 16) / kWoStageK;           // 6
+  static constexpr int kWoStageBytes = kWoStageK * 2 * kW2Rows * 16; // 13824
   static constexpr int kTmemY = 0;
   static constexpr int kTmemH = kDP;
   static constexpr int kTmemCols = 512;
@@ -766,9 +769,17 @@ struct Ffn2Cfg {
 static_assert(Ffn2Cfg::kSmemBytes <= 232448, "FFN pair shared memory budget");
 static_assert(Ffn2Cfg::kW1Stages * Ffn2Cfg::kW1StageK == kDP / 16 && Ffn2Cfg::kW2Stages * Ffn2Cfg::kW2StageK == kFFChunk / 16, "stages");
 
+// kFuse: the attention output projection (attention_layer.py:218) + its residual / pre-norm
+// (encoder_stack.py:72-93) run in front of the FFN on the same tile: a_img is then the attention
+// operand image, Y <- x_old + att*Wo (out-proj UMMAs accumulate onto the residual already in TMEM),
+// the row warps turn Y (= x_mid, never written to HBM) into the FFN's bf16 operand tile in shared
+// memory (`mid`: identity for ReZero, LayerNorm otherwise), then the FFN proceeds as before.
+template <bool kFuse>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFfnThreads, 1)
 ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ w2img,
-                const float* __restrict__ b1, int ff, int ntiles, RowEpi epi, int stagger_cycles) {
+                const float* __restrict__ b1, int ff, int ntiles, RowEpi epi, int stagger_cycles,
+                const uint8_t* __restrict__ wo2img, const float* __restrict__ mid_ln_g,
+                const float* __restrict__ mid_ln_b) {
   using C = Ffn2Cfg;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem + C::kOffA;
@@ -786,7 +797,9 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
   uint64_t* hs_free = a_full + 6;          // [2]
   uint64_t* y_full = a_full + 8;
   uint64_t* y_empty = a_full + 9;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 10);
+  uint64_t* ymid_full = a_full + 10;       // out-proj UMMAs done: Y holds x_mid (kFuse)
+  uint64_t* a2_full = a_full + 11;         // both CTAs' row warps wrote the FFN operand tile (kFuse, leader)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -813,6 +826,8 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
     mbar_init(&hs_free[1], 1);
     mbar_init(y_full, 1);
     mbar_init(y_empty, 8);         // 4 row-epilogue warps x 2 CTAs (leader only)
+    mbar_init(ymid_full, 1);
+    mbar_init(a2_full, 8);
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < ff; i += blockDim.x) sB1[i] = b1[i];
@@ -860,6 +875,10 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
         mbar_wait(a_empty, (ti & 1) ^ 1);
         mbar_arrive_expect_tx(a_full, C::kABytes);
         bulk_g2s(sA, reinterpret_cast<const uint8_t*>(a_img) + (size_t)tile * C::kABytes, C::kABytes, a_full);
+        if constexpr (kFuse) {
+          const uint8_t* wo = wo2img + (size_t)rank * C::kWoStages * C::kWoStageBytes;
+          for (int s = 0; s < C::kWoStages; ++s) push(wo + s * C::kWoStageBytes, C::kWoStageBytes);
+        }
         push_w1(0);
         for (int c = 0; c < nchunks; ++c) {
           if (c + 1 < nchunks) push_w1(c + 1);
@@ -933,6 +952,34 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
         for (int ti = 0; ti < rounds; ++ti) {
           { TRACE_T0(); mbar_wait_cluster(a_full, ti & 1); TRACE_ADD(t_afull); }
           tc_fence_after();
+          if constexpr (kFuse) {
+            // Y (= x_old, stored by the row warps) += att * Wo^T
+            TRACE_T0();
+            mbar_wait_cluster(y_empty, ti & 1);
+            TRACE_ADD(t_yempty);
+            tc_fence_after();
+            for (int s = 0; s < C::kWoStages; ++s) {
+              mbar_wait_cluster(&full[slot], phase);
+              tc_fence_after();
+              const uint32_t sb = smem_u32(sRing + slot * C::kSlotBytes);
+#pragma unroll
+              for (int kk = 0; kk < C::kWoStageK; ++kk) {
+                const int kstep = s * C::kWoStageK + kk;
+                const uint64_t adesc = make_kc16_desc(a_addr + kstep * 4096, kTileM * 16, 128);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const uint64_t bdesc = make_kc16_desc(sb + kk * (2 * C::kW2Rows * 16) + j * (kNC / 2) * 16,
+                                                        C::kW2Rows * 16, 128);
+                  umma_bf16_ss_pair(tmem_base + C::kTmemY + j * kNC, adesc, bdesc, idesc_y, true);
+                }
+              }
+              umma_commit_pair(&empty[slot], kBoth);
+              if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+            }
+            umma_commit_pair(ymid_full, kBoth);
+            mbar_wait_cluster(a2_full, ti & 1);   // FFN operand tile written by both CTAs' row warps
+            tc_fence_after();
+          }
           gemm1(n);
           for (int c = 0; c < nchunks; ++c) {
             if (c + 1 < nchunks) {
@@ -940,7 +987,7 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
             } else {
               umma_commit_pair(a_empty, kBoth);
             }
-            if (c == 0) {
+            if (!kFuse && c == 0) {
               TRACE_T0();
               mbar_wait_cluster(y_empty, ti & 1);   // "Y holds x_old": both CTAs' row warps initialised it
               TRACE_ADD(t_yempty);
@@ -972,6 +1019,7 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
         for (int ti = 0; ti < rounds; ++ti) {
           mbar_wait(a_full, ti & 1);
           mbar_arrive_cluster(a_full, 0);
+          if constexpr (kFuse) relay_stages(C::kWoStages);
           relay_stages(C::kW1Stages);
           for (int c = 0; c < nchunks; ++c) {
             if (c + 1 < nchunks) relay_stages(C::kW1Stages);
@@ -1081,6 +1129,55 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
 #ifdef DCB_TRACE
         t_phaseA += clock64() - _ta0;
 #endif
+        if constexpr (kFuse) {
+          // mid epilogue: Y = x_mid after the out-proj.  Produce the FFN's bf16 operand tile in sA
+          // (the attention tile there has been consumed: ymid_full follows the out-proj UMMAs).
+          mbar_wait(ymid_full, ti & 1);
+          tc_fence_after();
+          float mean = 0.f, rstd = 1.f;
+          if (mid_ln_g) {
+            float s1 = 0.f, s2 = 0.f, shift = 0.f;
+#pragma unroll 2
+            for (int cb = 0; cb < kDP / 16; ++cb) {
+              uint32_t acc[16];
+              tmem_ld16(tmem_row + C::kTmemY + cb * 16, acc);
+              tmem_ld_wait();
+              if (cb == 0) shift = __uint_as_float(acc[0]);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float dlt = (cb * 16 + i < kD) ? __uint_as_float(acc[i]) - shift : 0.f;
+                s1 += dlt;
+                s2 += dlt * dlt;
+              }
+            }
+            const float m1 = s1 * (1.f / kD);
+            mean = shift + m1;
+            rstd = rsqrtf(fmaxf(s2 * (1.f / kD) - m1 * m1, 0.f) + 1e-6f);
+          }
+          uint4* arow = reinterpret_cast<uint4*>(sA) + r;
+#pragma unroll 2
+          for (int cb = 0; cb < kDP / 16; ++cb) {
+            uint32_t acc[16];
+            tmem_ld16(tmem_row + C::kTmemY + cb * 16, acc);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = cb * 16 + i;
+              float t = __uint_as_float(acc[i]);
+              if (mid_ln_g) t = (t - mean) * rstd * __ldg(mid_ln_g + col) + __ldg(mid_ln_b + col);
+              v[i] = col < kD ? t : 0.f;
+            }
+            arow[(size_t)(cb * 2) * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                         pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            arow[(size_t)(cb * 2 + 1) * kTileM] =
+                make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                           pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+          }
+          tc_fence_before();
+          fence_proxy_async_smem();
+          arrive_leader(a2_full);
+        }
         // phase B: drain the finished tile
         TRACE_T0();
         mbar_wait(y_full, ti & 1);
@@ -1400,7 +1497,9 @@ cudaError_t kernels_init() {
   e = cudaFuncSetAttribute(gemm_kernel<2, EPI_ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            GemmCfg<2>::kSmemBytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(ffn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Ffn2Cfg::kSmemBytes);
+  e = cudaFuncSetAttribute(ffn_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ffn2Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(ffn_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ffn2Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(ffn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg::kSmemBytes);
   if (e != cudaSuccess) return e;
@@ -1482,7 +1581,8 @@ static void launch_ffn_cs(const __nv_bfloat16* a_img, const uint8_t* w_img, cons
 }
 
 void launch_ffn_pair(const __nv_bfloat16* a_img, const uint8_t* w2img, const float* b1, int ff, int ntiles,
-                     const RowEpi& epi, cudaStream_t st) {
+                     const RowEpi& epi, cudaStream_t st, const uint8_t* wo2img, const float* mid_ln_g,
+                     const float* mid_ln_b) {
   static int max_pairs = 0;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(kFfnThreads);
@@ -1491,7 +1591,7 @@ void launch_ffn_pair(const __nv_bfloat16* a_img, const uint8_t* w2img, const flo
   if (!max_pairs) {
     cfg.gridDim = dim3(num_sms() / 2 * 2);
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, ffn_pair_kernel, &cfg) != cudaSuccess || nc <= 0) nc = num_sms() / 2;
+    if (cudaOccupancyMaxActiveClusters(&nc, ffn_pair_kernel<false>, &cfg) != cudaSuccess || nc <= 0) nc = num_sms() / 2;
     max_pairs = nc;
     if (getenv("DCB_VERBOSE")) fprintf(stderr, "[dcb200] ffn pair kernel: %d co-resident CTA pairs\n", nc);
   }
@@ -1500,7 +1600,10 @@ void launch_ffn_pair(const __nv_bfloat16* a_img, const uint8_t* w2img, const flo
   cfg.gridDim = dim3(pairs * 2);
   static int stagger = -1;
   if (stagger < 0) { const char* env = getenv("DCB_FFN_STAGGER"); stagger = env ? atoi(env) : 0; }
-  cudaLaunchKernelEx(&cfg, ffn_pair_kernel, a_img, w2img, b1, ff, ntiles, epi, stagger);
+  if (wo2img)
+    cudaLaunchKernelEx(&cfg, ffn_pair_kernel<true>, a_img, w2img, b1, ff, ntiles, epi, stagger, wo2img, mid_ln_g, mid_ln_b);
+  else
+    cudaLaunchKernelEx(&cfg, ffn_pair_kernel<false>, a_img, w2img, b1, ff, ntiles, epi, stagger, wo2img, mid_ln_g, mid_ln_b);
 }
 
 void launch_ffn(const __nv_bfloat16* a_img, const uint8_t* w_img, const float* b1, int ff, int ntiles,

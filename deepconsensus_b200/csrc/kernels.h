@@ -21,8 +21,12 @@ void launch_gemm_qkv(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int
 void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int win, int nwindows,
                       cudaStream_t st);
 // CTA-pair (cta_group::2) version; w2img is the per-rank half-chunk weight image.
+// With wo2img != null the attention out-projection (+ residual, + pre-norm `mid_ln_*` or identity) is
+// fused in front: a_img is then the attention operand image and epi.x the residual before the
+// attention sub-layer.
 void launch_ffn_pair(const __nv_bfloat16* a_img, const uint8_t* w2img, const float* b1, int ff, int ntiles,
-                     const RowEpi& epi, cudaStream_t st);
+                     const RowEpi& epi, cudaStream_t st, const uint8_t* wo2img = nullptr,
+                     const float* mid_ln_g = nullptr, const float* mid_ln_b = nullptr);
 void launch_ffn(const __nv_bfloat16* a_img, const uint8_t* w_img, const float* b1, int ff, int ntiles,
                 const RowEpi& epi, cudaStream_t st);
 int read_ffn_trace(unsigned long long* out, int n);

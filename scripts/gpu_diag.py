@@ -29,7 +29,9 @@ def run_case(tag, p, B, seed, calib="0,1.197654,-0.99781"):
   rows = synthetic.make_rows(p, B, seed=seed + 100)
   cal = C.parse_calibration_string(calib)
   m = engine.B200Model(p, w, max_batch=max(B, 1), calibration=cal)
-  m.set_debug(True)
+  nodebug = bool(os.environ.get('DIAG_NODEBUG'))
+  if not nodebug:
+    m.set_debug(True)
   t = time.time()
   out = m.forward(rows, want_probs=True, want_logits=True, strict_input=False)
   say("forward ok: wall %.3fs device %.3f ms launches %d" % (time.time() - t, m.last_ms, m.last_launches))
@@ -39,7 +41,7 @@ def run_case(tag, p, B, seed, calib="0,1.197654,-0.99781"):
   # residual stream of the last chunk
   ntok = B * L
   try:
-    for si, name in enumerate(stage_names(p.num_hidden_layers)):
+    for si, name in enumerate(stage_names(p.num_hidden_layers) if not nodebug else []):
       got = m.debug_residual(si, ntok) if ntok <= 200000 else None
       want = ref["intermediates"][name].reshape(-1, 280)[-got.shape[0]:]
       err = np.abs(got - want)
