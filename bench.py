@@ -251,15 +251,20 @@ def main():
   e2e_value = total_windows / dt_e2e
   F = flops_per_window(p)
   peaks = measured_peaks()
-  # dominant kernel: fused FFN.  Algorithmic FLOPs per launch = tokens * 4*d*ff.
-  ffn_flops = prof["ffn_tokens"] * 4.0 * p.hidden_size * p.filter_size
+  # dominant kernel: fused FFN (+ attention out-projection when fused into it).
+  # Algorithmic FLOPs per launch = tokens * (4*d*ff [+ 2*d*d]).
+  per_token = 4.0 * p.hidden_size * p.filter_size + (2.0 * p.hidden_size * p.hidden_size if prof["fused_oproj"] else 0.0)
+  ffn_flops = prof["ffn_tokens"] * per_token
   ffn_tflops = ffn_flops / (prof["ffn_ms_total"] * 1e-3) / 1e12 if prof["ffn_ms_total"] > 0 else None
   traffic = None
   tpath = os.path.join(ROOT, "profiles", "ffn_dram_traffic.json")
   if os.path.exists(tpath):
     with open(tpath) as f:
       traffic = json.load(f).get("dram_bytes_per_launch")
-  roof = dict(bound="tensor", kernel="ffn_kernel", achieved=ffn_tflops, peak=peaks["bf16_tflops"],
+  kshare = {k: round(v["ms"] / max(sum(x["ms"] for x in prof["kernels"].values()), 1e-9), 4) for k, v in prof["kernels"].items()}
+  roof = dict(bound="tensor", kernel="ffn_pair_kernel<fused out-proj>" if prof["fused_oproj"] else "ffn_pair_kernel",
+              achieved=ffn_tflops, flops_per_token=per_token, kernel_time_share=kshare,
+              kernel_ms_per_step={k: round(v["ms"] / args.steps, 4) for k, v in prof["kernels"].items()}, peak=peaks["bf16_tflops"],
               unit="TFLOP/s", frac=(ffn_tflops / peaks["bf16_tflops"]) if ffn_tflops else None,
               traffic=traffic, peak_source=peaks["source"] + " (burst bf16)",
               launches_timed=prof["ffn_launches"],

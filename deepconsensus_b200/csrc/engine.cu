@@ -50,7 +50,10 @@ struct dcb_engine {
   bool fuse_oproj = true;
   bool fused_last = false;
   bool profile = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // around every ffn_kernel launch
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // around every launch when profiling
+  std::vector<int> prof_kind;       // kernel class of each event pair
+  float prof_ms[6] = {0, 0, 0, 0, 0, 0};   // embed, gemm_row, qkv, attention, ffn(+out-proj), head
+  int prof_n[6] = {0, 0, 0, 0, 0, 0};
   size_t prof_used = 0;
   float prof_ffn_ms = 0.f;
   int prof_ffn_launches = 0;
@@ -500,6 +503,23 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
   CU(e, cudaEventRecord(e->ev0, st));
   int launches = 0;
   const size_t ximg = x_image_elems();
+  bool prof_err = false;
+  auto pbegin = [&](int kind) {
+    if (!e->profile) return;
+    if (e->prof_used == e->prof_events.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { prof_err = true; return; }
+      e->prof_events.emplace_back(a, b);
+    }
+    if (e->prof_kind.size() <= e->prof_used) e->prof_kind.resize(e->prof_used + 1);
+    e->prof_kind[e->prof_used] = kind;
+    cudaEventRecord(e->prof_events[e->prof_used].first, st);
+  };
+  auto pend = [&]() {
+    if (!e->profile || prof_err) return;
+    cudaEventRecord(e->prof_events[e->prof_used].second, st);
+    ++e->prof_used;
+  };
   for (int w0 = 0; w0 < batch; w0 += e->chunk_windows) {
     const int bw = std::min(e->chunk_windows, batch - w0);
     const int M = bw * L;
@@ -517,7 +537,9 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
       if (e->debug) cudaMemcpyAsync(e->d_dbg + (size_t)stage * e->chunk_tiles * ximg, e->d_x, (size_t)T * ximg * sizeof(float), cudaMemcpyDeviceToDevice, st);
       ++stage;
     };
+    pbegin(0);
     launch_embed(rows_chunk, R, L, M, T, e->echunks, e->d_cols, e->d_rowmeta, e->d_tables, e->table_elems, e->d_embqkv, e->d_status, st);
+    pend();
     ++launches;
     {
       RowEpi epi{};
@@ -526,15 +548,21 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
       epi.ln_g = c.rezero ? nullptr : e->layers[0].ln_g[0];
       epi.ln_b = c.rezero ? nullptr : e->layers[0].ln_b[0];
       epi.has_xold = 0; epi.L = L;
+      pbegin(1);
       launch_gemm_row(e->d_embqkv, e->d_wc, e->Epad / 16, T, epi, st);
+      pend();
       ++launches;
       snap();
     }
     for (int n_ = 0; n_ < c.num_hidden_layers; ++n_) {
       const LayerDev& ld = e->layers[n_];
       const bool last = n_ + 1 == c.num_hidden_layers;
+      pbegin(2);
       launch_gemm_qkv(e->d_xb, ld.wqkv, T, e->d_embqkv, st);
+      pend();
+      pbegin(3);
       launch_attention(e->d_embqkv, e->d_att, L, c.attn_win_size, bw, st);
+      pend();
       // attention out-proj + FFN: fused into one CTA-pair kernel unless debugging the intermediate
       const bool fused = e->ffn_pair && e->fuse_oproj && !e->debug;
       RowEpi ef{};
@@ -548,20 +576,13 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
         ea.ln_g = c.rezero ? nullptr : ld.ln_g[1];
         ea.ln_b = c.rezero ? nullptr : ld.ln_b[1];
         ea.has_xold = 1; ea.L = L;
+        pbegin(1);
         launch_gemm_row(e->d_att, ld.wo, kDP / 16, T, ea, st);
+        pend();
         ++launches;
         snap();
       }
-      const bool prof = e->profile;
-      if (prof) {
-        if (e->prof_used == e->prof_events.size()) {
-          cudaEvent_t a, b;
-          CU(e, cudaEventCreate(&a));
-          CU(e, cudaEventCreate(&b));
-          e->prof_events.emplace_back(a, b);
-        }
-        CU(e, cudaEventRecord(e->prof_events[e->prof_used].first, st));
-      }
+      pbegin(4);
       if (fused)
         launch_ffn_pair(e->d_att, ld.wffn2, ld.b1, c.filter_size, T, ef, st, ld.wo2,
                         c.rezero ? nullptr : ld.ln_g[1], c.rezero ? nullptr : ld.ln_b[1]);
@@ -569,11 +590,8 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
         launch_ffn_pair(e->d_xb, ld.wffn2, ld.b1, c.filter_size, T, ef, st);
       else
         launch_ffn(e->d_xb, ld.wffn, ld.b1, c.filter_size, T, ef, st);
-      if (prof) {
-        CU(e, cudaEventRecord(e->prof_events[e->prof_used].second, st));
-        ++e->prof_used;
-        e->prof_ffn_tokens += M;
-      }
+      pend();
+      if (e->profile) e->prof_ffn_tokens += M;
       if (!fused) snap();
       e->fused_last = fused;
       launches += 3;
@@ -590,7 +608,9 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
     hp.calib_thr = (float)c.calibration_threshold; hp.calib_w = (float)c.calibration_w; hp.calib_b = (float)c.calibration_b;
     hp.calib_thr64 = c.calibration_threshold; hp.calib_w64 = c.calibration_w; hp.calib_b64 = c.calibration_b;
     hp.max_q = (float)c.max_base_quality;
+    pbegin(5);
     launch_head(hp, T, st);
+    pend();
     ++launches;
     e->last_chunk_tokens = M;
   }
@@ -612,8 +632,10 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
     for (size_t i = 0; i < e->prof_used; ++i) {
       float ms = 0.f;
       CU(e, cudaEventElapsedTime(&ms, e->prof_events[i].first, e->prof_events[i].second));
-      e->prof_ffn_ms += ms;
-      ++e->prof_ffn_launches;
+      const int kind = e->prof_kind[i];
+      e->prof_ms[kind] += ms;
+      ++e->prof_n[kind];
+      if (kind == 4) { e->prof_ffn_ms += ms; ++e->prof_ffn_launches; }
     }
     e->prof_used = 0;
   }
@@ -640,6 +662,7 @@ int dcb_set_profile(dcb_engine* e, int32_t enabled) {
   e->prof_ffn_launches = 0;
   e->prof_ffn_tokens = 0;
   e->prof_used = 0;
+  for (int i = 0; i < 6; ++i) { e->prof_ms[i] = 0.f; e->prof_n[i] = 0; }
   return DCB_OK;
 }
 
@@ -648,6 +671,13 @@ int dcb_get_profile(dcb_engine* e, float* ffn_ms_total, int32_t* ffn_launches, i
   *ffn_ms_total = e->prof_ffn_ms;
   *ffn_launches = e->prof_ffn_launches;
   *ffn_tokens = e->prof_ffn_tokens;
+  return DCB_OK;
+}
+
+int dcb_get_profile_kernels(dcb_engine* e, float* ms6, int32_t* n6, int32_t* fused_oproj) {
+  if (!e || !ms6 || !n6 || !fused_oproj) return DCB_ERR_INVALID;
+  for (int i = 0; i < 6; ++i) { ms6[i] = e->prof_ms[i]; n6[i] = e->prof_n[i]; }
+  *fused_oproj = e->fused_last ? 1 : 0;
   return DCB_OK;
 }
 

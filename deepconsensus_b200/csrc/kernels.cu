@@ -1218,7 +1218,8 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
 // ldmatrix.trans on V); Q fragments are read straight from the global operand image.
 // FLOP share of this kernel is ~1-4 % of the model, so the legacy warp-level MMA path
 // is used here on purpose ("Window/tile alignment for attention").
-constexpr int kAttStride = 152;
+constexpr int kAttStride = 144;              // dense rows; 16-byte chunks are rotated by the row index
+constexpr int kAttChunks = kDHP / 8;         // 18 chunks per row
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
                                                uint32_t b1) {
@@ -1241,7 +1242,16 @@ __device__ __forceinline__ size_t img_off(int tok, int col, int chunks) {
   return (((size_t)tile * chunks + (col >> 3)) * kTileM + r) * 8 + (col & 7);
 }
 
-__global__ void __launch_bounds__(128)
+// Shared-memory K/V rows are dense (288 B) with the 18 16-byte chunks of row r rotated by r
+// (physical chunk = (c + r) mod 18): 8 consecutive rows then hit 8 distinct 16-byte bank groups
+// (48 r mod 128 is a permutation of the multiples of 16), which keeps both the 32-bit K-fragment
+// loads and ldmatrix.trans on V conflict-free without padding -- 73.7 KB per CTA, 3 CTAs per SM.
+__device__ __forceinline__ int att_rot(int chunk, int rowmod) {
+  const int t = chunk + rowmod;
+  return t >= kAttChunks ? t - kAttChunks : t;
+}
+
+__global__ void __launch_bounds__(128, 3)
 band_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ att,
                       int L, int win, int nwindows) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -1254,19 +1264,34 @@ band_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
   constexpr int qkv_chunks = kQKVN / 8;  // 108
   const int kcol = (2 + head) * kDHP, vcol = (4 + head) * kDHP, qcol = head * kDHP;
   const int tok0 = w * L;
+#ifdef DCB_TRACE
+  const long long _t_start = clock64();
+#endif
 
-  // stage K, V with cp.async (all copies in flight at once): 16-byte chunks,
-  // (row, chunk) -> smem[row*304 + chunk*16]; rows >= L are zero filled.
-  for (int idx = threadIdx.x; idx < Lp * (kDHP / 8) * 2; idx += blockDim.x) {
-    const int which = idx / (Lp * (kDHP / 8));
-    const int rem = idx - which * (Lp * (kDHP / 8));
-    const int ch = rem / Lp, row = rem - ch * Lp;  // row fastest: coalesced 16 B chunks
-    __nv_bfloat16* dst = (which ? sV : sK) + (size_t)row * kAttStride + ch * 8;
+  // stage K, V with cp.async: thread = row (coalesced 16 B chunks across the warp), no divisions
+  for (int row = threadIdx.x; row < Lp; row += blockDim.x) {
+    const int rm = row % kAttChunks;
+    __nv_bfloat16* dk = sK + (size_t)row * kAttStride;
+    __nv_bfloat16* dv = sV + (size_t)row * kAttStride;
     if (row < L) {
-      const __nv_bfloat16* src = qkv + img_off(tok0 + row, (which ? vcol : kcol) + ch * 8, qkv_chunks);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+      const int tok = tok0 + row;
+      const size_t base = ((size_t)(tok / kTileM) * qkv_chunks) * kTileM * 8 + (size_t)(tok % kTileM) * 8;
+      const __nv_bfloat16* gk = qkv + base + (size_t)(kcol >> 3) * kTileM * 8;
+      const __nv_bfloat16* gv = qkv + base + (size_t)(vcol >> 3) * kTileM * 8;
+#pragma unroll
+      for (int ch = 0; ch < kAttChunks; ++ch) {
+        const int pc = att_rot(ch, rm) * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dk + pc)),
+                     "l"(gk + (size_t)ch * kTileM * 8) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dv + pc)),
+                     "l"(gv + (size_t)ch * kTileM * 8) : "memory");
+      }
     } else {
-      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int ch = 0; ch < kAttChunks; ++ch) {
+        *reinterpret_cast<uint4*>(dk + ch * 8) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dv + ch * 8) = make_uint4(0, 0, 0, 0);
+      }
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1292,6 +1317,9 @@ band_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
   if (warp * 16 < L) load_q(warp);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+#ifdef DCB_TRACE
+  const long long _t_staged = clock64();
+#endif
 
   for (int qb = warp; qb * 16 < L; qb += 4) {
     const int i0 = qb * 16;
@@ -1305,19 +1333,36 @@ band_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
     int jlo = i0 - band; if (jlo < 0) jlo = 0; jlo &= ~15;
     int jhi = i0 + 15 + band + 1; if (jhi > L) jhi = L;
     for (int j0 = jlo; j0 < jhi; j0 += 16) {
-      // S tile 16 x 16 = two n-tiles of 8 keys
-      float s[2][4];
+      // S tile 16 x 16 = two n-tiles of 8 keys; two partial accumulators per n-tile shorten the
+      // dependent HMMA chains (4 independent chains instead of 2)
+      float s[2][4], s2[2][4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        const __nv_bfloat16* krow = sK + (size_t)(j0 + nt * 8 + g) * kAttStride + 2 * t;
+        s2[nt][0] = s2[nt][1] = s2[nt][2] = s2[nt][3] = 0.f;
+      }
+      const int krow0 = j0 + g, krow1 = j0 + 8 + g;
+      const __nv_bfloat16* kr0 = sK + (size_t)krow0 * kAttStride + 2 * t;
+      const __nv_bfloat16* kr1 = sK + (size_t)krow1 * kAttStride + 2 * t;
+      const int km0 = krow0 % kAttChunks, km1 = krow1 % kAttChunks;
 #pragma unroll
-        for (int ks = 0; ks < kDHP / 16; ++ks) {
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks * 16);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 8);
-          mma_bf16_16816(s[nt], qa[ks], b0, b1);
+      for (int ks = 0; ks < kDHP / 16; ++ks) {
+        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(kr0 + att_rot(2 * ks, km0) * 8);
+        const uint32_t a1 = *reinterpret_cast<const uint32_t*>(kr0 + att_rot(2 * ks + 1, km0) * 8);
+        const uint32_t c0 = *reinterpret_cast<const uint32_t*>(kr1 + att_rot(2 * ks, km1) * 8);
+        const uint32_t c1 = *reinterpret_cast<const uint32_t*>(kr1 + att_rot(2 * ks + 1, km1) * 8);
+        if (ks & 1) {
+          mma_bf16_16816(s2[0], qa[ks], a0, a1);
+          mma_bf16_16816(s2[1], qa[ks], c0, c1);
+        } else {
+          mma_bf16_16816(s[0], qa[ks], a0, a1);
+          mma_bf16_16816(s[1], qa[ks], c0, c1);
         }
       }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[nt][e] += s2[nt][e];
       // mask: |i - j| <= band and j < L  (tf.where(mask, logits, -1e9): exp underflows to 0)
       float tmax0 = -INFINITY, tmax1 = -INFINITY;
 #pragma unroll
@@ -1364,12 +1409,14 @@ band_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
       l0 = l0 * sc0 + ps0;
       l1 = l1 * sc1 + ps1;
       // O = O * scale + P V
-      const uint32_t vbase = smem_u32(sV + (size_t)(j0 + (lane & 15)) * kAttStride);
+      const int vrow = j0 + (lane & 15);
+      const int vm = vrow % kAttChunks;
+      const uint32_t vbase = smem_u32(sV + (size_t)vrow * kAttStride);
 #pragma unroll
       for (int nt = 0; nt < kDHP / 8; ++nt) {
         o[nt][0] *= sc0; o[nt][1] *= sc0; o[nt][2] *= sc1; o[nt][3] *= sc1;
         uint32_t b0, b1;
-        ldmatrix_x2_trans(b0, b1, vbase + nt * 16);
+        ldmatrix_x2_trans(b0, b1, vbase + att_rot(nt, vm) * 16);
         mma_bf16_16816(o[nt], pa, b0, b1);
       }
     }
@@ -1390,6 +1437,14 @@ band_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
             pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
     }
   }
+#ifdef DCB_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 256) {
+    unsigned long long* tr = g_ffn_trace + blockIdx.x * 16;
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tr[13] = _t_staged - _t_start; tr[14] = clock64() - _t_staged; tr[15] = smid;
+  }
+#endif
 }
 
 // =====================================================================================

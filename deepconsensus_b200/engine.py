@@ -66,7 +66,7 @@ class DcbTensor(ctypes.Structure):
 # Every symbol include/dcb200.h declares; tests check the built library exports all of them.
 ABI_SYMBOLS = (
     "dcb_create", "dcb_load_weights", "dcb_forward", "dcb_last_forward_ms",
-    "dcb_last_forward_launches", "dcb_set_profile", "dcb_get_profile", "dcb_set_debug", "dcb_debug_residual", "dcb_debug_trace", "dcb_alloc_host",
+    "dcb_last_forward_launches", "dcb_set_profile", "dcb_get_profile", "dcb_get_profile_kernels", "dcb_set_debug", "dcb_debug_residual", "dcb_debug_trace", "dcb_alloc_host",
     "dcb_free_host", "dcb_alloc_device", "dcb_free_device", "dcb_memcpy_h2d", "dcb_memcpy_d2h",
     "dcb_synchronize", "dcb_last_error", "dcb_version", "dcb_destroy",
 )
@@ -96,6 +96,8 @@ def load_library() -> ctypes.CDLL:
   lib.dcb_set_profile.argtypes = [vp, i32]
   lib.dcb_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32),
                                   ctypes.POINTER(ctypes.c_int64)]
+  lib.dcb_get_profile_kernels.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32),
+                                          ctypes.POINTER(i32)]
   lib.dcb_debug_residual.argtypes = [vp, i32, vp, ctypes.c_int64]
   lib.dcb_alloc_host.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
   lib.dcb_free_host.argtypes = [vp]
@@ -268,7 +270,12 @@ class B200Model:
     ms, n, tok = ctypes.c_float(), ctypes.c_int32(), ctypes.c_int64()
     self._check(self._lib.dcb_get_profile(self._handle, ctypes.byref(ms), ctypes.byref(n),
                                           ctypes.byref(tok)))
-    return dict(ffn_ms_total=float(ms.value), ffn_launches=int(n.value), ffn_tokens=int(tok.value))
+    ms6, n6, fused = (ctypes.c_float * 6)(), (ctypes.c_int32 * 6)(), ctypes.c_int32()
+    self._check(self._lib.dcb_get_profile_kernels(self._handle, ms6, n6, ctypes.byref(fused)))
+    names = ("embed", "row_gemm", "qkv_gemm", "attention", "ffn", "head")
+    return dict(ffn_ms_total=float(ms.value), ffn_launches=int(n.value), ffn_tokens=int(tok.value),
+                fused_oproj=bool(fused.value),
+                kernels={k: dict(ms=float(ms6[i]), launches=int(n6[i])) for i, k in enumerate(names)})
 
   def set_debug(self, enabled: bool = True) -> None:
     self._check(self._lib.dcb_set_debug(self._handle, int(enabled)))

@@ -108,6 +108,10 @@ int dcb_last_forward_launches(dcb_engine* e, int32_t* n);
  * accumulated device time, launch count and tokens processed since dcb_set_profile. */
 int dcb_set_profile(dcb_engine* e, int32_t enabled);
 int dcb_get_profile(dcb_engine* e, float* ffn_ms_total, int32_t* ffn_launches, int64_t* ffn_tokens);
+/* Device time (ms) and launch count per kernel class since dcb_set_profile: [0] embed, [1] row GEMM
+ * (condenser / unfused out-proj), [2] QKV GEMM, [3] attention, [4] FFN (+ fused out-proj), [5] head;
+ * *fused_oproj = 1 when the attention out-projection runs inside the FFN kernel. */
+int dcb_get_profile_kernels(dcb_engine* e, float* ms6, int32_t* n6, int32_t* fused_oproj);
 
 /* Debug/test hook: copy the fp32 residual stream after stage `stage` of the LAST chunk of the
  * last forward into out [tokens, 280] (row-major).  stage 0 = condenser+pos-enc,
