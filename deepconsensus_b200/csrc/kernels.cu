@@ -886,17 +886,26 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
         }
       }
     }
-   } else if (warp == 1) {
+   } else if (warp == 1 || warp == 2) {
     if (lane == 0) {
       if (leader) {
-        // ----------------------------------------------------------- UMMA issuer (leader only)
+        // ----------------------------------------------------------- UMMA issuers (leader only)
+        // Two issuing threads share the tensor pipe: warp 1 issues the out-proj and every GEMM1,
+        // warp 2 every GEMM2.  (One thread alone spends ~70 cycles per UMMA on descriptor set-up,
+        // barrier polls and commits and cannot keep the pipe fed with 64-72-cycle instructions.)
+        // Both walk the same global sequence of ring stages and act only on their own.
         constexpr uint32_t idesc_h = make_idesc_bf16(2 * kTileM, kFFChunk);
         constexpr uint32_t idesc_y = make_idesc_bf16(2 * kTileM, kNC);
         constexpr uint16_t kBoth = 3;
+        const bool g1 = warp == 1;
         const uint32_t a_addr = smem_u32(sA);
         uint32_t slot = 0, phase = 0, n = 0;
         long long t_hfree = 0, t_full = 0, t_hsfull = 0, t_issue = 0, t_afull = 0, t_yempty = 0;
         const long long t_begin = clock64();
+        auto skip = [&](int count) {
+          for (int s = 0; s < count; ++s)
+            if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+        };
         auto gemm1 = [&](uint32_t nn) {
           TRACE_T0();
           mbar_wait_cluster(h_free, (nn & 1) ^ 1);
@@ -920,7 +929,7 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
           }
           umma_commit_pair(h_full, kBoth);
         };
-        auto gemm2 = [&](uint32_t nn, int c) {
+        auto gemm2 = [&](uint32_t nn) {
           const uint32_t b = nn & 1;
           TRACE_T0();
           mbar_wait_cluster(&hs_full[b], (nn >> 1) & 1);
@@ -950,62 +959,66 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
           umma_commit_pair(&hs_free[b], kBoth);
         };
         for (int ti = 0; ti < rounds; ++ti) {
-          { TRACE_T0(); mbar_wait_cluster(a_full, ti & 1); TRACE_ADD(t_afull); }
-          tc_fence_after();
-          if constexpr (kFuse) {
-            // Y (= x_old, stored by the row warps) += att * Wo^T
-            TRACE_T0();
-            mbar_wait_cluster(y_empty, ti & 1);
-            TRACE_ADD(t_yempty);
+          if (g1) {
+            { TRACE_T0(); mbar_wait_cluster(a_full, ti & 1); TRACE_ADD(t_afull); }
             tc_fence_after();
-            for (int s = 0; s < C::kWoStages; ++s) {
-              mbar_wait_cluster(&full[slot], phase);
-              tc_fence_after();
-              const uint32_t sb = smem_u32(sRing + slot * C::kSlotBytes);
-#pragma unroll
-              for (int kk = 0; kk < C::kWoStageK; ++kk) {
-                const int kstep = s * C::kWoStageK + kk;
-                const uint64_t adesc = make_kc16_desc(a_addr + kstep * 4096, kTileM * 16, 128);
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                  const uint64_t bdesc = make_kc16_desc(sb + kk * (2 * C::kW2Rows * 16) + j * (kNC / 2) * 16,
-                                                        C::kW2Rows * 16, 128);
-                  umma_bf16_ss_pair(tmem_base + C::kTmemY + j * kNC, adesc, bdesc, idesc_y, true);
-                }
-              }
-              umma_commit_pair(&empty[slot], kBoth);
-              if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
-            }
-            umma_commit_pair(ymid_full, kBoth);
-            mbar_wait_cluster(a2_full, ti & 1);   // FFN operand tile written by both CTAs' row warps
-            tc_fence_after();
-          }
-          gemm1(n);
-          for (int c = 0; c < nchunks; ++c) {
-            if (c + 1 < nchunks) {
-              gemm1(n + c + 1);
-            } else {
-              umma_commit_pair(a_empty, kBoth);
-            }
-            if (!kFuse && c == 0) {
+            if constexpr (kFuse) {
+              // Y (= x_old, stored by the row warps) += att * Wo^T
               TRACE_T0();
-              mbar_wait_cluster(y_empty, ti & 1);   // "Y holds x_old": both CTAs' row warps initialised it
+              mbar_wait_cluster(y_empty, ti & 1);
               TRACE_ADD(t_yempty);
               tc_fence_after();
+              for (int s = 0; s < C::kWoStages; ++s) {
+                mbar_wait_cluster(&full[slot], phase);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(sRing + slot * C::kSlotBytes);
+#pragma unroll
+                for (int kk = 0; kk < C::kWoStageK; ++kk) {
+                  const int kstep = s * C::kWoStageK + kk;
+                  const uint64_t adesc = make_kc16_desc(a_addr + kstep * 4096, kTileM * 16, 128);
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) {
+                    const uint64_t bdesc = make_kc16_desc(sb + kk * (2 * C::kW2Rows * 16) + j * (kNC / 2) * 16,
+                                                          C::kW2Rows * 16, 128);
+                    umma_bf16_ss_pair(tmem_base + C::kTmemY + j * kNC, adesc, bdesc, idesc_y, true);
+                  }
+                }
+                umma_commit_pair(&empty[slot], kBoth);
+                if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+              }
+              umma_commit_pair(ymid_full, kBoth);
+              mbar_wait_cluster(a2_full, ti & 1);   // FFN operand tile written by both CTAs' row warps
+              tc_fence_after();
             }
-            gemm2(n + c, c);
+            gemm1(n);
+            for (int c = 0; c < nchunks; ++c) {
+              if (c + 1 < nchunks) gemm1(n + c + 1);
+              else umma_commit_pair(a_empty, kBoth);   // every UMMA that reads sA has been issued
+              skip(C::kW2Stages);
+            }
+          } else {
+            if constexpr (kFuse) skip(C::kWoStages);
+            skip(C::kW1Stages);
+            for (int c = 0; c < nchunks; ++c) {
+              if (c + 1 < nchunks) skip(C::kW1Stages);
+              if (!kFuse && c == 0) {
+                mbar_wait_cluster(y_empty, ti & 1);   // "Y holds x_old": both CTAs' row warps initialised it
+                tc_fence_after();
+              }
+              gemm2(n + c);
+            }
+            umma_commit_pair(y_full, kBoth);
           }
-          umma_commit_pair(y_full, kBoth);
           n += nchunks;
         }
 #ifdef DCB_TRACE
-        if (blockIdx.x < 256) {
+        if (g1 && blockIdx.x < 256) {
           unsigned long long* tr = g_ffn_trace + blockIdx.x * 16;
           tr[0] = clock64() - t_begin; tr[1] = t_hfree; tr[2] = t_full; tr[3] = t_hsfull;
           tr[4] = t_issue; tr[5] = t_afull; tr[6] = t_yempty; tr[7] = rounds;
         }
 #endif
-      } else {
+      } else if (warp == 1) {
         // ----------------------------------------------------------- relay (peer): forward "my half
         // of this stage / my x tile has landed" to the leader's barriers, in consumption order
         uint32_t slot = 0, phase = 0;
@@ -1091,44 +1104,44 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
     } else {
       setmaxnreg_inc<216>();
       long long t_yfull = 0, t_row1 = 0, t_ldtm = 0, t_phaseA = 0;
-      for (int ti = 0; ti < rounds; ++ti) {
-        const int tile_raw = tile_of(ti);
-        const bool valid = tile_raw < ntiles;
+      const float4* xbase = reinterpret_cast<const float4*>(epi.x) + r;
+      auto xrow_of = [&](int tile) { return xbase + (size_t)tile * (x_image_elems() / 4); };
+      // ---- first tile: Y <- x_old (residual-in-accumulator), two batches of 9 column blocks
+      {
 #ifdef DCB_TRACE
         const long long _ta0 = clock64();
 #endif
-        // phase A: residual-in-accumulator.  Y <- x_old (tcgen05.st) so GEMM2 accumulates on top of it
-        // and the drain below needs no global loads.  (Y is free: this warp drained it last round.)
-        {
-          // two batches of 9 column blocks: all 36 16-byte loads of a batch are in flight together
-          // (HBM latency ~2000 cycles: bytes in flight per SM set the pace of this phase)
-          const int tile_ld = min(tile_raw, ntiles - 1);
-          const float4* xrow = reinterpret_cast<const float4*>(epi.x + (size_t)tile_ld * x_image_elems()) + r;
+        const float4* xrow = xrow_of(min(tile_of(0), ntiles - 1));
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float4 buf[9][4];
+        for (int half = 0; half < 2; ++half) {
+          float4 buf[9][4];
 #pragma unroll
-            for (int k = 0; k < 9; ++k)
+          for (int kq = 0; kq < 9; ++kq)
 #pragma unroll
-              for (int i = 0; i < 4; ++i) buf[k][i] = xrow[(size_t)((half * 9 + k) * 4 + i) * kTileM];
+            for (int i = 0; i < 4; ++i) buf[kq][i] = xrow[(size_t)((half * 9 + kq) * 4 + i) * kTileM];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-              uint32_t v[16];
+          for (int kq = 0; kq < 9; ++kq) {
+            uint32_t v[16];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                v[4 * i + 0] = __float_as_uint(buf[k][i].x); v[4 * i + 1] = __float_as_uint(buf[k][i].y);
-                v[4 * i + 2] = __float_as_uint(buf[k][i].z); v[4 * i + 3] = __float_as_uint(buf[k][i].w);
-              }
-              tmem_st16(tmem_row + C::kTmemY + (half * 9 + k) * 16, v);
+            for (int i = 0; i < 4; ++i) {
+              v[4 * i + 0] = __float_as_uint(buf[kq][i].x); v[4 * i + 1] = __float_as_uint(buf[kq][i].y);
+              v[4 * i + 2] = __float_as_uint(buf[kq][i].z); v[4 * i + 3] = __float_as_uint(buf[kq][i].w);
             }
+            tmem_st16(tmem_row + C::kTmemY + (half * 9 + kq) * 16, v);
           }
-          tmem_st_wait();
-          tc_fence_before();
-          arrive_leader(y_empty);
         }
+        tmem_st_wait();
+        tc_fence_before();
+        arrive_leader(y_empty);
 #ifdef DCB_TRACE
         t_phaseA += clock64() - _ta0;
 #endif
+      }
+      for (int ti = 0; ti < rounds; ++ti) {
+        const int tile_raw = tile_of(ti);
+        const bool valid = tile_raw < ntiles;
+        const bool has_next = ti + 1 < rounds;
+        const float4* xnext = xrow_of(min(tile_of(ti + 1), ntiles - 1));
         if constexpr (kFuse) {
           // mid epilogue: Y = x_mid after the out-proj.  Produce the FFN's bf16 operand tile in sA
           // (the attention tile there has been consumed: ymid_full follows the out-proj UMMAs).
@@ -1178,18 +1191,87 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
           fence_proxy_async_smem();
           arrive_leader(a2_full);
         }
-        // phase B: drain the finished tile
+        // ---- drain the finished tile AND re-initialise Y with the next tile's residual in the same
+        // pass: each 16-column block is read out (x_new = Y + b2 -> global) and immediately
+        // overwritten with x_old of the next tile, whose loads were issued kRowPF blocks ahead.
+        RowPrefetch pf;
+        if (has_next) {
+#pragma unroll
+          for (int kq = 0; kq < kRowPF; ++kq)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pf.buf[kq][i] = xnext[(size_t)(kq * 4 + i) * kTileM];
+        }
         TRACE_T0();
         mbar_wait(y_full, ti & 1);
         TRACE_ADD(t_yfull);
         tc_fence_after();
-        if (valid) {
-          RowEpi edr = epi;
-          edr.has_xold = 0;               // x_old is already inside the accumulator
-          RowPrefetch unused;
-          const RowStats st = row_epilogue_pass1(edr, tmem_row + C::kTmemY, tile_raw, r, unused, &t_ldtm);
+        {
+          const int tile_st = min(tile_raw, ntiles - 1);
+          float4* xrow = reinterpret_cast<float4*>(epi.x + (size_t)tile_st * x_image_elems()) + r;
+          uint4* xbrow = epi.xb ? reinterpret_cast<uint4*>(epi.xb + (size_t)tile_st * act_image_elems(kDP)) + r : nullptr;
+          const bool ln = epi.ln_g != nullptr;
+          float s1 = 0.f, s2 = 0.f, shift = 0.f;
+#pragma unroll
+          for (int cb = 0; cb < kDP / 16; ++cb) {
+            uint32_t acc[16];
+            tmem_ld16(tmem_row + C::kTmemY + cb * 16, acc);
+            tmem_ld_wait();
+            if (has_next) {
+              uint32_t nx[16];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 t = pf.buf[cb % kRowPF][i];
+                nx[4 * i + 0] = __float_as_uint(t.x); nx[4 * i + 1] = __float_as_uint(t.y);
+                nx[4 * i + 2] = __float_as_uint(t.z); nx[4 * i + 3] = __float_as_uint(t.w);
+              }
+              tmem_st16(tmem_row + C::kTmemY + cb * 16, nx);
+              if (cb + kRowPF < kDP / 16) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  pf.buf[cb % kRowPF][i] = xnext[(size_t)((cb + kRowPF) * 4 + i) * kTileM];
+              }
+            }
+            if (valid) {
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int col = cb * 16 + i;
+                float t = __uint_as_float(acc[i]);
+                if (epi.bias) t += __ldg(epi.bias + col);
+                v[i] = col < kD ? t : 0.f;
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                xrow[(size_t)(cb * 4 + i) * kTileM] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              if (ln) {
+                if (cb == 0) shift = v[0];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float dlt = (cb * 16 + i < kD) ? v[i] - shift : 0.f;
+                  s1 += dlt;
+                  s2 += dlt * dlt;
+                }
+              } else if (xbrow) {
+                xbrow[(size_t)(cb * 2) * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                              pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                xbrow[(size_t)(cb * 2 + 1) * kTileM] =
+                    make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                               pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+              }
+            }
+          }
+          if (has_next) {
+            tmem_st_wait();
+            tc_fence_before();
+            arrive_leader(y_empty);      // "Y holds x_old" of the next tile
+          }
           TRACE_ADD(t_row1);
-          if (epi.ln_g && epi.xb) row_epilogue_pass2<false>(epi, tile_raw, r, st.mean, st.rstd);
+          if (valid && ln && epi.xb) {
+            const float m1 = s1 * (1.f / kD);
+            const float mean = shift + m1;
+            const float rstd = rsqrtf(fmaxf(s2 * (1.f / kD) - m1 * m1, 0.f) + 1e-6f);
+            row_epilogue_pass2<false>(epi, tile_raw, r, mean, rstd);
+          }
         }
         tc_fence_before();
       }
@@ -1648,6 +1730,7 @@ void launch_ffn_pair(const __nv_bfloat16* a_img, const uint8_t* w2img, const flo
     int nc = 0;
     if (cudaOccupancyMaxActiveClusters(&nc, ffn_pair_kernel<false>, &cfg) != cudaSuccess || nc <= 0) nc = num_sms() / 2;
     max_pairs = nc;
+    if (const char* env = getenv("DCB_FFN_MAX_PAIRS")) { const int v = atoi(env); if (v > 0 && v < max_pairs) max_pairs = v; }
     if (getenv("DCB_VERBOSE")) fprintf(stderr, "[dcb200] ffn pair kernel: %d co-resident CTA pairs\n", nc);
   }
   int pairs = (ntiles + 1) / 2;
