@@ -1383,17 +1383,25 @@ band_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
   const int band = win > 0 ? win : L;  // attn_win_size None/0 => full attention
   constexpr float kLog2e = 1.4426950408889634f;
 
-  // Q fragments for 9 k-steps: rows i0+g, i0+g+8 (zero beyond L), straight from global
+  // Q fragments for 9 k-steps: rows i0+g, i0+g+8 (zero beyond L), straight from global.
+  // In the operand image a row's k-chunks are kTileM*8 elements apart, so every fragment address is
+  // the row base plus a compile-time constant (no per-load index arithmetic).
+  constexpr int kChunkElems = kTileM * 8;
   uint32_t qa[kDHP / 16][4];
   auto load_q = [&](int qb) {
     const int r0 = qb * 16 + g, r1 = r0 + 8;
+    const __nv_bfloat16* q0 = qkv + img_off(tok0 + (r0 < L ? r0 : 0), qcol + 2 * t, qkv_chunks);
+    const __nv_bfloat16* q1 = qkv + img_off(tok0 + (r1 < L ? r1 : 0), qcol + 2 * t, qkv_chunks);
 #pragma unroll
     for (int ks = 0; ks < kDHP / 16; ++ks) {
-      const int c0 = qcol + ks * 16 + 2 * t;
-      qa[ks][0] = r0 < L ? __ldg(reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r0, c0, qkv_chunks))) : 0u;
-      qa[ks][1] = r1 < L ? __ldg(reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r1, c0, qkv_chunks))) : 0u;
-      qa[ks][2] = r0 < L ? __ldg(reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r0, c0 + 8, qkv_chunks))) : 0u;
-      qa[ks][3] = r1 < L ? __ldg(reinterpret_cast<const uint32_t*>(qkv + img_off(tok0 + r1, c0 + 8, qkv_chunks))) : 0u;
+      const uint32_t v0 = __ldg(reinterpret_cast<const uint32_t*>(q0 + (2 * ks) * kChunkElems));
+      const uint32_t v1 = __ldg(reinterpret_cast<const uint32_t*>(q1 + (2 * ks) * kChunkElems));
+      const uint32_t v2 = __ldg(reinterpret_cast<const uint32_t*>(q0 + (2 * ks + 1) * kChunkElems));
+      const uint32_t v3 = __ldg(reinterpret_cast<const uint32_t*>(q1 + (2 * ks + 1) * kChunkElems));
+      qa[ks][0] = r0 < L ? v0 : 0u;
+      qa[ks][1] = r1 < L ? v1 : 0u;
+      qa[ks][2] = r0 < L ? v2 : 0u;
+      qa[ks][3] = r1 < L ? v3 : 0u;
     }
   };
   if (warp * 16 < L) load_q(warp);
@@ -1508,15 +1516,14 @@ band_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    __nv_bfloat16* o0 = att + img_off(tok0 + (r0 < L ? r0 : 0), head * kDHP + 2 * t, kDP / 8);
+    __nv_bfloat16* o1 = att + img_off(tok0 + (r1 < L ? r1 : 0), head * kDHP + 2 * t, kDP / 8);
 #pragma unroll
     for (int nt = 0; nt < kDHP / 8; ++nt) {
-      const int col = head * kDHP + nt * 8 + 2 * t;
       if (r0 < L)
-        *reinterpret_cast<uint32_t*>(att + img_off(tok0 + r0, col, kDP / 8)) =
-            pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
+        *reinterpret_cast<uint32_t*>(o0 + nt * kChunkElems) = pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
       if (r1 < L)
-        *reinterpret_cast<uint32_t*>(att + img_off(tok0 + r1, col, kDP / 8)) =
-            pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
+        *reinterpret_cast<uint32_t*>(o1 + nt * kChunkElems) = pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
     }
   }
 #ifdef DCB_TRACE
