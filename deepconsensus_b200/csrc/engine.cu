@@ -24,6 +24,7 @@ thread_local std::string g_create_error;
 
 struct LayerDev {
   __nv_bfloat16* wqkv = nullptr;  // 2 groups x [36][432][8]
+  uint8_t* wqkv2 = nullptr;       // 9 groups x [36][96][8] (qkv2_kernel)
   __nv_bfloat16* wo = nullptr;    // [36][288][8]
   uint8_t* wffn = nullptr;        // per ff chunk: [36][128][8] then [16][288][8]
   uint8_t* wffn2 = nullptr;       // CTA-pair image: per (chunk, rank): [36][64][8] then [16][144][8]
@@ -48,6 +49,7 @@ struct dcb_engine {
   bool debug = false;
   bool ffn_pair = true;
   bool fuse_oproj = true;
+  bool qkv2 = false;   // measured: not faster than gemm_kernel<3,QKV> (both sit on the per-SM L2 port), kept as an option
   bool fused_last = false;
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // around every launch when profiling
@@ -201,6 +203,7 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   e->echunks = e->Epad / 8;
   if (const char* env = getenv("DCB_FFN_PAIR")) e->ffn_pair = atoi(env) != 0;
   if (const char* env = getenv("DCB_FUSE_OPROJ")) e->fuse_oproj = atoi(env) != 0;
+  if (const char* env = getenv("DCB_QKV2")) e->qkv2 = atoi(env) != 0;
   int ct = cfg->chunk_tiles;
   if (const char* env = getenv("DCB_CHUNK_TILES")) ct = atoi(env);
   if (ct <= 0) ct = 8 * e->num_sms;   // measured: larger chunks win (kernels are not DRAM-bound)
@@ -386,6 +389,23 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
         img.insert(img.end(), part.begin(), part.end());
       }
       if ((rc = upload(e, &ld.wqkv, img))) return rc;
+      // 9 column groups of 96 for qkv2_kernel
+      std::vector<__nv_bfloat16> img9;
+      for (int grp = 0; grp < kQKVN / 96; ++grp) {
+        auto part = pack_b(kDP, 96, [&](int k, int nn) {
+          const int colg = grp * 96 + nn;
+          const int slot = colg / kDHP, dd = colg % kDHP;
+          if (k >= kD || dd >= kDH) return 0.f;
+          const int proj = slot / kHeads, head = slot % kHeads;
+          const float* w = proj == 0 ? wq : (proj == 1 ? wk : wv);
+          const float v = w[((size_t)k * kHeads + head) * kDH + dd];
+          return proj == 0 ? v * qscale : v;
+        });
+        img9.insert(img9.end(), part.begin(), part.end());
+      }
+      __nv_bfloat16* dptr = nullptr;
+      if ((rc = upload(e, &dptr, img9))) return rc;
+      ld.wqkv2 = reinterpret_cast<uint8_t*>(dptr);
     }
     {
       // out-proj: K index = head*144 + dd, N = e; ReZero alpha folded in (encoder_stack.py:88-90)
@@ -558,7 +578,8 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
       const LayerDev& ld = e->layers[n_];
       const bool last = n_ + 1 == c.num_hidden_layers;
       pbegin(2);
-      launch_gemm_qkv(e->d_xb, ld.wqkv, T, e->d_embqkv, st);
+      if (e->qkv2) launch_qkv2(e->d_xb, ld.wqkv2, T, e->d_embqkv, st);
+      else launch_gemm_qkv(e->d_xb, ld.wqkv, T, e->d_embqkv, st);
       pend();
       pbegin(3);
       launch_attention(e->d_embqkv, e->d_att, L, c.attn_win_size, bw, st);

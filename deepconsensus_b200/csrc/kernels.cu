@@ -377,6 +377,166 @@ gemm_kernel(const __nv_bfloat16* __restrict__ a_img, const __nv_bfloat16* __rest
 }
 
 // =====================================================================================
+// fused q/k/v projection, two tiles per weight pass
+// =====================================================================================
+// The QKV projection re-reads 498 KB of weights per 128-token tile, and an SM ingests only about
+// 30-50 B/cycle from L2, so the per-tile weight stream (not the 7.8 k cycles of UMMA work) sets the
+// pace.  This kernel therefore keeps TWO x tiles resident in shared memory and runs both against
+// every weight stage (halving the weight bytes per token), processes the 864 output columns in 9
+// groups of 96, and double-buffers the accumulators in TMEM (2 x [2 tiles x 96 cols]) so the
+// epilogue of group g (TMEM -> bf16 -> qkv operand image) overlaps the UMMAs of group g+1.
+struct Qkv2Cfg {
+  static constexpr int kGroupN = 96;
+  static constexpr int kGroups = kQKVN / kGroupN;                    // 9
+  static constexpr int kABytes = (kDP / 8) * kTileM * 16;            // 73728 per tile
+  static constexpr int kStageK = 6;
+  static constexpr int kStages = (kDP / 16) / kStageK;               // 3 stages per group
+  static constexpr int kStageBytes = kStageK * 2 * kGroupN * 16;     // 18432
+  static constexpr int kSlots = 3;
+  static constexpr int kGroupBytes = kStages * kStageBytes;          // 55296
+  static constexpr int kOffA0 = 0;
+  static constexpr int kOffA1 = kABytes;
+  static constexpr int kOffRing = 2 * kABytes;
+  static constexpr int kOffBars = kOffRing + kSlots * kStageBytes;
+  static constexpr int kSmemBytes = kOffBars + 256;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kThreads = 320;   // producer, UMMA issuer, 8 epilogue warps (4 per tile)
+};
+
+__global__ void __launch_bounds__(Qkv2Cfg::kThreads, 1)
+qkv2_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ b_img, int ntiles,
+            __nv_bfloat16* __restrict__ out_img) {
+  using C = Qkv2Cfg;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA[2] = {smem + C::kOffA0, smem + C::kOffA1};
+  uint8_t* sRing = smem + C::kOffRing;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
+  uint64_t* full = bars;                  // [kSlots]
+  uint64_t* empty = bars + C::kSlots;     // [kSlots]
+  uint64_t* a_full = bars + 2 * C::kSlots;
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* acc_full = a_full + 2;        // [2]
+  uint64_t* acc_empty = a_full + 4;       // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 6);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int npairs = (ntiles + 1) >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 256);
+    mbar_init(&acc_empty[1], 256);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0, it = 0;
+      for (int p = blockIdx.x; p < npairs; p += gridDim.x, ++it) {
+        mbar_wait(a_empty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(a_full, 2 * C::kABytes);
+        const int t0 = 2 * p, t1 = min(2 * p + 1, ntiles - 1);
+        bulk_g2s(sA[0], reinterpret_cast<const uint8_t*>(a_img) + (size_t)t0 * C::kABytes, C::kABytes, a_full);
+        bulk_g2s(sA[1], reinterpret_cast<const uint8_t*>(a_img) + (size_t)t1 * C::kABytes, C::kABytes, a_full);
+        for (int g = 0; g < C::kGroups; ++g)
+          for (int s = 0; s < C::kStages; ++s) {
+            mbar_wait(&empty[slot], phase ^ 1);
+            mbar_arrive_expect_tx(&full[slot], C::kStageBytes);
+            bulk_g2s(sRing + slot * C::kStageBytes, b_img + (size_t)g * C::kGroupBytes + s * C::kStageBytes,
+                     C::kStageBytes, &full[slot]);
+            if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, C::kGroupN);
+      const uint32_t a_addr[2] = {smem_u32(sA[0]), smem_u32(sA[1])};
+      uint32_t slot = 0, phase = 0, it = 0, gi = 0;
+      for (int p = blockIdx.x; p < npairs; p += gridDim.x, ++it) {
+        mbar_wait(a_full, it & 1);
+        tc_fence_after();
+        for (int g = 0; g < C::kGroups; ++g, ++gi) {
+          const uint32_t buf = gi & 1;
+          mbar_wait(&acc_empty[buf], ((gi >> 1) & 1) ^ 1);
+          tc_fence_after();
+          for (int s = 0; s < C::kStages; ++s) {
+            mbar_wait(&full[slot], phase);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(sRing + slot * C::kStageBytes);
+#pragma unroll
+            for (int kk = 0; kk < C::kStageK; ++kk) {
+              const int kstep = s * C::kStageK + kk;
+              const uint64_t bdesc = make_kc16_desc(sb + kk * (2 * C::kGroupN * 16), C::kGroupN * 16, 128);
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                const uint64_t adesc = make_kc16_desc(a_addr[t] + kstep * 4096, kTileM * 16, 128);
+                umma_bf16_ss(tmem_base + buf * (2 * C::kGroupN) + t * C::kGroupN, adesc, bdesc, idesc, kstep != 0);
+              }
+            }
+            umma_commit(&empty[slot]);
+            if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+          }
+          umma_commit(&acc_full[buf]);
+        }
+        umma_commit(a_empty);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int t = (warp - 2) >> 2;          // which tile of the pair
+    const int r = q * 32 + lane;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t gi = 0;
+    for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
+      const int tile = 2 * p + t;
+      const bool valid = tile < ntiles;
+      uint4* orow = reinterpret_cast<uint4*>(out_img + (size_t)(valid ? tile : 0) * kTileM * kQKVN) + r;
+      for (int g = 0; g < C::kGroups; ++g, ++gi) {
+        const uint32_t buf = gi & 1;
+        mbar_wait(&acc_full[buf], (gi >> 1) & 1);
+        tc_fence_after();
+        uint32_t acc[C::kGroupN / 16][16];
+#pragma unroll
+        for (int cb = 0; cb < C::kGroupN / 16; ++cb)
+          tmem_ld16(tmem_row + buf * (2 * C::kGroupN) + t * C::kGroupN + cb * 16, acc[cb]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf]);
+        if (valid) {
+#pragma unroll
+          for (int cb = 0; cb < C::kGroupN / 16; ++cb) {
+            const int kc = (g * C::kGroupN + cb * 16) / 8;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[cb][i]);
+            orow[(size_t)kc * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                   pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            orow[(size_t)(kc + 1) * kTileM] =
+                make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                           pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// =====================================================================================
 // fused FFN
 // =====================================================================================
 struct FfnCfg {
@@ -1651,6 +1811,8 @@ cudaError_t kernels_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(ffn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg::kSmemBytes);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(qkv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Qkv2Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(embed_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(band_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1684,6 +1846,13 @@ void launch_gemm_qkv(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int
   RowEpi none{};
   gemm_kernel<3, EPI_QKV><<<grid, 192, GemmCfg<3>::kSmemBytes, st>>>(a_img, b_img, kDP / 16, ntiles, 2,
                                                                      qkv_img, kQKVN / 8, none);
+}
+
+void launch_qkv2(const __nv_bfloat16* a_img, const uint8_t* b_img, int ntiles, __nv_bfloat16* qkv_img,
+                 cudaStream_t st) {
+  const int npairs = (ntiles + 1) / 2;
+  const int grid = npairs < num_sms() ? npairs : num_sms();
+  qkv2_kernel<<<grid, Qkv2Cfg::kThreads, Qkv2Cfg::kSmemBytes, st>>>(a_img, b_img, ntiles, qkv_img);
 }
 
 void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int win, int nwindows,

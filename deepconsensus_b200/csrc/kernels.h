@@ -18,6 +18,9 @@ void launch_gemm_row(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int
 // fused q/k/v projection: A [tile][36][128][8] -> qkv image [tile][108][128][8]
 void launch_gemm_qkv(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int ntiles,
                      __nv_bfloat16* qkv_img, cudaStream_t st);
+// two-tiles-per-weight-pass QKV projection; b_img: 9 groups x [36][96][8]
+void launch_qkv2(const __nv_bfloat16* a_img, const uint8_t* b_img, int ntiles, __nv_bfloat16* qkv_img,
+                 cudaStream_t st);
 void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int win, int nwindows,
                       cudaStream_t st);
 // CTA-pair (cta_group::2) version; w2img is the per-rank half-chunk weight image.
