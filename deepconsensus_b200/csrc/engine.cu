@@ -49,6 +49,7 @@ struct dcb_engine {
   bool debug = false;
   bool ffn_pair = true;
   bool fuse_oproj = true;
+  bool fuse_embed = true;
   bool qkv2 = false;   // measured: not faster than gemm_kernel<3,QKV> (both sit on the per-SM L2 port), kept as an option
   bool fused_last = false;
   bool profile = false;
@@ -204,6 +205,7 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   if (const char* env = getenv("DCB_FFN_PAIR")) e->ffn_pair = atoi(env) != 0;
   if (const char* env = getenv("DCB_FUSE_OPROJ")) e->fuse_oproj = atoi(env) != 0;
   if (const char* env = getenv("DCB_QKV2")) e->qkv2 = atoi(env) != 0;
+  if (const char* env = getenv("DCB_FUSE_EMBED")) e->fuse_embed = atoi(env) != 0;
   int ct = cfg->chunk_tiles;
   if (const char* env = getenv("DCB_CHUNK_TILES")) ct = atoi(env);
   if (ct <= 0) ct = 8 * e->num_sms;   // measured: larger chunks win (kernels are not DRAM-bound)
@@ -557,10 +559,6 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
       if (e->debug) cudaMemcpyAsync(e->d_dbg + (size_t)stage * e->chunk_tiles * ximg, e->d_x, (size_t)T * ximg * sizeof(float), cudaMemcpyDeviceToDevice, st);
       ++stage;
     };
-    pbegin(0);
-    launch_embed(rows_chunk, R, L, M, T, e->echunks, e->d_cols, e->d_rowmeta, e->d_tables, e->table_elems, e->d_embqkv, e->d_status, st);
-    pend();
-    ++launches;
     {
       RowEpi epi{};
       epi.x = e->d_x; epi.xb = e->d_xb; epi.bias = nullptr;
@@ -568,10 +566,23 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
       epi.ln_g = c.rezero ? nullptr : e->layers[0].ln_g[0];
       epi.ln_b = c.rezero ? nullptr : e->layers[0].ln_b[0];
       epi.has_xold = 0; epi.L = L;
-      pbegin(1);
-      launch_gemm_row(e->d_embqkv, e->d_wc, e->Epad / 16, T, epi, st);
-      pend();
-      ++launches;
+      bool fused_embed = false;
+      if (e->fuse_embed) {
+        pbegin(1);
+        fused_embed = launch_embed_condense(rows_chunk, R, L, M, T, e->echunks, e->d_cols, e->d_rowmeta, e->d_tables,
+                                            e->table_elems, e->d_wc, epi, e->d_status, st);
+        pend();
+        if (fused_embed) ++launches;
+      }
+      if (!fused_embed) {
+        pbegin(0);
+        launch_embed(rows_chunk, R, L, M, T, e->echunks, e->d_cols, e->d_rowmeta, e->d_tables, e->table_elems, e->d_embqkv, e->d_status, st);
+        pend();
+        pbegin(1);
+        launch_gemm_row(e->d_embqkv, e->d_wc, e->Epad / 16, T, epi, st);
+        pend();
+        launches += 2;
+      }
       snap();
     }
     for (int n_ = 0; n_ < c.num_hidden_layers; ++n_) {

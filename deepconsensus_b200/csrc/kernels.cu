@@ -181,12 +181,22 @@ __device__ __forceinline__ RowStats row_epilogue_pass1(const RowEpi& e, uint32_t
 #ifdef DCB_TRACE
     if (t_ldtm) *t_ldtm += clock64() - _tl0;
 #endif
+    float pev[16];
+    if (e.pe) {
+      // one token's 16 positional values are 64 contiguous bytes: 4 x 128-bit loads (rows differ per lane)
+      const float4* pr = reinterpret_cast<const float4*>(e.pe + (size_t)l * kDP + cb * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 t = __ldg(pr + i);
+        pev[4 * i + 0] = t.x; pev[4 * i + 1] = t.y; pev[4 * i + 2] = t.z; pev[4 * i + 3] = t.w;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int col = cb * 16 + i;
       float t = v[i] + __uint_as_float(acc[i]);
       if (e.bias) t += __ldg(e.bias + col);
-      if (e.pe) t += __ldg(e.pe + (size_t)l * kDP + col);
+      if (e.pe) t += pev[i];
       v[i] = col < kD ? t : 0.f;
     }
 #pragma unroll
@@ -374,6 +384,232 @@ gemm_kernel(const __nv_bfloat16* __restrict__ a_img, const __nv_bfloat16* __rest
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+}
+
+// =====================================================================================
+// fused embedding + condenser
+// =====================================================================================
+// Builds the concatenated-embedding operand (networks.py:457-507) straight into shared memory, K-slab
+// by K-slab, and multiplies it with the condenser weights (networks.py:426-434) -- the [tokens x E]
+// bf16 embedding never goes to HBM.  Roles: warp 0 streams condenser-weight slabs (bulk copies), warp 1
+// issues the UMMAs, warps 2-9 turn the tile's R x 128 input values into table ids (format_rows clip,
+// shift, truncate, range check) and then assemble 16-byte K-chunks of each slab from the shared-memory
+// tables, warps 10-13 run the row epilogue (+positional encoding, fp32 residual image, next sub-layer's
+// bf16 operand / LayerNorm).
+struct EmbCfg {
+  static constexpr int kSlabK = 5;                                   // k-steps per A slab / B stage
+  static constexpr int kASlabBytes = kSlabK * 2 * kTileM * 16;       // 20480
+  static constexpr int kBSlabBytes = kSlabK * 2 * kDP * 16;          // 46080
+  static constexpr int kThreads = 512;   // 4 warpgroups: {producer, UMMA, 2 idle}, 2 x builders, row epilogue
+  static constexpr int kTmemCols = 512;
+};
+
+__global__ void __launch_bounds__(EmbCfg::kThreads, 1)
+embed_condense_kernel(const float* __restrict__ rows, int R, int L, int M, int ntiles, int echunks,
+                      const EmbedCol* __restrict__ cols, const EmbedRow* __restrict__ rowmeta,
+                      const __nv_bfloat16* __restrict__ tables, int table_elems,
+                      const __nv_bfloat16* __restrict__ wc_img, RowEpi epi, int* __restrict__ status) {
+  using C = EmbCfg;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tab_bytes = (table_elems * 2 + 127) & ~127;
+  const int cols_bytes = (echunks * 8 * (int)sizeof(EmbedCol) + 127) & ~127;
+  const int ids_bytes = (R * kTileM * 2 + 127) & ~127;
+  __nv_bfloat16* s_tab = reinterpret_cast<__nv_bfloat16*>(smem);
+  EmbedCol* s_cols = reinterpret_cast<EmbedCol*>(smem + tab_bytes);
+  uint16_t* s_ids = reinterpret_cast<uint16_t*>(smem + tab_bytes + cols_bytes);
+  uint8_t* sAslab = smem + ((tab_bytes + cols_bytes + ids_bytes + 1023) & ~1023);
+  uint8_t* sB = sAslab + 2 * C::kASlabBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * C::kBSlabBytes);
+  uint64_t* a_full = bars;          // [2] builders -> MMA
+  uint64_t* a_empty = bars + 2;     // [2] MMA -> builders
+  uint64_t* b_full = bars + 4;      // [2]
+  uint64_t* b_empty = bars + 6;     // [2]
+  uint64_t* acc_full = bars + 8;
+  uint64_t* acc_empty = bars + 9;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 10);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ksteps = echunks / 2;
+  const int nslabs = (ksteps + C::kSlabK - 1) / C::kSlabK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 256);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < table_elems; i += blockDim.x) s_tab[i] = tables[i];
+  for (int i = threadIdx.x; i < echunks * 8; i += blockDim.x) s_cols[i] = cols[i];
+  if (warp == 1) tmem_alloc(tmem_holder, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp < 4) {
+   setmaxnreg_dec<56>();
+   if (warp == 0) {
+    // ------------------------------------------------------------- condenser-weight producer
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+        for (int sl = 0; sl < nslabs; ++sl, ++n) {
+          const uint32_t b = n & 1;
+          const int kh = min(C::kSlabK, ksteps - sl * C::kSlabK);
+          mbar_wait(&b_empty[b], ((n >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&b_full[b], kh * 2 * kDP * 16);
+          bulk_g2s(sB + b * C::kBSlabBytes,
+                   reinterpret_cast<const uint8_t*>(wc_img) + (size_t)sl * C::kBSlabBytes, kh * 2 * kDP * 16,
+                   &b_full[b]);
+        }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- UMMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, kNC);
+      uint32_t n = 0, it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        mbar_wait(acc_empty, (it & 1) ^ 1);
+        tc_fence_after();
+        for (int sl = 0; sl < nslabs; ++sl, ++n) {
+          const uint32_t b = n & 1;
+          const int kh = min(C::kSlabK, ksteps - sl * C::kSlabK);
+          mbar_wait(&a_full[b], (n >> 1) & 1);
+          mbar_wait(&b_full[b], (n >> 1) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(sAslab + b * C::kASlabBytes);
+          const uint32_t sb = smem_u32(sB + b * C::kBSlabBytes);
+          for (int kk = 0; kk < kh; ++kk) {
+            const uint64_t adesc = make_kc16_desc(sa + kk * 4096, kTileM * 16, 128);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t bdesc = make_kc16_desc(sb + kk * (2 * kDP * 16) + j * kNC * 16, kDP * 16, 128);
+              umma_bf16_ss(tmem_base + j * kNC, adesc, bdesc, idesc, (sl | kk) != 0);
+            }
+          }
+          umma_commit(&a_empty[b]);
+          umma_commit(&b_empty[b]);
+        }
+        umma_commit(acc_full);
+      }
+    }
+   }
+  } else if (warp < 12) {
+    setmaxnreg_dec<72>();
+    // ------------------------------------------------------------- builders (256 threads)
+    const int bt = threadIdx.x - 128;   // 0..255
+    uint32_t n = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      // every slab of the previous tile has been built (program order), but its last reads of s_ids
+      // happen in other builder threads: synchronise the builders before overwriting the ids
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      {
+        // thread = (token r, input rows rr0, rr0+2, ...): 8 independent global loads in flight per batch
+        const int r = bt & (kTileM - 1), rr0 = bt >> 7;
+        const int tok = tile * kTileM + r;
+        const bool tvalid = tok < M;
+        const int bw = tvalid ? tok / L : 0, l = tvalid ? tok - bw * L : 0;
+        const float* base = rows + (size_t)bw * R * L + l;
+        for (int rr = rr0; rr < R; rr += 16) {
+          float f[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int ru = rr + 2 * u;
+            f[u] = (tvalid && ru < R) ? __ldg(base + (size_t)ru * L) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int ru = rr + 2 * u;
+            if (ru < R) {
+              int id = 0;
+              if (tvalid) {
+                const EmbedRow m = rowmeta[ru];
+                float v = f[u];
+                if (m.clip_hi > 0.f) v = fminf(fmaxf(v, 0.f), m.clip_hi);  // format_rows (data_providers.py:151-162)
+                v += (float)m.shift;                                         // networks.py:495
+                id = (int)v;                                                 // tf.cast(float32 -> int32) truncates
+                if (id < 0 || id >= m.vocab) {
+                  atomicOr(status, 1);
+                  id = id < 0 ? 0 : m.vocab - 1;
+                }
+              }
+              s_ids[ru * kTileM + r] = (uint16_t)id;
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int sl = 0; sl < nslabs; ++sl, ++n) {
+        const uint32_t b = n & 1;
+        const int kh = min(C::kSlabK, ksteps - sl * C::kSlabK);
+        mbar_wait(&a_empty[b], ((n >> 1) & 1) ^ 1);
+        uint4* dst = reinterpret_cast<uint4*>(sAslab + b * C::kASlabBytes);
+        for (int idx = bt; idx < kh * 2 * kTileM; idx += 256) {
+          const int kcl = idx / kTileM, r = idx % kTileM;
+          const int kc = sl * C::kSlabK * 2 + kcl;
+          uint4 val;
+          const EmbedCol c0 = s_cols[kc * 8];
+          if (c0.width == 8 && c0.col == 0 && c0.src_row >= 0) {
+            const int id = s_ids[c0.src_row * kTileM + r];
+            val = *reinterpret_cast<const uint4*>(s_tab + c0.table_off + id * 8);
+          } else {
+            uint32_t packed[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t pr = 0;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const EmbedCol c = s_cols[kc * 8 + 2 * j + h];
+                uint32_t bits = 0;
+                if (c.src_row >= 0) {
+                  const int id = s_ids[c.src_row * kTileM + r];
+                  bits = __bfloat16_as_ushort(s_tab[c.table_off + id * c.width + c.col]);
+                }
+                pr |= bits << (16 * h);
+              }
+              packed[j] = pr;
+            }
+            val = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          }
+          dst[(size_t)kcl * kTileM + r] = val;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&a_full[b]);
+      }
+    }
+  } else {
+    setmaxnreg_inc<216>();
+    // ------------------------------------------------------------- row epilogue (4 warps)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      RowPrefetch pf;
+      mbar_wait(acc_full, it & 1);
+      tc_fence_after();
+      const RowStats st = row_epilogue_pass1(epi, tmem_row, tile, r, pf);
+      tc_fence_before();
+      mbar_arrive(acc_empty);
+      if (epi.ln_g && epi.xb) row_epilogue_pass2<false>(epi, tile, r, st.mean, st.rstd);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+size_t embed_condense_smem_bytes(int R, int echunks, int table_elems) {
+  const size_t tab = (table_elems * 2 + 127) & ~127, colsb = (echunks * 8 * sizeof(EmbedCol) + 127) & ~(size_t)127;
+  const size_t ids = ((size_t)R * kTileM * 2 + 127) & ~(size_t)127;
+  return ((tab + colsb + ids + 1023) & ~(size_t)1023) + 2 * EmbCfg::kASlabBytes + 2 * EmbCfg::kBSlabBytes + 256;
 }
 
 // =====================================================================================
@@ -1811,6 +2047,8 @@ cudaError_t kernels_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(ffn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg::kSmemBytes);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(embed_condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(qkv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Qkv2Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(embed_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -1846,6 +2084,17 @@ void launch_gemm_qkv(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int
   RowEpi none{};
   gemm_kernel<3, EPI_QKV><<<grid, 192, GemmCfg<3>::kSmemBytes, st>>>(a_img, b_img, kDP / 16, ntiles, 2,
                                                                      qkv_img, kQKVN / 8, none);
+}
+
+bool launch_embed_condense(const float* rows, int R, int L, int M, int ntiles, int echunks, const EmbedCol* cols,
+                           const EmbedRow* rowmeta, const __nv_bfloat16* tables, int table_elems,
+                           const __nv_bfloat16* wc_img, const RowEpi& epi, int* status, cudaStream_t st) {
+  const size_t smem = embed_condense_smem_bytes(R, echunks, table_elems);
+  if (smem > 227 * 1024) return false;
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  embed_condense_kernel<<<grid, EmbCfg::kThreads, smem, st>>>(rows, R, L, M, ntiles, echunks, cols, rowmeta, tables,
+                                                              table_elems, wc_img, epi, status);
+  return true;
 }
 
 void launch_qkv2(const __nv_bfloat16* a_img, const uint8_t* b_img, int ntiles, __nv_bfloat16* qkv_img,

@@ -18,6 +18,11 @@ void launch_gemm_row(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int
 // fused q/k/v projection: A [tile][36][128][8] -> qkv image [tile][108][128][8]
 void launch_gemm_qkv(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int ntiles,
                      __nv_bfloat16* qkv_img, cudaStream_t st);
+// fused embedding + condenser (+pos-enc, residual image, next operand); false if it does not fit smem
+size_t embed_condense_smem_bytes(int R, int echunks, int table_elems);
+bool launch_embed_condense(const float* rows, int R, int L, int M, int ntiles, int echunks, const EmbedCol* cols,
+                           const EmbedRow* rowmeta, const __nv_bfloat16* tables, int table_elems,
+                           const __nv_bfloat16* wc_img, const RowEpi& epi, int* status, cudaStream_t st);
 // two-tiles-per-weight-pass QKV projection; b_img: 9 groups x [36][96][8]
 void launch_qkv2(const __nv_bfloat16* a_img, const uint8_t* b_img, int ntiles, __nv_bfloat16* qkv_img,
                  cudaStream_t st);
