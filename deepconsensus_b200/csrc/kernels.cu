@@ -1946,14 +1946,21 @@ head_kernel(HeadParams p) {
   const int tok = tile * kTileM + r;
   if (tok >= p.M) return;
   const float4* xrow = reinterpret_cast<const float4*>(p.x + (size_t)tile * x_image_elems()) + r;
-  // pass 1: mean / variance (biased, eps = 1e-6: encoder_stack.py:131-133)
+  // pass 1: mean / variance (biased, eps = 1e-6: encoder_stack.py:131-133); 10 loads in flight per batch
   float s1 = 0.f, s2 = 0.f;
   const float shift = xrow[0].x;
-  for (int ch = 0; ch < kD / 4; ++ch) {
-    const float4 v = xrow[(size_t)ch * kTileM];
-    const float a = v.x - shift, b = v.y - shift, c = v.z - shift, d = v.w - shift;
-    s1 += (a + b) + (c + d);
-    s2 += (a * a + b * b) + (c * c + d * d);
+  constexpr int kHB = 10;
+  static_assert((kD / 4) % kHB == 0, "head batch");
+  for (int c0 = 0; c0 < kD / 4; c0 += kHB) {
+    float4 v[kHB];
+#pragma unroll
+    for (int u = 0; u < kHB; ++u) v[u] = xrow[(size_t)(c0 + u) * kTileM];
+#pragma unroll
+    for (int u = 0; u < kHB; ++u) {
+      const float a = v[u].x - shift, b = v[u].y - shift, c = v[u].z - shift, d = v[u].w - shift;
+      s1 += (a + b) + (c + d);
+      s2 += (a * a + b * b) + (c * c + d * d);
+    }
   }
   const float m1 = s1 * (1.f / kD);
   const float mean = shift + m1;
@@ -1962,15 +1969,20 @@ head_kernel(HeadParams p) {
   float lg[kVocab];
 #pragma unroll
   for (int j = 0; j < kVocab; ++j) lg[j] = 0.f;
-  for (int ch = 0; ch < kD / 4; ++ch) {
-    const float4 v = xrow[(size_t)ch * kTileM];
-    const float xs[4] = {v.x, v.y, v.z, v.w};
+  for (int c0 = 0; c0 < kD / 4; c0 += kHB) {
+    float4 v[kHB];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int col = ch * 4 + i;
-      const float z = (xs[i] - mean) * rstd * sG[col] + sBt[col];
+    for (int u = 0; u < kHB; ++u) v[u] = xrow[(size_t)(c0 + u) * kTileM];
 #pragma unroll
-      for (int j = 0; j < kVocab; ++j) lg[j] = fmaf(z, sW[col * kVocab + j], lg[j]);
+    for (int u = 0; u < kHB; ++u) {
+      const float xs[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int col = (c0 + u) * 4 + i;
+        const float z = (xs[i] - mean) * rstd * sG[col] + sBt[col];
+#pragma unroll
+        for (int j = 0; j < kVocab; ++j) lg[j] = fmaf(z, sW[col * kVocab + j], lg[j]);
+      }
     }
   }
   float mx = -INFINITY;
