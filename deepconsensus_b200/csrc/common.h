@@ -57,11 +57,11 @@ struct RowEpi {
   float* x;              // fp32 residual image of the chunk (read when has_xold, always written)
   __nv_bfloat16* xb;     // bf16 operand image for the next GEMM (may be null: skip)
   const float* bias;     // [288] or null
-  const float* pe;       // [L][288] or null
+  const float* pe;       // [Lw][288] or null (rows >= max_length are zero)
   const float* ln_g;     // [288] or null  (null => xb = bf16(x_new))
   const float* ln_b;     // [288]
   int has_xold;
-  int L;
+  int L;                 // tokens per window in the flattened layout (Lw): position = token % L
 };
 
 struct HeadParams {
@@ -74,7 +74,8 @@ struct HeadParams {
   uint8_t* quals;        // [M] Phred+33
   float* probs;          // [M][5] or null
   float* logits;         // [M][5] or null
-  int M;                 // valid tokens
+  int M;                 // tokens in the layout (windows * Lw)
+  int L, Lw;             // window length / tokens per window in the layout (Lw >= L: padding rows are skipped)
   int calib_enabled;
   float calib_thr, calib_w, calib_b;
   double calib_w64, calib_b64, calib_thr64;

@@ -40,7 +40,7 @@ struct LayerDev {
 struct dcb_engine {
   dcb_config cfg{};
   std::string err;
-  int R = 0, L = 0, E = 0, Epad = 0, echunks = 0;
+  int R = 0, L = 0, Lw = 0, E = 0, Epad = 0, echunks = 0;   // Lw: tokens per window in the layout (>= L)
   int chunk_tiles = 0, chunk_windows = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
@@ -195,6 +195,14 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   e->cfg = *cfg;
   e->num_sms = prop.multiProcessorCount;
   e->L = cfg->max_length;
+  // window-aligned tiling: one window per 128-token tile when it fits (lets QKV + attention fuse);
+  // otherwise windows are packed back to back
+  e->Lw = e->L;
+  {
+    const char* env = getenv("DCB_ALIGN");
+    const bool align = env ? atoi(env) != 0 : true;
+    if (align && e->L <= kTileM) e->Lw = kTileM;
+  }
   e->R = 4 * cfg->max_passes + (cfg->use_ccs_bq ? 6 : 5);  // data_providers.py:61-78
   e->E = cfg->max_passes * (cfg->per_base_hidden_size + cfg->pw_hidden_size + cfg->ip_hidden_size +
                             cfg->strand_hidden_size) +
@@ -209,9 +217,9 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   int ct = cfg->chunk_tiles;
   if (const char* env = getenv("DCB_CHUNK_TILES")) ct = atoi(env);
   if (ct <= 0) ct = 8 * e->num_sms;   // measured: larger chunks win (kernels are not DRAM-bound)
-  const int max_tiles = (int)(((int64_t)cfg->max_batch * e->L + kTileM - 1) / kTileM);
-  e->chunk_windows = std::max(1, std::min(cfg->max_batch, ct * kTileM / e->L));
-  e->chunk_tiles = std::min(max_tiles, (e->chunk_windows * e->L + kTileM - 1) / kTileM);
+  const int max_tiles = (int)(((int64_t)cfg->max_batch * e->Lw + kTileM - 1) / kTileM);
+  e->chunk_windows = std::max(1, std::min(cfg->max_batch, ct * kTileM / e->Lw));
+  e->chunk_tiles = std::min(max_tiles, (e->chunk_windows * e->Lw + kTileM - 1) / kTileM);
 
   auto bail = [&](int rc) { std::string m = e->err; dcb_destroy(e); g_create_error = m; return rc; };
 #define TRY(x) do { int _rc = (x); if (_rc) return bail(_rc); } while (0)
@@ -334,7 +342,7 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
   }
   // ---- positional encoding table [L][288] (tf-models RelativePositionEmbedding; networks.py:301-323)
   {
-    std::vector<float> pe((size_t)e->L * kDP, 0.f);
+    std::vector<float> pe((size_t)e->Lw * kDP, 0.f);
     if (c.add_pos_encoding) {
       const int nt = kD / 2;
       const float inc = (float)(log(1e4 / 1.0) / (double)(nt - 1));
@@ -544,7 +552,8 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
   };
   for (int w0 = 0; w0 < batch; w0 += e->chunk_windows) {
     const int bw = std::min(e->chunk_windows, batch - w0);
-    const int M = bw * L;
+    const int Lw = e->Lw;
+    const int M = bw * Lw;          // tokens in the (possibly window-aligned) layout
     const int T = (M + kTileM - 1) / kTileM;
     const float* rows_chunk;
     if (rows_dev) {
@@ -565,18 +574,18 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
       epi.pe = c.add_pos_encoding ? e->d_pe : nullptr;
       epi.ln_g = c.rezero ? nullptr : e->layers[0].ln_g[0];
       epi.ln_b = c.rezero ? nullptr : e->layers[0].ln_b[0];
-      epi.has_xold = 0; epi.L = L;
+      epi.has_xold = 0; epi.L = Lw;
       bool fused_embed = false;
       if (e->fuse_embed) {
         pbegin(1);
-        fused_embed = launch_embed_condense(rows_chunk, R, L, M, T, e->echunks, e->d_cols, e->d_rowmeta, e->d_tables,
+        fused_embed = launch_embed_condense(rows_chunk, R, L, Lw, M, T, e->echunks, e->d_cols, e->d_rowmeta, e->d_tables,
                                             e->table_elems, e->d_wc, epi, e->d_status, st);
         pend();
         if (fused_embed) ++launches;
       }
       if (!fused_embed) {
         pbegin(0);
-        launch_embed(rows_chunk, R, L, M, T, e->echunks, e->d_cols, e->d_rowmeta, e->d_tables, e->table_elems, e->d_embqkv, e->d_status, st);
+        launch_embed(rows_chunk, R, L, Lw, M, T, e->echunks, e->d_cols, e->d_rowmeta, e->d_tables, e->table_elems, e->d_embqkv, e->d_status, st);
         pend();
         pbegin(1);
         launch_gemm_row(e->d_embqkv, e->d_wc, e->Epad / 16, T, epi, st);
@@ -593,7 +602,7 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
       else launch_gemm_qkv(e->d_xb, ld.wqkv, T, e->d_embqkv, st);
       pend();
       pbegin(3);
-      launch_attention(e->d_embqkv, e->d_att, L, c.attn_win_size, bw, st);
+      launch_attention(e->d_embqkv, e->d_att, L, Lw, c.attn_win_size, bw, st);
       pend();
       // attention out-proj + FFN: fused into one CTA-pair kernel unless debugging the intermediate
       const bool fused = e->ffn_pair && e->fuse_oproj && !e->debug;
@@ -601,13 +610,13 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
       ef.x = e->d_x; ef.xb = last ? nullptr : e->d_xb; ef.bias = ld.b2; ef.pe = nullptr;
       ef.ln_g = (c.rezero || last) ? nullptr : e->layers[n_ + 1].ln_g[0];
       ef.ln_b = (c.rezero || last) ? nullptr : e->layers[n_ + 1].ln_b[0];
-      ef.has_xold = 1; ef.L = L;
+      ef.has_xold = 1; ef.L = Lw;
       if (!fused) {
         RowEpi ea{};
         ea.x = e->d_x; ea.xb = e->d_xb; ea.bias = nullptr; ea.pe = nullptr;
         ea.ln_g = c.rezero ? nullptr : ld.ln_g[1];
         ea.ln_b = c.rezero ? nullptr : ld.ln_b[1];
-        ea.has_xold = 1; ea.L = L;
+        ea.has_xold = 1; ea.L = Lw;
         pbegin(1);
         launch_gemm_row(e->d_att, ld.wo, kDP / 16, T, ea, st);
         pend();
@@ -623,7 +632,7 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
       else
         launch_ffn(e->d_xb, ld.wffn, ld.b1, c.filter_size, T, ef, st);
       pend();
-      if (e->profile) e->prof_ffn_tokens += M;
+      if (e->profile) e->prof_ffn_tokens += (long long)bw * L;   // valid tokens (layout padding is not algorithmic work)
       if (!fused) snap();
       e->fused_last = fused;
       launches += 3;
@@ -635,7 +644,7 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
     hp.quals = (out_dev ? quals_out : e->d_quals) + t0;
     hp.probs = probs_out ? ((out_dev ? probs_out : e->d_probs) + t0 * kVocab) : nullptr;
     hp.logits = logits_out ? ((out_dev ? logits_out : e->d_logits) + t0 * kVocab) : nullptr;
-    hp.M = M;
+    hp.M = M; hp.L = L; hp.Lw = Lw;
     hp.calib_enabled = c.calibration_enabled;
     hp.calib_thr = (float)c.calibration_threshold; hp.calib_w = (float)c.calibration_w; hp.calib_b = (float)c.calibration_b;
     hp.calib_thr64 = c.calibration_threshold; hp.calib_w64 = c.calibration_w; hp.calib_b64 = c.calibration_b;
@@ -718,14 +727,16 @@ int dcb_debug_residual(dcb_engine* e, int32_t stage, float* out, int64_t out_ele
   if (!e->debug || !e->d_dbg) return fail(e, DCB_ERR_STATE, "debug capture not enabled");
   const int stages = 1 + 2 * e->cfg.num_hidden_layers;
   if (stage < 0 || stage >= stages) return fail(e, DCB_ERR_INVALID, "stage %d outside [0,%d)", stage, stages);
-  const int M = e->last_chunk_tokens;
+  const int Mlay = e->last_chunk_tokens;               // tokens in the layout
+  const int M = Mlay / e->Lw * e->L;                   // valid tokens
   if (out_elems < (int64_t)M * kD) return fail(e, DCB_ERR_INVALID, "output too small: need %lld", (long long)M * kD);
   CU(e, cudaSetDevice(e->cfg.device));
-  const int T = (M + kTileM - 1) / kTileM;
+  const int T = (Mlay + kTileM - 1) / kTileM;
   std::vector<float> img((size_t)T * x_image_elems());
   CU(e, cudaMemcpy(img.data(), e->d_dbg + (size_t)stage * e->chunk_tiles * x_image_elems(), img.size() * sizeof(float), cudaMemcpyDeviceToHost));
   for (int t = 0; t < M; ++t) {
-    const int tile = t / kTileM, r = t % kTileM;
+    const int tl = t / e->L * e->Lw + t % e->L;        // position of valid token t in the layout
+    const int tile = tl / kTileM, r = tl % kTileM;
     for (int col = 0; col < kD; ++col)
       out[(size_t)t * kD + col] = img[(((size_t)tile * kXChunks + col / 4) * kTileM + r) * 4 + col % 4];
   }

@@ -29,7 +29,7 @@ namespace dcb {
 // (clip -> shift -> truncate -> range check) in shared memory with coalesced loads along L;
 // phase 2 assembles 16-byte K-chunks of the operand image from the shared-memory tables.
 __global__ void __launch_bounds__(256)
-embed_rows_kernel(const float* __restrict__ rows, int R, int L, int M, int echunks,
+embed_rows_kernel(const float* __restrict__ rows, int R, int L, int Lw, int M, int echunks,
                   const EmbedCol* __restrict__ cols, const EmbedRow* __restrict__ rowmeta,
                   const __nv_bfloat16* __restrict__ tables, int table_elems,
                   __nv_bfloat16* __restrict__ emb, int* __restrict__ status) {
@@ -47,9 +47,9 @@ embed_rows_kernel(const float* __restrict__ rows, int R, int L, int M, int echun
     const int tok = tile * kTileM + r;
     int id = 0;
     if (tok < M) {
-      const int b = tok / L, l = tok - b * L;
+      const int b = tok / Lw, l = tok - b * Lw;
       const EmbedRow m = rowmeta[rr];
-      float f = __ldg(rows + ((size_t)b * R + rr) * L + l);
+      float f = l < L ? __ldg(rows + ((size_t)b * R + rr) * L + l) : 0.f;   // window padding rows embed to id 0
       if (m.clip_hi > 0.f) f = fminf(fmaxf(f, 0.f), m.clip_hi);  // format_rows (data_providers.py:151-162)
       f += (float)m.shift;                                         // networks.py:495
       id = (int)f;  // truncation toward zero == tf.cast(float32 -> int32)
@@ -405,7 +405,7 @@ struct EmbCfg {
 };
 
 __global__ void __launch_bounds__(EmbCfg::kThreads, 1)
-embed_condense_kernel(const float* __restrict__ rows, int R, int L, int M, int ntiles, int echunks,
+embed_condense_kernel(const float* __restrict__ rows, int R, int L, int Lw, int M, int ntiles, int echunks,
                       const EmbedCol* __restrict__ cols, const EmbedRow* __restrict__ rowmeta,
                       const __nv_bfloat16* __restrict__ tables, int table_elems,
                       const __nv_bfloat16* __restrict__ wc_img, RowEpi epi, int* __restrict__ status) {
@@ -511,8 +511,9 @@ embed_condense_kernel(const float* __restrict__ rows, int R, int L, int M, int n
         // thread = (token r, input rows rr0, rr0+2, ...): 8 independent global loads in flight per batch
         const int r = bt & (kTileM - 1), rr0 = bt >> 7;
         const int tok = tile * kTileM + r;
-        const bool tvalid = tok < M;
-        const int bw = tvalid ? tok / L : 0, l = tvalid ? tok - bw * L : 0;
+        const int bw0 = tok / Lw, l0 = tok - bw0 * Lw;
+        const bool tvalid = tok < M && l0 < L;      // layout padding (l >= L) embeds to id 0 everywhere
+        const int bw = tvalid ? bw0 : 0, l = tvalid ? l0 : 0;
         const float* base = rows + (size_t)bw * R * L + l;
         for (int rr = rr0; rr < R; rr += 16) {
           float f[8];
@@ -1731,7 +1732,7 @@ __device__ __forceinline__ int att_rot(int chunk, int rowmod) {
 
 __global__ void __launch_bounds__(128, 3)
 band_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ att,
-                      int L, int win, int nwindows) {
+                      int L, int Lw, int win, int nwindows) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int w = blockIdx.x >> 1;
   const int head = blockIdx.x & 1;
@@ -1741,7 +1742,7 @@ band_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
   __nv_bfloat16* sV = sK + (size_t)Lp * kAttStride;
   constexpr int qkv_chunks = kQKVN / 8;  // 108
   const int kcol = (2 + head) * kDHP, vcol = (4 + head) * kDHP, qcol = head * kDHP;
-  const int tok0 = w * L;
+  const int tok0 = w * Lw;   // windows start every Lw tokens in the flattened layout (Lw >= L)
 #ifdef DCB_TRACE
   const long long _t_start = clock64();
 #endif
@@ -1945,6 +1946,9 @@ head_kernel(HeadParams p) {
   const int tile = blockIdx.x, r = threadIdx.x;
   const int tok = tile * kTileM + r;
   if (tok >= p.M) return;
+  const int wdw = tok / p.Lw, pos = tok - wdw * p.Lw;
+  if (pos >= p.L) return;                       // layout padding row
+  const size_t oidx = (size_t)wdw * p.L + pos;  // outputs are dense [B, L]
   const float4* xrow = reinterpret_cast<const float4*>(p.x + (size_t)tile * x_image_elems()) + r;
   // pass 1: mean / variance (biased, eps = 1e-6: encoder_stack.py:131-133); 10 loads in flight per batch
   float s1 = 0.f, s2 = 0.f;
@@ -2015,15 +2019,15 @@ head_kernel(HeadParams p) {
   }
   qi = qi < 0 ? 0 : qi;
   const char vocab[kVocab] = {' ', 'A', 'T', 'C', 'G'};
-  p.bases[tok] = (uint8_t)vocab[arg];
-  p.quals[tok] = (uint8_t)(qi + 33);
+  p.bases[oidx] = (uint8_t)vocab[arg];
+  p.quals[oidx] = (uint8_t)(qi + 33);
   if (p.probs) {
 #pragma unroll
-    for (int j = 0; j < kVocab; ++j) p.probs[(size_t)tok * kVocab + j] = pr[j];
+    for (int j = 0; j < kVocab; ++j) p.probs[oidx * kVocab + j] = pr[j];
   }
   if (p.logits) {
 #pragma unroll
-    for (int j = 0; j < kVocab; ++j) p.logits[(size_t)tok * kVocab + j] = lg[j];
+    for (int j = 0; j < kVocab; ++j) p.logits[oidx * kVocab + j] = lg[j];
   }
 }
 
@@ -2075,11 +2079,11 @@ size_t embed_smem_bytes(int R, int echunks, int table_elems) {
          (size_t)R * kTileM * 2;
 }
 
-void launch_embed(const float* rows, int R, int L, int M, int ntiles, int echunks,
+void launch_embed(const float* rows, int R, int L, int Lw, int M, int ntiles, int echunks,
                   const EmbedCol* cols, const EmbedRow* rowmeta, const __nv_bfloat16* tables,
                   int table_elems, __nv_bfloat16* emb, int* status, cudaStream_t st) {
   embed_rows_kernel<<<ntiles, 256, embed_smem_bytes(R, echunks, table_elems), st>>>(
-      rows, R, L, M, echunks, cols, rowmeta, tables, table_elems, emb, status);
+      rows, R, L, Lw, M, echunks, cols, rowmeta, tables, table_elems, emb, status);
 }
 
 void launch_gemm_row(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int ksteps, int ntiles,
@@ -2098,13 +2102,13 @@ void launch_gemm_qkv(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int
                                                                      qkv_img, kQKVN / 8, none);
 }
 
-bool launch_embed_condense(const float* rows, int R, int L, int M, int ntiles, int echunks, const EmbedCol* cols,
+bool launch_embed_condense(const float* rows, int R, int L, int Lw, int M, int ntiles, int echunks, const EmbedCol* cols,
                            const EmbedRow* rowmeta, const __nv_bfloat16* tables, int table_elems,
                            const __nv_bfloat16* wc_img, const RowEpi& epi, int* status, cudaStream_t st) {
   const size_t smem = embed_condense_smem_bytes(R, echunks, table_elems);
   if (smem > 227 * 1024) return false;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  embed_condense_kernel<<<grid, EmbCfg::kThreads, smem, st>>>(rows, R, L, M, ntiles, echunks, cols, rowmeta, tables,
+  embed_condense_kernel<<<grid, EmbCfg::kThreads, smem, st>>>(rows, R, L, Lw, M, ntiles, echunks, cols, rowmeta, tables,
                                                               table_elems, wc_img, epi, status);
   return true;
 }
@@ -2116,11 +2120,11 @@ void launch_qkv2(const __nv_bfloat16* a_img, const uint8_t* b_img, int ntiles, _
   qkv2_kernel<<<grid, Qkv2Cfg::kThreads, Qkv2Cfg::kSmemBytes, st>>>(a_img, b_img, ntiles, qkv_img);
 }
 
-void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int win, int nwindows,
+void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int Lw, int win, int nwindows,
                       cudaStream_t st) {
   const int Lp = (L + 15) & ~15;
   const size_t smem = (size_t)2 * Lp * kAttStride * 2;
-  band_attention_kernel<<<nwindows * 2, 128, smem, st>>>(qkv, att, L, win, nwindows);
+  band_attention_kernel<<<nwindows * 2, 128, smem, st>>>(qkv, att, L, Lw, win, nwindows);
 }
 
 static int g_ffn_cluster = 0;

@@ -9,7 +9,7 @@ namespace dcb {
 cudaError_t kernels_init();
 
 size_t embed_smem_bytes(int R, int echunks, int table_elems);
-void launch_embed(const float* rows, int R, int L, int M, int ntiles, int echunks,
+void launch_embed(const float* rows, int R, int L, int Lw, int M, int ntiles, int echunks,
                   const EmbedCol* cols, const EmbedRow* rowmeta, const __nv_bfloat16* tables,
                   int table_elems, __nv_bfloat16* emb, int* status, cudaStream_t st);
 // D = A * B^T with the 288-wide row epilogue (condenser + pos-enc, attention out-proj).
@@ -20,13 +20,13 @@ void launch_gemm_qkv(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int
                      __nv_bfloat16* qkv_img, cudaStream_t st);
 // fused embedding + condenser (+pos-enc, residual image, next operand); false if it does not fit smem
 size_t embed_condense_smem_bytes(int R, int echunks, int table_elems);
-bool launch_embed_condense(const float* rows, int R, int L, int M, int ntiles, int echunks, const EmbedCol* cols,
+bool launch_embed_condense(const float* rows, int R, int L, int Lw, int M, int ntiles, int echunks, const EmbedCol* cols,
                            const EmbedRow* rowmeta, const __nv_bfloat16* tables, int table_elems,
                            const __nv_bfloat16* wc_img, const RowEpi& epi, int* status, cudaStream_t st);
 // two-tiles-per-weight-pass QKV projection; b_img: 9 groups x [36][96][8]
 void launch_qkv2(const __nv_bfloat16* a_img, const uint8_t* b_img, int ntiles, __nv_bfloat16* qkv_img,
                  cudaStream_t st);
-void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int win, int nwindows,
+void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int Lw, int win, int nwindows,
                       cudaStream_t st);
 // CTA-pair (cta_group::2) version; w2img is the per-rank half-chunk weight image.
 // With wo2img != null the attention out-projection (+ residual, + pre-norm `mid_ln_*` or identity) is
