@@ -25,6 +25,7 @@ thread_local std::string g_create_error;
 struct LayerDev {
   __nv_bfloat16* wqkv = nullptr;  // 2 groups x [36][432][8]
   uint8_t* wqkv2 = nullptr;       // 9 groups x [36][96][8] (qkv2_kernel)
+  uint8_t* wqa = nullptr;         // fused QKV+attention: per (head, rank) [36][216][8], rows = q|k|v halves
   __nv_bfloat16* wo = nullptr;    // [36][288][8]
   uint8_t* wffn = nullptr;        // per ff chunk: [36][128][8] then [16][288][8]
   uint8_t* wffn2 = nullptr;       // CTA-pair image: per (chunk, rank): [36][64][8] then [16][144][8]
@@ -50,6 +51,7 @@ struct dcb_engine {
   bool ffn_pair = true;
   bool fuse_oproj = true;
   bool fuse_embed = true;
+  bool fuse_qa = true;
   bool qkv2 = false;   // measured: not faster than gemm_kernel<3,QKV> (both sit on the per-SM L2 port), kept as an option
   bool fused_last = false;
   bool profile = false;
@@ -214,6 +216,7 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   if (const char* env = getenv("DCB_FUSE_OPROJ")) e->fuse_oproj = atoi(env) != 0;
   if (const char* env = getenv("DCB_QKV2")) e->qkv2 = atoi(env) != 0;
   if (const char* env = getenv("DCB_FUSE_EMBED")) e->fuse_embed = atoi(env) != 0;
+  if (const char* env = getenv("DCB_FUSE_QA")) e->fuse_qa = atoi(env) != 0;
   int ct = cfg->chunk_tiles;
   if (const char* env = getenv("DCB_CHUNK_TILES")) ct = atoi(env);
   if (ct <= 0) ct = 8 * e->num_sms;   // measured: larger chunks win (kernels are not DRAM-bound)
@@ -416,6 +419,23 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
       __nv_bfloat16* dptr = nullptr;
       if ((rc = upload(e, &dptr, img9))) return rc;
       ld.wqkv2 = reinterpret_cast<uint8_t*>(dptr);
+      // fused QKV + attention (CTA pairs): for head h and rank rk the 216 rows of a k-step are
+      // [q_h | k_h | v_h], each the rk-th half (72 columns) of that 144-wide matrix
+      std::vector<__nv_bfloat16> imga;
+      for (int h = 0; h < kHeads; ++h)
+        for (int rk = 0; rk < 2; ++rk) {
+          auto part = pack_b(kDP, 3 * (kDHP / 2), [&](int k, int nn) {
+            const int m = nn / (kDHP / 2), dd = rk * (kDHP / 2) + nn % (kDHP / 2);
+            if (k >= kD || dd >= kDH) return 0.f;
+            const float* w = m == 0 ? wq : (m == 1 ? wk : wv);
+            const float v = w[((size_t)k * kHeads + h) * kDH + dd];
+            return m == 0 ? v * qscale : v;
+          });
+          imga.insert(imga.end(), part.begin(), part.end());
+        }
+      __nv_bfloat16* dptr2 = nullptr;
+      if ((rc = upload(e, &dptr2, imga))) return rc;
+      ld.wqa = reinterpret_cast<uint8_t*>(dptr2);
     }
     {
       // out-proj: K index = head*144 + dd, N = e; ReZero alpha folded in (encoder_stack.py:88-90)
@@ -597,13 +617,20 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
     for (int n_ = 0; n_ < c.num_hidden_layers; ++n_) {
       const LayerDev& ld = e->layers[n_];
       const bool last = n_ + 1 == c.num_hidden_layers;
-      pbegin(2);
-      if (e->qkv2) launch_qkv2(e->d_xb, ld.wqkv2, T, e->d_embqkv, st);
-      else launch_gemm_qkv(e->d_xb, ld.wqkv, T, e->d_embqkv, st);
-      pend();
-      pbegin(3);
-      launch_attention(e->d_embqkv, e->d_att, L, Lw, c.attn_win_size, bw, st);
-      pend();
+      if (e->fuse_qa && Lw == kTileM) {
+        pbegin(2);
+        launch_qkv_attn(e->d_xb, ld.wqa, T, L, c.attn_win_size, e->d_att, st);
+        pend();
+        --launches;   // one launch instead of two (3 per layer are added below)
+      } else {
+        pbegin(2);
+        if (e->qkv2) launch_qkv2(e->d_xb, ld.wqkv2, T, e->d_embqkv, st);
+        else launch_gemm_qkv(e->d_xb, ld.wqkv, T, e->d_embqkv, st);
+        pend();
+        pbegin(3);
+        launch_attention(e->d_embqkv, e->d_att, L, Lw, c.attn_win_size, bw, st);
+        pend();
+      }
       // attention out-proj + FFN: fused into one CTA-pair kernel unless debugging the intermediate
       const bool fused = e->ffn_pair && e->fuse_oproj && !e->debug;
       RowEpi ef{};

@@ -1934,6 +1934,305 @@ band_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
 }
 
 // =====================================================================================
+// fused q/k/v projection + banded attention (window-aligned tiles, CTA pairs)
+// =====================================================================================
+// One 128-row tile = one window (engine layout Lw == 128).  A CTA pair handles two windows with
+// M=256 UMMAs (each CTA holds half of every weight k-step).  Per head: Q|K|V = X * [Wq|Wk|Wv]_h
+// (54 UMMAs, N=144) land in TMEM, 8 worker warps move them as bf16 into shared memory (rows of
+// 288 B, 16-byte chunks rotated by the row index -- the layout band_attention_kernel stages into),
+// then each worker warp runs the banded softmax attention of one 16-query block straight from
+// shared memory (mma.sync) while the tensor core already computes the next head's projections.
+// q, k and v never touch HBM (-516 KB per window and layer through the SM's L2 port).
+struct QaCfg {
+  static constexpr int kABytes = (kDP / 8) * kTileM * 16;            // 73728
+  static constexpr int kMatBytes = kTileM * kDHP * 2;                // 36864: q, k or v of one head
+  static constexpr int kRows = 3 * (kDHP / 2);                       // 216 weight rows per CTA per k-step
+  static constexpr int kStageBytes = 2 * kRows * 16;                 // 6912: one k-step
+  static constexpr int kSlots = 6;
+  static constexpr int kHeadBytes = (kDP / 16) * kStageBytes;        // 124416 per (head, rank)
+  static constexpr int kOffA = 0;
+  static constexpr int kOffQ = kABytes;
+  static constexpr int kOffRing = kOffQ + 3 * kMatBytes;
+  static constexpr int kOffBars = kOffRing + kSlots * kStageBytes;
+  static constexpr int kSmemBytes = kOffBars + 256;
+  static constexpr int kThreads = 320;
+  static constexpr int kTmemCols = 512;
+};
+static_assert(QaCfg::kSmemBytes <= 232448, "qkv+attention shared memory budget");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QaCfg::kThreads, 1)
+qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ w_img, int ntiles,
+                     int L, int win, __nv_bfloat16* __restrict__ att) {
+  using C = QaCfg;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem + C::kOffA;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem + C::kOffQ);
+  __nv_bfloat16* sK = sQ + kTileM * kDHP;
+  __nv_bfloat16* sV = sK + kTileM * kDHP;
+  uint8_t* sRing = smem + C::kOffRing;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
+  uint64_t* full = bars;                    // [kSlots]
+  uint64_t* empty = bars + C::kSlots;       // [kSlots]
+  uint64_t* a_full = bars + 2 * C::kSlots;
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* acc_full = a_full + 2;
+  uint64_t* acc_free = a_full + 3;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int npairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
+  const int tile_pairs = (ntiles + 1) >> 1;
+  const int rounds = (tile_pairs + npairs - 1) / npairs;
+  auto tile_of = [&](int ti) { return ((ti * npairs + pair) << 1) + (int)rank; };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::kSlots; ++i) { mbar_init(&full[i], leader ? 2 : 1); mbar_init(&empty[i], 1); }
+    mbar_init(a_full, leader ? 2 : 1);
+    mbar_init(a_empty, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_free, 16);     // 8 worker warps x 2 CTAs (leader only)
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_holder, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int ti = 0; ti < rounds; ++ti) {
+        const int tile = min(tile_of(ti), ntiles - 1);
+        mbar_wait(a_empty, (ti & 1) ^ 1);
+        mbar_arrive_expect_tx(a_full, C::kABytes);
+        bulk_g2s(sA, reinterpret_cast<const uint8_t*>(a_img) + (size_t)tile * C::kABytes, C::kABytes, a_full);
+        for (int h = 0; h < kHeads; ++h) {
+          const uint8_t* src = w_img + ((size_t)h * 2 + rank) * C::kHeadBytes;
+          for (int ks = 0; ks < kDP / 16; ++ks) {
+            mbar_wait(&empty[slot], phase ^ 1);
+            mbar_arrive_expect_tx(&full[slot], C::kStageBytes);
+            bulk_g2s(sRing + slot * C::kStageBytes, src + (size_t)ks * C::kStageBytes, C::kStageBytes, &full[slot]);
+            if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      if (leader) {
+        constexpr uint32_t idesc = make_idesc_bf16(2 * kTileM, kNC);
+        constexpr uint16_t kBoth = 3;
+        const uint32_t a_addr = smem_u32(sA);
+        uint32_t hi = 0;
+        for (int ti = 0; ti < rounds; ++ti) {
+          mbar_wait_cluster(a_full, ti & 1);
+          tc_fence_after();
+          for (int h = 0; h < kHeads; ++h, ++hi) {
+            mbar_wait_cluster(acc_free, (hi & 1) ^ 1);
+            tc_fence_after();
+            for (int ks = 0; ks < kDP / 16; ++ks) {
+              mbar_wait_cluster(&full[slot], phase);
+              tc_fence_after();
+              const uint32_t sb = smem_u32(sRing + slot * C::kStageBytes);
+              const uint64_t adesc = make_kc16_desc(a_addr + ks * 4096, kTileM * 16, 128);
+#pragma unroll
+              for (int m = 0; m < 3; ++m) {
+                const uint64_t bdesc = make_kc16_desc(sb + m * (kDHP / 2) * 16, C::kRows * 16, 128);
+                umma_bf16_ss_pair(tmem_base + m * kDHP, adesc, bdesc, idesc, ks != 0);
+              }
+              umma_commit_pair(&empty[slot], kBoth);
+              if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+            }
+            umma_commit_pair(acc_full, kBoth);
+          }
+          umma_commit_pair(a_empty, kBoth);
+        }
+      } else {
+        for (int ti = 0; ti < rounds; ++ti) {
+          mbar_wait(a_full, ti & 1);
+          mbar_arrive_cluster(a_full, 0);
+          for (int s = 0; s < kHeads * (kDP / 16); ++s) {
+            mbar_wait(&full[slot], phase);
+            mbar_arrive_cluster(&full[slot], 0);
+            if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------- workers (8 warps)
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                 // token row this thread moves out of TMEM
+    const int rm = r % kAttChunks;
+    const int halfsel = ew >> 2;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int g = lane >> 2, t = lane & 3;
+    const int band = win > 0 ? win : L;
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr int kChunkElems = kTileM * 8;
+    uint32_t hi = 0;
+    for (int ti = 0; ti < rounds; ++ti) {
+      const int tile_raw = tile_of(ti);
+      const bool valid = tile_raw < ntiles;
+      for (int h = 0; h < kHeads; ++h, ++hi) {
+        mbar_wait(acc_full, hi & 1);
+        tc_fence_after();
+        // ---- TMEM -> bf16 -> shared memory (27 column blocks of 16: q 0-8, k 9-17, v 18-26)
+        const int cb0 = halfsel ? 14 : 0, cb1 = halfsel ? 27 : 14;
+#pragma unroll 2
+        for (int cb = cb0; cb < cb1; ++cb) {
+          uint32_t acc[16];
+          tmem_ld16(tmem_row + cb * 16, acc);
+          tmem_ld_wait();
+          const int m = cb / 9, j = cb - m * 9;
+          __nv_bfloat16* dst = sQ + (size_t)m * kTileM * kDHP + (size_t)r * kDHP;
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
+          *reinterpret_cast<uint4*>(dst + att_rot(2 * j, rm) * 8) =
+              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          *reinterpret_cast<uint4*>(dst + att_rot(2 * j + 1, rm) * 8) =
+              make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (leader) mbar_arrive(acc_free); else mbar_arrive_cluster(acc_free, 0); }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+
+        // ---- banded attention of query block `ew` (rows 16*ew .. +15) from shared memory
+        {
+          const int i0 = ew * 16;
+          const int r0 = i0 + g, r1 = r0 + 8;
+          const int qm0 = r0 % kAttChunks, qm1 = r1 % kAttChunks;
+          const __nv_bfloat16* q0 = sQ + (size_t)r0 * kDHP + 2 * t;
+          const __nv_bfloat16* q1 = sQ + (size_t)r1 * kDHP + 2 * t;
+          uint32_t qa[kDHP / 16][4];
+#pragma unroll
+          for (int ks = 0; ks < kDHP / 16; ++ks) {
+            qa[ks][0] = *reinterpret_cast<const uint32_t*>(q0 + att_rot(2 * ks, qm0) * 8);
+            qa[ks][1] = *reinterpret_cast<const uint32_t*>(q1 + att_rot(2 * ks, qm1) * 8);
+            qa[ks][2] = *reinterpret_cast<const uint32_t*>(q0 + att_rot(2 * ks + 1, qm0) * 8);
+            qa[ks][3] = *reinterpret_cast<const uint32_t*>(q1 + att_rot(2 * ks + 1, qm1) * 8);
+          }
+          float o[kDHP / 8][4];
+#pragma unroll
+          for (int nt = 0; nt < kDHP / 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+          float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+          int jlo = i0 - band; if (jlo < 0) jlo = 0; jlo &= ~15;
+          int jhi = i0 + 15 + band + 1; if (jhi > L) jhi = L;
+          for (int j0 = jlo; j0 < jhi; j0 += 16) {
+            float sc[2][4], sc2[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+              sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+              sc2[nt][0] = sc2[nt][1] = sc2[nt][2] = sc2[nt][3] = 0.f;
+            }
+            const int krow0 = j0 + g, krow1 = j0 + 8 + g;
+            const __nv_bfloat16* kr0 = sK + (size_t)krow0 * kDHP + 2 * t;
+            const __nv_bfloat16* kr1 = sK + (size_t)krow1 * kDHP + 2 * t;
+            const int km0 = krow0 % kAttChunks, km1 = krow1 % kAttChunks;
+#pragma unroll
+            for (int ks = 0; ks < kDHP / 16; ++ks) {
+              const uint32_t a0 = *reinterpret_cast<const uint32_t*>(kr0 + att_rot(2 * ks, km0) * 8);
+              const uint32_t a1 = *reinterpret_cast<const uint32_t*>(kr0 + att_rot(2 * ks + 1, km0) * 8);
+              const uint32_t c0 = *reinterpret_cast<const uint32_t*>(kr1 + att_rot(2 * ks, km1) * 8);
+              const uint32_t c1 = *reinterpret_cast<const uint32_t*>(kr1 + att_rot(2 * ks + 1, km1) * 8);
+              if (ks & 1) {
+                mma_bf16_16816(sc2[0], qa[ks], a0, a1);
+                mma_bf16_16816(sc2[1], qa[ks], c0, c1);
+              } else {
+                mma_bf16_16816(sc[0], qa[ks], a0, a1);
+                mma_bf16_16816(sc[1], qa[ks], c0, c1);
+              }
+            }
+            float tmax0 = -INFINITY, tmax1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = (e < 2) ? r0 : r1;
+                const int j = j0 + nt * 8 + 2 * t + (e & 1);
+                const int dlt = i - j;
+                const bool ok = (j < L) && (dlt <= band) && (dlt >= -band);
+                sc[nt][e] = ok ? sc[nt][e] + sc2[nt][e] : -INFINITY;
+              }
+              tmax0 = fmaxf(tmax0, fmaxf(sc[nt][0], sc[nt][1]));
+              tmax1 = fmaxf(tmax1, fmaxf(sc[nt][2], sc[nt][3]));
+            }
+            tmax0 = fmaxf(tmax0, __shfl_xor_sync(0xffffffffu, tmax0, 1));
+            tmax0 = fmaxf(tmax0, __shfl_xor_sync(0xffffffffu, tmax0, 2));
+            tmax1 = fmaxf(tmax1, __shfl_xor_sync(0xffffffffu, tmax1, 1));
+            tmax1 = fmaxf(tmax1, __shfl_xor_sync(0xffffffffu, tmax1, 2));
+            const float mn0 = fmaxf(m0, tmax0), mn1 = fmaxf(m1, tmax1);
+            const float base0 = mn0 == -INFINITY ? 0.f : mn0, base1 = mn1 == -INFINITY ? 0.f : mn1;
+            const float f0 = exp2f((m0 - base0) * kLog2e), f1 = exp2f((m1 - base1) * kLog2e);
+            m0 = mn0; m1 = mn1;
+            float ps0 = 0.f, ps1 = 0.f;
+            uint32_t pa[4];
+            {
+              float p[2][4];
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) {
+                p[nt][0] = exp2f((sc[nt][0] - base0) * kLog2e);
+                p[nt][1] = exp2f((sc[nt][1] - base0) * kLog2e);
+                p[nt][2] = exp2f((sc[nt][2] - base1) * kLog2e);
+                p[nt][3] = exp2f((sc[nt][3] - base1) * kLog2e);
+                ps0 += p[nt][0] + p[nt][1];
+                ps1 += p[nt][2] + p[nt][3];
+              }
+              pa[0] = pack_bf16x2(p[0][0], p[0][1]);
+              pa[1] = pack_bf16x2(p[0][2], p[0][3]);
+              pa[2] = pack_bf16x2(p[1][0], p[1][1]);
+              pa[3] = pack_bf16x2(p[1][2], p[1][3]);
+            }
+            l0 = l0 * f0 + ps0;
+            l1 = l1 * f1 + ps1;
+            const int vrow = j0 + (lane & 15);
+            const int vm = vrow % kAttChunks;
+            const uint32_t vbase = smem_u32(sV + (size_t)vrow * kDHP);
+#pragma unroll
+            for (int nt = 0; nt < kDHP / 8; ++nt) {
+              o[nt][0] *= f0; o[nt][1] *= f0; o[nt][2] *= f1; o[nt][3] *= f1;
+              uint32_t b0, b1;
+              ldmatrix_x2_trans(b0, b1, vbase + att_rot(nt, vm) * 16);
+              mma_bf16_16816(o[nt], pa, b0, b1);
+            }
+          }
+          l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+          l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+          l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+          l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+          const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+          if (valid) {
+            __nv_bfloat16* obase = att + ((size_t)tile_raw * (kDP / 8) + h * kAttChunks) * kChunkElems + 2 * t;
+#pragma unroll
+            for (int nt = 0; nt < kDHP / 8; ++nt) {
+              if (r0 < L)
+                *reinterpret_cast<uint32_t*>(obase + (size_t)nt * kChunkElems + r0 * 8) = pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
+              if (r1 < L)
+                *reinterpret_cast<uint32_t*>(obase + (size_t)nt * kChunkElems + r1 * 8) = pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // q/k/v of this head fully consumed
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, C::kTmemCols);
+  }
+}
+
+// =====================================================================================
 // head: final LayerNorm -> fc1 -> softmax -> argmax / Phred / ASCII
 // =====================================================================================
 __global__ void __launch_bounds__(128)
@@ -2063,6 +2362,8 @@ cudaError_t kernels_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(ffn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg::kSmemBytes);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(qkv_attn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QaCfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(embed_condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(qkv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Qkv2Cfg::kSmemBytes);
@@ -2118,6 +2419,25 @@ void launch_qkv2(const __nv_bfloat16* a_img, const uint8_t* b_img, int ntiles, _
   const int npairs = (ntiles + 1) / 2;
   const int grid = npairs < num_sms() ? npairs : num_sms();
   qkv2_kernel<<<grid, Qkv2Cfg::kThreads, Qkv2Cfg::kSmemBytes, st>>>(a_img, b_img, ntiles, qkv_img);
+}
+
+void launch_qkv_attn(const __nv_bfloat16* a_img, const uint8_t* w_img, int ntiles, int L, int win,
+                     __nv_bfloat16* att, cudaStream_t st) {
+  static int max_pairs = 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(QaCfg::kThreads);
+  cfg.dynamicSmemBytes = QaCfg::kSmemBytes;
+  cfg.stream = st;
+  if (!max_pairs) {
+    cfg.gridDim = dim3(num_sms() / 2 * 2);
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, qkv_attn_pair_kernel, &cfg) != cudaSuccess || nc <= 0) nc = num_sms() / 2;
+    max_pairs = nc;
+  }
+  int pairs = (ntiles + 1) / 2;
+  if (pairs > max_pairs) pairs = max_pairs;
+  cfg.gridDim = dim3(pairs * 2);
+  cudaLaunchKernelEx(&cfg, qkv_attn_pair_kernel, a_img, w_img, ntiles, L, win, att);
 }
 
 void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int Lw, int win, int nwindows,

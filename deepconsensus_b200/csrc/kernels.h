@@ -26,6 +26,10 @@ bool launch_embed_condense(const float* rows, int R, int L, int Lw, int M, int n
 // two-tiles-per-weight-pass QKV projection; b_img: 9 groups x [36][96][8]
 void launch_qkv2(const __nv_bfloat16* a_img, const uint8_t* b_img, int ntiles, __nv_bfloat16* qkv_img,
                  cudaStream_t st);
+// fused QKV projection + banded attention on window-aligned tiles (Lw == 128); w_img: per (head, rank)
+// [18 k-steps][2][216][8] with rows = [q|k|v] halves
+void launch_qkv_attn(const __nv_bfloat16* a_img, const uint8_t* w_img, int ntiles, int L, int win,
+                     __nv_bfloat16* att, cudaStream_t st);
 void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int Lw, int win, int nwindows,
                       cudaStream_t st);
 // CTA-pair (cta_group::2) version; w2img is the per-rank half-chunk weight image.
