@@ -1945,7 +1945,8 @@ band_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
 // q, k and v never touch HBM (-516 KB per window and layer through the SM's L2 port).
 struct QaCfg {
   static constexpr int kABytes = (kDP / 8) * kTileM * 16;            // 73728
-  static constexpr int kMatBytes = kTileM * kDHP * 2;                // 36864: q, k or v of one head
+  static constexpr int kStride = 152;                                // padded row (304 B): conflict-free, no index rotation
+  static constexpr int kMatBytes = kTileM * kStride * 2;             // 38912: q, k or v of one head
   static constexpr int kRows = 3 * (kDHP / 2);                       // 216 weight rows per CTA per k-step
   static constexpr int kStageBytes = 2 * kRows * 16;                 // 6912: one k-step
   static constexpr int kSlots = 6;
@@ -1955,11 +1956,14 @@ struct QaCfg {
   static constexpr int kOffRing = kOffQ + 3 * kMatBytes;
   static constexpr int kOffBars = kOffRing + kSlots * kStageBytes;
   static constexpr int kSmemBytes = kOffBars + 256;
-  static constexpr int kThreads = 320;
+  static constexpr int kThreads = 384;   // WG0 = {producer, UMMA issuer / relay, 2 idle}, WG1-2 = 8 worker warps
   static constexpr int kTmemCols = 512;
 };
 static_assert(QaCfg::kSmemBytes <= 232448, "qkv+attention shared memory budget");
 
+// kTwoPass: attn_win_size <= 16, i.e. every 16-query block sees at most 3 key tiles (two-pass softmax);
+// otherwise the general online-softmax loop (any band, incl. full attention).
+template <bool kTwoPass>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QaCfg::kThreads, 1)
 qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ w_img, int ntiles,
                      int L, int win, __nv_bfloat16* __restrict__ att) {
@@ -1967,8 +1971,9 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem + C::kOffA;
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem + C::kOffQ);
-  __nv_bfloat16* sK = sQ + kTileM * kDHP;
-  __nv_bfloat16* sV = sK + kTileM * kDHP;
+  constexpr int kS = C::kStride;
+  __nv_bfloat16* sK = sQ + kTileM * kS;
+  __nv_bfloat16* sV = sK + kTileM * kS;
   uint8_t* sRing = smem + C::kOffRing;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
   uint64_t* full = bars;                    // [kSlots]
@@ -2001,7 +2006,9 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 0) {
+  if (warp < 4) {
+   setmaxnreg_dec<40>();
+   if (warp == 0) {
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
       for (int ti = 0; ti < rounds; ++ti) {
@@ -2063,12 +2070,13 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
         }
       }
     }
+   }
   } else {
+    setmaxnreg_inc<232>();
     // ------------------------------------------------------------- workers (8 warps)
-    const int ew = warp - 2;
+    const int ew = warp - 4;
     const int q = warp & 3;
     const int r = q * 32 + lane;                 // token row this thread moves out of TMEM
-    const int rm = r % kAttChunks;
     const int halfsel = ew >> 2;
     const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
     const int g = lane >> 2, t = lane & 3;
@@ -2090,13 +2098,13 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
           tmem_ld16(tmem_row + cb * 16, acc);
           tmem_ld_wait();
           const int m = cb / 9, j = cb - m * 9;
-          __nv_bfloat16* dst = sQ + (size_t)m * kTileM * kDHP + (size_t)r * kDHP;
+          __nv_bfloat16* dst = sQ + (size_t)m * kTileM * kS + (size_t)r * kS;
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
-          *reinterpret_cast<uint4*>(dst + att_rot(2 * j, rm) * 8) =
+          *reinterpret_cast<uint4*>(dst + (2 * j) * 8) =
               make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          *reinterpret_cast<uint4*>(dst + att_rot(2 * j + 1, rm) * 8) =
+          *reinterpret_cast<uint4*>(dst + (2 * j + 1) * 8) =
               make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
         }
         tc_fence_before();
@@ -2108,23 +2116,104 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
         {
           const int i0 = ew * 16;
           const int r0 = i0 + g, r1 = r0 + 8;
-          const int qm0 = r0 % kAttChunks, qm1 = r1 % kAttChunks;
-          const __nv_bfloat16* q0 = sQ + (size_t)r0 * kDHP + 2 * t;
-          const __nv_bfloat16* q1 = sQ + (size_t)r1 * kDHP + 2 * t;
+          const __nv_bfloat16* q0 = sQ + (size_t)r0 * kS + 2 * t;
+          const __nv_bfloat16* q1 = sQ + (size_t)r1 * kS + 2 * t;
           uint32_t qa[kDHP / 16][4];
 #pragma unroll
           for (int ks = 0; ks < kDHP / 16; ++ks) {
-            qa[ks][0] = *reinterpret_cast<const uint32_t*>(q0 + att_rot(2 * ks, qm0) * 8);
-            qa[ks][1] = *reinterpret_cast<const uint32_t*>(q1 + att_rot(2 * ks, qm1) * 8);
-            qa[ks][2] = *reinterpret_cast<const uint32_t*>(q0 + att_rot(2 * ks + 1, qm0) * 8);
-            qa[ks][3] = *reinterpret_cast<const uint32_t*>(q1 + att_rot(2 * ks + 1, qm1) * 8);
+            qa[ks][0] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16);
+            qa[ks][1] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16);
+            qa[ks][2] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + 8);
+            qa[ks][3] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + 8);
           }
           float o[kDHP / 8][4];
 #pragma unroll
           for (int nt = 0; nt < kDHP / 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
-          float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+          float l0 = 0.f, l1 = 0.f;
           int jlo = i0 - band; if (jlo < 0) jlo = 0; jlo &= ~15;
           int jhi = i0 + 15 + band + 1; if (jhi > L) jhi = L;
+          const int nkt = (jhi - jlo + 15) >> 4;
+          constexpr int kMaxKT = 3;
+          if constexpr (kTwoPass) {
+            // ---- band fits in <= 3 key tiles (attn_win_size <= 16): two-pass softmax.  All score tiles
+            // are computed first (independent HMMA chains), one row maximum, one exponentiation, then
+            // P*V accumulates without any rescaling.
+            float sc[kMaxKT][2][4];
+#pragma unroll
+            for (int kt = 0; kt < kMaxKT; ++kt)
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) sc[kt][nt][0] = sc[kt][nt][1] = sc[kt][nt][2] = sc[kt][nt][3] = 0.f;
+#pragma unroll
+            for (int kt = 0; kt < kMaxKT; ++kt) {
+              if (kt < nkt) {
+                const int krow0 = jlo + kt * 16 + g, krow1 = krow0 + 8;
+                const __nv_bfloat16* kr0 = sK + (size_t)krow0 * kS + 2 * t;
+                const __nv_bfloat16* kr1 = sK + (size_t)krow1 * kS + 2 * t;
+#pragma unroll
+                for (int ks = 0; ks < kDHP / 16; ++ks) {
+                  const uint32_t a0 = *reinterpret_cast<const uint32_t*>(kr0 + ks * 16);
+                  const uint32_t a1 = *reinterpret_cast<const uint32_t*>(kr0 + ks * 16 + 8);
+                  const uint32_t c0 = *reinterpret_cast<const uint32_t*>(kr1 + ks * 16);
+                  const uint32_t c1 = *reinterpret_cast<const uint32_t*>(kr1 + ks * 16 + 8);
+                  mma_bf16_16816(sc[kt][0], qa[ks], a0, a1);
+                  mma_bf16_16816(sc[kt][1], qa[ks], c0, c1);
+                }
+              }
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int kt = 0; kt < kMaxKT; ++kt)
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int i = (e < 2) ? r0 : r1;
+                  const int j = jlo + kt * 16 + nt * 8 + 2 * t + (e & 1);
+                  const int dlt = i - j;
+                  const bool ok = (kt < nkt) && (j < L) && (dlt <= band) && (dlt >= -band);
+                  const float v = ok ? sc[kt][nt][e] : -INFINITY;
+                  sc[kt][nt][e] = v;
+                  if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+                }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float base0 = mx0 == -INFINITY ? 0.f : mx0 * kLog2e, base1 = mx1 == -INFINITY ? 0.f : mx1 * kLog2e;
+            uint32_t pa[kMaxKT][4];
+#pragma unroll
+            for (int kt = 0; kt < kMaxKT; ++kt) {
+              float p[2][4];
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) {
+                p[nt][0] = exp2f(fmaf(sc[kt][nt][0], kLog2e, -base0));
+                p[nt][1] = exp2f(fmaf(sc[kt][nt][1], kLog2e, -base0));
+                p[nt][2] = exp2f(fmaf(sc[kt][nt][2], kLog2e, -base1));
+                p[nt][3] = exp2f(fmaf(sc[kt][nt][3], kLog2e, -base1));
+                l0 += p[nt][0] + p[nt][1];
+                l1 += p[nt][2] + p[nt][3];
+              }
+              pa[kt][0] = pack_bf16x2(p[0][0], p[0][1]);
+              pa[kt][1] = pack_bf16x2(p[0][2], p[0][3]);
+              pa[kt][2] = pack_bf16x2(p[1][0], p[1][1]);
+              pa[kt][3] = pack_bf16x2(p[1][2], p[1][3]);
+            }
+#pragma unroll
+            for (int kt = 0; kt < kMaxKT; ++kt) {
+              if (kt < nkt) {
+                const int vrow = jlo + kt * 16 + (lane & 15);
+                const uint32_t vbase = smem_u32(sV + (size_t)vrow * kS);
+#pragma unroll
+                for (int nt = 0; nt < kDHP / 8; ++nt) {
+                  uint32_t b0, b1;
+                  ldmatrix_x2_trans(b0, b1, vbase + nt * 16);
+                  mma_bf16_16816(o[nt], pa[kt], b0, b1);
+                }
+              }
+            }
+          } else {
+          // ---- general band (incl. full attention): online softmax over 16-key tiles
+          float m0 = -INFINITY, m1 = -INFINITY;
           for (int j0 = jlo; j0 < jhi; j0 += 16) {
             float sc[2][4], sc2[2][4];
 #pragma unroll
@@ -2133,15 +2222,14 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
               sc2[nt][0] = sc2[nt][1] = sc2[nt][2] = sc2[nt][3] = 0.f;
             }
             const int krow0 = j0 + g, krow1 = j0 + 8 + g;
-            const __nv_bfloat16* kr0 = sK + (size_t)krow0 * kDHP + 2 * t;
-            const __nv_bfloat16* kr1 = sK + (size_t)krow1 * kDHP + 2 * t;
-            const int km0 = krow0 % kAttChunks, km1 = krow1 % kAttChunks;
+            const __nv_bfloat16* kr0 = sK + (size_t)krow0 * kS + 2 * t;
+            const __nv_bfloat16* kr1 = sK + (size_t)krow1 * kS + 2 * t;
 #pragma unroll
             for (int ks = 0; ks < kDHP / 16; ++ks) {
-              const uint32_t a0 = *reinterpret_cast<const uint32_t*>(kr0 + att_rot(2 * ks, km0) * 8);
-              const uint32_t a1 = *reinterpret_cast<const uint32_t*>(kr0 + att_rot(2 * ks + 1, km0) * 8);
-              const uint32_t c0 = *reinterpret_cast<const uint32_t*>(kr1 + att_rot(2 * ks, km1) * 8);
-              const uint32_t c1 = *reinterpret_cast<const uint32_t*>(kr1 + att_rot(2 * ks + 1, km1) * 8);
+              const uint32_t a0 = *reinterpret_cast<const uint32_t*>(kr0 + ks * 16);
+              const uint32_t a1 = *reinterpret_cast<const uint32_t*>(kr0 + ks * 16 + 8);
+              const uint32_t c0 = *reinterpret_cast<const uint32_t*>(kr1 + ks * 16);
+              const uint32_t c1 = *reinterpret_cast<const uint32_t*>(kr1 + ks * 16 + 8);
               if (ks & 1) {
                 mma_bf16_16816(sc2[0], qa[ks], a0, a1);
                 mma_bf16_16816(sc2[1], qa[ks], c0, c1);
@@ -2193,15 +2281,15 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
             l0 = l0 * f0 + ps0;
             l1 = l1 * f1 + ps1;
             const int vrow = j0 + (lane & 15);
-            const int vm = vrow % kAttChunks;
-            const uint32_t vbase = smem_u32(sV + (size_t)vrow * kDHP);
+            const uint32_t vbase = smem_u32(sV + (size_t)vrow * kS);
 #pragma unroll
             for (int nt = 0; nt < kDHP / 8; ++nt) {
               o[nt][0] *= f0; o[nt][1] *= f0; o[nt][2] *= f1; o[nt][3] *= f1;
               uint32_t b0, b1;
-              ldmatrix_x2_trans(b0, b1, vbase + att_rot(nt, vm) * 16);
+              ldmatrix_x2_trans(b0, b1, vbase + nt * 16);
               mma_bf16_16816(o[nt], pa, b0, b1);
             }
+          }
           }
           l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
           l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -2362,7 +2450,9 @@ cudaError_t kernels_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(ffn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg::kSmemBytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(qkv_attn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QaCfg::kSmemBytes);
+  e = cudaFuncSetAttribute(qkv_attn_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QaCfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(qkv_attn_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QaCfg::kSmemBytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(embed_condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
@@ -2431,13 +2521,14 @@ void launch_qkv_attn(const __nv_bfloat16* a_img, const uint8_t* w_img, int ntile
   if (!max_pairs) {
     cfg.gridDim = dim3(num_sms() / 2 * 2);
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, qkv_attn_pair_kernel, &cfg) != cudaSuccess || nc <= 0) nc = num_sms() / 2;
+    if (cudaOccupancyMaxActiveClusters(&nc, qkv_attn_pair_kernel<true>, &cfg) != cudaSuccess || nc <= 0) nc = num_sms() / 2;
     max_pairs = nc;
   }
   int pairs = (ntiles + 1) / 2;
   if (pairs > max_pairs) pairs = max_pairs;
   cfg.gridDim = dim3(pairs * 2);
-  cudaLaunchKernelEx(&cfg, qkv_attn_pair_kernel, a_img, w_img, ntiles, L, win, att);
+  if (win > 0 && win <= 16) cudaLaunchKernelEx(&cfg, qkv_attn_pair_kernel<true>, a_img, w_img, ntiles, L, win, att);
+  else cudaLaunchKernelEx(&cfg, qkv_attn_pair_kernel<false>, a_img, w_img, ntiles, L, win, att);
 }
 
 void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int Lw, int win, int nwindows,
