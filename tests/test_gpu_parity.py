@@ -161,15 +161,18 @@ def test_run_model_on_examples_and_stitch(engine_mod, golden_dir):
 
 
 def test_unfused_fallback_paths_agree_with_fused(engine_mod):
-  """DCB_FUSE_OPROJ / DCB_FUSE_EMBED / DCB_FFN_PAIR select measured alternatives of the same math;
+  """DCB_FUSE_OPROJ / DCB_FUSE_EMBED / DCB_FUSE_QA / DCB_ALIGN / DCB_FFN_PAIR select measured alternatives of the same math;
   they are read when an engine is created, so flip them around model construction."""
   p = params_lib.synthetic_params(20, 120, num_hidden_layers=2)
   w = weights_lib.init_weights(p, seed=21)
   rows = synthetic.make_rows(p, 5, seed=22)
   ref = omodel.forward(rows, p, w)["logits"]
   outs = {}
-  for name, env in (("fused", {}), ("unfused", {"DCB_FUSE_OPROJ": "0", "DCB_FUSE_EMBED": "0"}),
-                    ("single_cta", {"DCB_FFN_PAIR": "0"}), ("qkv2", {"DCB_QKV2": "1"})):
+  for name, env in (("fused", {}),
+                    ("unfused", {"DCB_FUSE_OPROJ": "0", "DCB_FUSE_EMBED": "0", "DCB_FUSE_QA": "0"}),
+                    ("packed", {"DCB_ALIGN": "0"}),                     # windows packed back to back, separate QKV / attention
+                    ("single_cta", {"DCB_FFN_PAIR": "0", "DCB_FUSE_QA": "0"}),
+                    ("qkv2", {"DCB_FUSE_QA": "0", "DCB_QKV2": "1"})):
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
     try:
@@ -184,4 +187,5 @@ def test_unfused_fallback_paths_agree_with_fused(engine_mod):
           os.environ[k] = v
     assert np.abs(outs[name] - ref).max() <= LOGIT_TOL_FP32, name
   assert np.abs(outs["fused"] - outs["unfused"]).max() < 0.05
-  assert np.array_equal(outs["fused"], outs["qkv2"])         # same arithmetic, different tiling
+  assert np.abs(outs["fused"] - outs["packed"]).max() < 0.05
+  assert np.abs(outs["qkv2"] - outs["unfused"]).max() < 0.05
