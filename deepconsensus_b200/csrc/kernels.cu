@@ -1588,6 +1588,14 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
           fence_proxy_async_smem();
           arrive_leader(a2_full);
         }
+        // The row warps now idle for the 16 hidden chunks: pull the next tile's residual into L2 so the
+        // hand-over pass below reads it at L2 latency instead of HBM latency (8 rows share a 128-byte line:
+        // thread r fetches the lines of chunks c == r (mod 8)).
+        if (has_next) {
+#pragma unroll
+          for (int c = 0; c < kXChunks / 8; ++c)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(xnext + (size_t)(c * 8 + (r & 7)) * kTileM));
+        }
         // ---- drain the finished tile AND re-initialise Y with the next tile's residual in the same
         // pass: each 16-column block is read out (x_new = Y + b2 -> global) and immediately
         // overwritten with x_old of the next tile, whose loads were issued kRowPF blocks ahead.
