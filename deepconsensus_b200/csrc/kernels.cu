@@ -2043,14 +2043,19 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
         constexpr uint16_t kBoth = 3;
         const uint32_t a_addr = smem_u32(sA);
         uint32_t hi = 0;
+        long long t_afull = 0, t_accfree = 0, t_full = 0, t_issue = 0;
+        const long long t_begin = clock64();
         for (int ti = 0; ti < rounds; ++ti) {
-          mbar_wait_cluster(a_full, ti & 1);
+          { TRACE_T0(); mbar_wait_cluster(a_full, ti & 1); TRACE_ADD(t_afull); }
           tc_fence_after();
           for (int h = 0; h < kHeads; ++h, ++hi) {
+            TRACE_T0();
             mbar_wait_cluster(acc_free, (hi & 1) ^ 1);
+            TRACE_ADD(t_accfree);
             tc_fence_after();
             for (int ks = 0; ks < kDP / 16; ++ks) {
               mbar_wait_cluster(&full[slot], phase);
+              TRACE_ADD(t_full);
               tc_fence_after();
               const uint32_t sb = smem_u32(sRing + slot * C::kStageBytes);
               const uint64_t adesc = make_kc16_desc(a_addr + ks * 4096, kTileM * 16, 128);
@@ -2061,11 +2066,18 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
               }
               umma_commit_pair(&empty[slot], kBoth);
               if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
+              TRACE_ADD(t_issue);
             }
             umma_commit_pair(acc_full, kBoth);
           }
           umma_commit_pair(a_empty, kBoth);
         }
+#ifdef DCB_TRACE
+        if (blockIdx.x < 108) {
+          unsigned long long* tr = g_ffn_trace + (blockIdx.x % 108 + 148) * 16;
+          tr[0] = clock64() - t_begin; tr[1] = t_afull; tr[2] = t_accfree; tr[3] = t_full; tr[4] = t_issue; tr[7] = rounds;
+        }
+#endif
       } else {
         for (int ti = 0; ti < rounds; ++ti) {
           mbar_wait(a_full, ti & 1);
@@ -2077,6 +2089,18 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
           }
         }
       }
+    }
+   } else {
+    // warps 2-3 (otherwise idle): pull the NEXT tile's operand image into L2 so its bulk load, which can
+    // only be issued once this tile's UMMAs have released sA, completes at L2 latency
+    const int pt = threadIdx.x - 64;   // 0..63
+    for (int ti = 0; ti + 1 < rounds; ++ti) {
+      const int tile = min(tile_of(ti + 1), ntiles - 1);
+      const uint8_t* base = reinterpret_cast<const uint8_t*>(a_img) + (size_t)tile * C::kABytes;
+      for (int ln = pt; ln < C::kABytes / 128; ln += 64)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)ln * 128));
+      // pace: one tile ahead is enough -- wait until this round's tile has been consumed
+      mbar_wait(a_empty, ti & 1);
     }
    }
   } else {
@@ -2092,11 +2116,14 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr int kChunkElems = kTileM * 8;
     uint32_t hi = 0;
+    long long t_accfull = 0, t_epi = 0, t_att = 0;
     for (int ti = 0; ti < rounds; ++ti) {
       const int tile_raw = tile_of(ti);
       const bool valid = tile_raw < ntiles;
       for (int h = 0; h < kHeads; ++h, ++hi) {
+        TRACE_T0();
         mbar_wait(acc_full, hi & 1);
+        TRACE_ADD(t_accfull);
         tc_fence_after();
         // ---- TMEM -> bf16 -> shared memory (27 column blocks of 16: q 0-8, k 9-17, v 18-26)
         const int cb0 = halfsel ? 14 : 0, cb1 = halfsel ? 27 : 14;
@@ -2119,6 +2146,7 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
         __syncwarp();
         if (lane == 0) { if (leader) mbar_arrive(acc_free); else mbar_arrive_cluster(acc_free, 0); }
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        TRACE_ADD(t_epi);
 
         // ---- banded attention of query block `ew` (rows 16*ew .. +15) from shared memory
         {
@@ -2316,8 +2344,15 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
           }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");   // q/k/v of this head fully consumed
+        TRACE_ADD(t_att);
       }
     }
+#ifdef DCB_TRACE
+    if (warp == 4 && lane == 0 && blockIdx.x < 108) {
+      unsigned long long* tr = g_ffn_trace + (blockIdx.x % 108 + 148) * 16;
+      tr[8] = t_accfull; tr[9] = t_epi; tr[10] = t_att;
+    }
+#endif
   }
   tc_fence_before();
   __syncthreads();
