@@ -8,8 +8,8 @@ and only the TF-free, pure-NumPy modules are executed:
   deepconsensus/quality_calibration/calibration_lib.py
   deepconsensus/postprocess/stitch_utils.py
 
-The model itself (networks.py etc.) needs real TensorFlow and cannot be run: no numeric golden
-exists for it (see oracle/model.py header).  Also converts a slice of the reference's real
+The model itself (networks.py etc.) is executed separately on a NumPy stand-in for TensorFlow by
+scripts/make_model_golden.py.  This script also converts a slice of the reference's real
 inference windows (testdata/human_1m/tf_examples/inference) into an .npz fixture with a
 TF-free TFRecord/protobuf reader, so GPU tests can use real pileups without /root/reference.
 

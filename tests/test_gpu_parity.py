@@ -189,3 +189,27 @@ def test_unfused_fallback_paths_agree_with_fused(engine_mod):
   assert np.abs(outs["fused"] - outs["unfused"]).max() < 0.05
   assert np.abs(outs["fused"] - outs["packed"]).max() < 0.05
   assert np.abs(outs["qkv2"] - outs["unfused"]).max() < 0.05
+
+
+@pytest.mark.parametrize("name", ["rezero_p20", "layernorm_p20", "rezero_p20_bq", "layernorm_p20_bq", "rezero_p5_win3"])
+def test_engine_against_reference_code_goldens(engine_mod, golden_dir, name):
+  """CUDA path vs outputs of the reference's OWN model code (tests/golden/ref_model_*.npz, generated by
+  scripts/make_model_golden.py) -- no oracle in between."""
+  z = np.load(os.path.join(golden_dir, "ref_model_%s.npz" % name))
+  p = params_lib.get_config(str(z["config"]))
+  for k, v in eval(str(z["overrides"])).items():
+    p[k] = v
+  params_lib.modify_params(p, max_length=int(z["max_length"]))
+  w = weights_lib.init_weights(p, seed=int(z["seed"]))
+  rows = z["rows"]
+  model = engine_mod.B200Model(p, w, max_batch=rows.shape[0])
+  out = model.forward(rows, want_probs=True, want_logits=True, strict_input=False)
+  model.close()
+  assert np.abs(out["logits"] - z["logits"]).max() <= LOGIT_TOL_FP32
+  srt = np.sort(z["logits"], axis=-1)
+  safe = (srt[..., -1] - srt[..., -2]) > MARGIN
+  y, q = opost.quality_from_probs(z["probs"], 93, None)
+  rb, rq = opost.to_ascii(y, q)
+  assert (out["bases"][safe] == rb[safe]).all()
+  assert (out["bases"] == rb).mean() > 0.98
+  assert np.abs(out["probs"] - z["probs"]).max() < 0.05

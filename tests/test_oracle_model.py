@@ -78,3 +78,36 @@ def test_postprocess_matches_quick_inference_semantics():
   assert q.tolist() == [[4, 93, 0, 3]]                     # 3.98*w+b = 3.77, 1.249*w+b = 0.498 -> 0 ; 3.0103*w+b = 2.607
   seq, qual = opost.to_strings(y[0], q[0])
   assert seq == "A  C" and qual == "%~!$"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The pin: vectors produced by EXECUTING the reference's own networks.py / encoder_stack.py / attention_layer.py /
+# ffn_layer.py / data_providers.format_rows / model_configs / model_utils.modify_params on a NumPy stand-in for the
+# TF primitives (scripts/make_model_golden.py + scripts/tf_shim.py).  Weights are regenerated from the seed.
+REF_MODEL_CASES = ["rezero_p20", "layernorm_p20", "rezero_p20_bq", "layernorm_p20_bq", "rezero_p5_win3"]
+
+
+def _load_ref_case(golden_dir, name):
+  z = np.load(os.path.join(golden_dir, "ref_model_%s.npz" % name))
+  over = eval(str(z["overrides"]))            # a repr()'d dict of plain python values written by our own script
+  p = params_lib.get_config(str(z["config"]))
+  for k, v in over.items():
+    p[k] = v
+  params_lib.modify_params(p, max_length=int(z["max_length"]))
+  derived = eval(str(z["derived"]))
+  for k, v in derived.items():                # model_utils.modify_params ran for real when the golden was made
+    assert p[k] == v, (k, p[k], v)
+  w = weights_lib.init_weights(p, seed=int(z["seed"]))
+  return z, p, w
+
+
+@pytest.mark.parametrize("name", REF_MODEL_CASES)
+def test_oracle_matches_reference_code(golden_dir, name):
+  z, p, w = _load_ref_case(golden_dir, name)
+  np.testing.assert_array_equal(omodel.format_rows(z["rows"].copy(), p), z["formatted"])   # data_providers.py:127-184
+  out = omodel.forward(z["rows"], p, w)
+  # float32 both sides, different summation order only
+  assert np.abs(out["final_output"] - z["final_output"]).max() < 5e-5
+  assert np.abs(out["logits"] - z["logits"]).max() < 5e-5
+  assert np.abs(out["probs"] - z["probs"]).max() < 5e-6
+  assert (out["probs"].argmax(-1) == z["probs"].argmax(-1)).mean() == 1.0
