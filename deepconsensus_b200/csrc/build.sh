@@ -3,8 +3,10 @@
 set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="${DCB_EXTRA_FLAGS:-} -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden"
-$NVCC $FLAGS -c kernels.cu -o kernels.o
-$NVCC $FLAGS -Xcompiler -fvisibility=default -c engine.cu -o engine.o
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libdcb200.so kernels.o engine.o -Xlinker -soname=libdcb200.so
-echo "built $(pwd)/libdcb200.so"
+FLAGS="${DCB_EXTRA_FLAGS:-} -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -diag-suppress 177 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden"
+OUT=${DCB_OUT:-libdcb200.so}      # experiment builds: DCB_OUT=libdcb200_exp.so DCB_EXTRA_FLAGS=-D...  (loaded via DCB200_LIB)
+TAG=${OUT%.so}
+$NVCC $FLAGS -c kernels.cu -o $TAG.kernels.o
+$NVCC $FLAGS -Xcompiler -fvisibility=default -c engine.cu -o $TAG.engine.o
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT $TAG.kernels.o $TAG.engine.o -Xlinker -soname=$OUT
+echo "built $(pwd)/$OUT"

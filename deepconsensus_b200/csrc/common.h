@@ -64,6 +64,22 @@ struct RowEpi {
   int L;                 // tokens per window in the flattened layout (Lw): position = token % L
 };
 
+// ------------------------------------------------------------------ whole-stack kernel
+constexpr int kMaxLayers = 8;
+struct StackParams {
+  const uint8_t* wq3[kMaxLayers];    // per layer: [head][rank][q|k|v] x [36 k-chunks][72 rows][8] bf16
+  const uint8_t* wo2[kMaxLayers];    // per layer: [rank][36][144][8] (ReZero alpha folded in)
+  const uint8_t* wffn2[kMaxLayers];  // per layer: [chunk][rank]{[36][64][8], [16][144][8]}
+  const float* b1[kMaxLayers];       // [ff]
+  const float* b2[kMaxLayers];       // [288] (alpha folded in)
+  const float* ln_g0[kMaxLayers];    // pre-norm of the attention sub-layer, or null (ReZero)
+  const float* ln_b0[kMaxLayers];
+  const float* ln_g1[kMaxLayers];    // pre-norm of the FFN sub-layer, or null
+  const float* ln_b1[kMaxLayers];
+  int num_layers;
+  int ff;
+};
+
 struct HeadParams {
   const float* x;        // fp32 residual image
   const float* ln_g;     // final LayerNorm gamma/beta [288]

@@ -25,6 +25,7 @@ thread_local std::string g_create_error;
 struct LayerDev {
   __nv_bfloat16* wqkv = nullptr;  // 2 groups x [36][432][8]
   uint8_t* wqkv2 = nullptr;       // 9 groups x [36][96][8] (qkv2_kernel)
+  uint8_t* wq3 = nullptr;         // stack kernel: per (head, rank, q|k|v) [36][72][8]
   uint8_t* wqa = nullptr;         // fused QKV+attention: per (head, rank) [36][216][8], rows = q|k|v halves
   __nv_bfloat16* wo = nullptr;    // [36][288][8]
   uint8_t* wffn = nullptr;        // per ff chunk: [36][128][8] then [16][288][8]
@@ -44,22 +45,36 @@ struct dcb_engine {
   int R = 0, L = 0, Lw = 0, E = 0, Epad = 0, echunks = 0;   // Lw: tokens per window in the layout (>= L)
   int chunk_tiles = 0, chunk_windows = 0;
   int num_sms = 148;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream = nullptr;        // compute (+ result D2H)
+  cudaStream_t copy_stream = nullptr;   // H2D of the rows of the NEXT submission, overlapping the kernels of the current one
+  // Two-deep submission pipeline (dcb_submit / dcb_wait): only the input rows and the status word are per slot; every
+  // other buffer is reused in stream order.
+  struct Slot {
+    float* d_rows = nullptr;
+    int* d_status = nullptr;
+    int* h_status = nullptr;            // pinned
+    cudaEvent_t rows_ready = nullptr, ev0 = nullptr, ev1 = nullptr, done = nullptr;
+    bool busy = false, used = false;
+    int64_t ticket = -1;
+    int launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // around every launch when profiling
+    std::vector<int> prof_kind;                                    // kernel class of each event pair
+    size_t prof_used = 0;
+  } slots[2];
+  int64_t next_ticket = 0;
   bool weights_loaded = false;
   bool debug = false;
   bool ffn_pair = true;
   bool fuse_oproj = true;
   bool fuse_embed = true;
   bool fuse_qa = true;
+  bool stack = true;   // whole encoder stack in one launch (stack_pair_kernel) when the configuration allows it
   bool qkv2 = false;   // measured: not faster than gemm_kernel<3,QKV> (both sit on the per-SM L2 port), kept as an option
   bool fused_last = false;
+  bool stack_last = false;
   bool profile = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // around every launch when profiling
-  std::vector<int> prof_kind;       // kernel class of each event pair
   float prof_ms[6] = {0, 0, 0, 0, 0, 0};   // embed, gemm_row, qkv, attention, ffn(+out-proj), head
   int prof_n[6] = {0, 0, 0, 0, 0, 0};
-  size_t prof_used = 0;
   float prof_ffn_ms = 0.f;
   int prof_ffn_launches = 0;
   long long prof_ffn_tokens = 0;
@@ -76,14 +91,12 @@ struct dcb_engine {
   std::vector<LayerDev> layers;
   float *d_fln_g = nullptr, *d_fln_b = nullptr, *d_wfc = nullptr, *d_bfc = nullptr;
   // workspace
-  float* d_rows = nullptr;
   __nv_bfloat16* d_embqkv = nullptr;
   float* d_x = nullptr;
   __nv_bfloat16* d_xb = nullptr;
   __nv_bfloat16* d_att = nullptr;
   uint8_t *d_bases = nullptr, *d_quals = nullptr;
   float *d_probs = nullptr, *d_logits = nullptr;
-  int* d_status = nullptr;
   float* d_dbg = nullptr;  // [stages][chunk_tiles * x_image]
   std::vector<void*> owned;
 };
@@ -217,6 +230,7 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   if (const char* env = getenv("DCB_QKV2")) e->qkv2 = atoi(env) != 0;
   if (const char* env = getenv("DCB_FUSE_EMBED")) e->fuse_embed = atoi(env) != 0;
   if (const char* env = getenv("DCB_FUSE_QA")) e->fuse_qa = atoi(env) != 0;
+  if (const char* env = getenv("DCB_STACK")) e->stack = atoi(env) != 0;
   int ct = cfg->chunk_tiles;
   if (const char* env = getenv("DCB_CHUNK_TILES")) ct = atoi(env);
   if (ct <= 0) ct = 8 * e->num_sms;   // measured: larger chunks win (kernels are not DRAM-bound)
@@ -229,11 +243,20 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
 #define CUC(call) do { cudaError_t _s = (call); if (_s != cudaSuccess) { fail(e, DCB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_s)); return bail(DCB_ERR_CUDA); } } while (0)
   CUC(cudaSetDevice(cfg->device));
   CUC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  CUC(cudaEventCreate(&e->ev0));
-  CUC(cudaEventCreate(&e->ev1));
+  CUC(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  for (auto& sl : e->slots) {
+    CUC(cudaEventCreateWithFlags(&sl.rows_ready, cudaEventDisableTiming));
+    CUC(cudaEventCreate(&sl.ev0));
+    CUC(cudaEventCreate(&sl.ev1));
+    CUC(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    CUC(cudaMallocHost(reinterpret_cast<void**>(&sl.h_status), sizeof(int)));
+  }
   CUC(kernels_init());
   const size_t T = e->chunk_tiles;
-  TRY(dev_alloc(e, &e->d_rows, (size_t)e->chunk_windows * e->R * e->L));
+  for (auto& sl : e->slots) {
+    TRY(dev_alloc(e, &sl.d_rows, (size_t)cfg->max_batch * e->R * e->L));
+    TRY(dev_alloc(e, &sl.d_status, 1));
+  }
   TRY(dev_alloc(e, &e->d_embqkv, T * kTileM * (size_t)std::max(e->Epad, kQKVN)));
   TRY(dev_alloc(e, &e->d_x, T * x_image_elems()));
   TRY(dev_alloc(e, &e->d_xb, T * act_image_elems(kDP)));
@@ -241,7 +264,6 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   const size_t mtok = (size_t)cfg->max_batch * e->L;
   TRY(dev_alloc(e, &e->d_bases, mtok));
   TRY(dev_alloc(e, &e->d_quals, mtok));
-  TRY(dev_alloc(e, &e->d_status, 1));
 #undef TRY
 #undef CUC
   *out = e;
@@ -251,11 +273,20 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
 void dcb_destroy(dcb_engine* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
+  if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void* p : e->owned) cudaFree(p);
-  for (auto& pr : e->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-  if (e->ev0) cudaEventDestroy(e->ev0);
-  if (e->ev1) cudaEventDestroy(e->ev1);
+  for (auto& sl : e->slots)
+    for (auto& pr : sl.prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+  for (auto& sl : e->slots) {
+    if (sl.rows_ready) cudaEventDestroy(sl.rows_ready);
+    if (sl.ev0) cudaEventDestroy(sl.ev0);
+    if (sl.ev1) cudaEventDestroy(sl.ev1);
+    if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.h_status) cudaFreeHost(sl.h_status);
+  }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -436,6 +467,23 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
       __nv_bfloat16* dptr2 = nullptr;
       if ((rc = upload(e, &dptr2, imga))) return rc;
       ld.wqa = reinterpret_cast<uint8_t*>(dptr2);
+      // stack kernel: one [36][72][8] block per (head, rank, q|k|v), consumed as three 6-k-step stages
+      std::vector<__nv_bfloat16> img3;
+      for (int h = 0; h < kHeads; ++h)
+        for (int rk = 0; rk < 2; ++rk)
+          for (int m = 0; m < 3; ++m) {
+            auto part = pack_b(kDP, kDHP / 2, [&](int k, int nn) {
+              const int dd = rk * (kDHP / 2) + nn;
+              if (k >= kD || dd >= kDH) return 0.f;
+              const float* w = m == 0 ? wq : (m == 1 ? wk : wv);
+              const float v = w[((size_t)k * kHeads + h) * kDH + dd];
+              return m == 0 ? v * qscale : v;
+            });
+            img3.insert(img3.end(), part.begin(), part.end());
+          }
+      __nv_bfloat16* dptr3 = nullptr;
+      if ((rc = upload(e, &dptr3, img3))) return rc;
+      ld.wq3 = reinterpret_cast<uint8_t*>(dptr3);
     }
     {
       // out-proj: K index = head*144 + dd, N = e; ReZero alpha folded in (encoder_stack.py:88-90)
@@ -533,12 +581,16 @@ int dcb_set_debug(dcb_engine* e, int32_t enabled) {
   return DCB_OK;
 }
 
-int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, uint8_t* bases_out,
-                uint8_t* quals_out, float* probs_out, float* logits_out) {
-  if (!e) return DCB_ERR_INVALID;
+int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, uint8_t* bases_out,
+               uint8_t* quals_out, float* probs_out, float* logits_out, int64_t* ticket_out) {
+  if (!e || !ticket_out) return DCB_ERR_INVALID;
   if (!e->weights_loaded) return fail(e, DCB_ERR_STATE, "dcb_forward before dcb_load_weights");
+  dcb_engine::Slot& sl = e->slots[e->next_ticket & 1];
+  if (sl.busy) return fail(e, DCB_ERR_STATE, "two submissions in flight: dcb_wait(ticket %lld) first", (long long)sl.ticket);
   if (batch < 0 || batch > e->cfg.max_batch) return fail(e, DCB_ERR_INVALID, "batch %d outside [0, max_batch=%d]", batch, e->cfg.max_batch);
-  if (batch == 0) { e->last_ms = 0.f; e->last_launches = 0; return DCB_OK; }
+  sl.launches = 0;
+  sl.ticket = e->next_ticket;
+  if (batch == 0) { sl.busy = true; sl.used = false; *ticket_out = e->next_ticket++; return DCB_OK; }
   if (!rows || !bases_out || !quals_out) return fail(e, DCB_ERR_INVALID, "null rows / output buffer");
   CU(e, cudaSetDevice(e->cfg.device));
   const dcb_config& c = e->cfg;
@@ -549,40 +601,41 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
   const bool rows_dev = flags & DCB_ROWS_ON_DEVICE;
   const bool out_dev = flags & DCB_OUT_ON_DEVICE;
   cudaStream_t st = e->stream;
-  CU(e, cudaMemsetAsync(e->d_status, 0, sizeof(int), st));
-  CU(e, cudaEventRecord(e->ev0, st));
+  if (!rows_dev) {
+    // The slot's previous forward (two submissions ago) was waited for before the slot was handed out again, so its
+    // rows buffer is free; the copy overlaps whatever the compute stream is still running for the other slot.
+    CU(e, cudaMemcpyAsync(sl.d_rows, rows, (size_t)batch * R * L * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
+    CU(e, cudaEventRecord(sl.rows_ready, e->copy_stream));
+    CU(e, cudaStreamWaitEvent(st, sl.rows_ready, 0));
+  }
+  const float* rows_base = rows_dev ? rows : sl.d_rows;
+  CU(e, cudaMemsetAsync(sl.d_status, 0, sizeof(int), st));
+  CU(e, cudaEventRecord(sl.ev0, st));
   int launches = 0;
   const size_t ximg = x_image_elems();
   bool prof_err = false;
   auto pbegin = [&](int kind) {
     if (!e->profile) return;
-    if (e->prof_used == e->prof_events.size()) {
+    if (sl.prof_used == sl.prof_events.size()) {
       cudaEvent_t a, b;
       if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { prof_err = true; return; }
-      e->prof_events.emplace_back(a, b);
+      sl.prof_events.emplace_back(a, b);
     }
-    if (e->prof_kind.size() <= e->prof_used) e->prof_kind.resize(e->prof_used + 1);
-    e->prof_kind[e->prof_used] = kind;
-    cudaEventRecord(e->prof_events[e->prof_used].first, st);
+    if (sl.prof_kind.size() <= sl.prof_used) sl.prof_kind.resize(sl.prof_used + 1);
+    sl.prof_kind[sl.prof_used] = kind;
+    cudaEventRecord(sl.prof_events[sl.prof_used].first, st);
   };
   auto pend = [&]() {
     if (!e->profile || prof_err) return;
-    cudaEventRecord(e->prof_events[e->prof_used].second, st);
-    ++e->prof_used;
+    cudaEventRecord(sl.prof_events[sl.prof_used].second, st);
+    ++sl.prof_used;
   };
   for (int w0 = 0; w0 < batch; w0 += e->chunk_windows) {
     const int bw = std::min(e->chunk_windows, batch - w0);
     const int Lw = e->Lw;
     const int M = bw * Lw;          // tokens in the (possibly window-aligned) layout
     const int T = (M + kTileM - 1) / kTileM;
-    const float* rows_chunk;
-    if (rows_dev) {
-      rows_chunk = rows + (size_t)w0 * R * L;
-    } else {
-      CU(e, cudaMemcpyAsync(e->d_rows, rows + (size_t)w0 * R * L, (size_t)bw * R * L * sizeof(float),
-                            cudaMemcpyHostToDevice, st));
-      rows_chunk = e->d_rows;
-    }
+    const float* rows_chunk = rows_base + (size_t)w0 * R * L;
     int stage = 0;
     auto snap = [&]() {
       if (e->debug) cudaMemcpyAsync(e->d_dbg + (size_t)stage * e->chunk_tiles * ximg, e->d_x, (size_t)T * ximg * sizeof(float), cudaMemcpyDeviceToDevice, st);
@@ -599,13 +652,13 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
       if (e->fuse_embed) {
         pbegin(1);
         fused_embed = launch_embed_condense(rows_chunk, R, L, Lw, M, T, e->echunks, e->d_cols, e->d_rowmeta, e->d_tables,
-                                            e->table_elems, e->d_wc, epi, e->d_status, st);
+                                            e->table_elems, e->d_wc, epi, sl.d_status, st);
         pend();
         if (fused_embed) ++launches;
       }
       if (!fused_embed) {
         pbegin(0);
-        launch_embed(rows_chunk, R, L, Lw, M, T, e->echunks, e->d_cols, e->d_rowmeta, e->d_tables, e->table_elems, e->d_embqkv, e->d_status, st);
+        launch_embed(rows_chunk, R, L, Lw, M, T, e->echunks, e->d_cols, e->d_rowmeta, e->d_tables, e->table_elems, e->d_embqkv, sl.d_status, st);
         pend();
         pbegin(1);
         launch_gemm_row(e->d_embqkv, e->d_wc, e->Epad / 16, T, epi, st);
@@ -614,7 +667,28 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
       }
       snap();
     }
-    for (int n_ = 0; n_ < c.num_hidden_layers; ++n_) {
+    const bool use_stack = e->stack && e->fuse_qa && e->ffn_pair && e->fuse_oproj && !e->debug && Lw == kTileM &&
+                           c.attn_win_size > 0 && c.attn_win_size <= 16 && c.num_hidden_layers <= kMaxLayers;
+    if (use_stack) {
+      StackParams sp{};
+      sp.num_layers = c.num_hidden_layers;
+      sp.ff = c.filter_size;
+      for (int n_ = 0; n_ < c.num_hidden_layers; ++n_) {
+        const LayerDev& ld = e->layers[n_];
+        sp.wq3[n_] = ld.wq3; sp.wo2[n_] = ld.wo2; sp.wffn2[n_] = ld.wffn2;
+        sp.b1[n_] = ld.b1; sp.b2[n_] = ld.b2;
+        sp.ln_g0[n_] = c.rezero ? nullptr : ld.ln_g[0]; sp.ln_b0[n_] = c.rezero ? nullptr : ld.ln_b[0];
+        sp.ln_g1[n_] = c.rezero ? nullptr : ld.ln_g[1]; sp.ln_b1[n_] = c.rezero ? nullptr : ld.ln_b[1];
+      }
+      pbegin(4);
+      launch_stack(e->d_x, T, L, c.attn_win_size, sp, st);
+      pend();
+      if (e->profile) e->prof_ffn_tokens += (long long)bw * L;
+      e->fused_last = true;
+      e->stack_last = true;
+      ++launches;
+    } else e->stack_last = false;
+    for (int n_ = 0; !use_stack && n_ < c.num_hidden_layers; ++n_) {
       const LayerDev& ld = e->layers[n_];
       const bool last = n_ + 1 == c.num_hidden_layers;
       if (e->fuse_qa && Lw == kTileM) {
@@ -682,7 +756,7 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
     ++launches;
     e->last_chunk_tokens = M;
   }
-  CU(e, cudaEventRecord(e->ev1, st));
+  CU(e, cudaEventRecord(sl.ev1, st));
   if (!out_dev) {
     const size_t ntok = (size_t)batch * L;
     CU(e, cudaMemcpyAsync(bases_out, e->d_bases, ntok, cudaMemcpyDeviceToHost, st));
@@ -690,25 +764,49 @@ int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
     if (probs_out) CU(e, cudaMemcpyAsync(probs_out, e->d_probs, ntok * kVocab * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (logits_out) CU(e, cudaMemcpyAsync(logits_out, e->d_logits, ntok * kVocab * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
-  int status = 0;
-  CU(e, cudaMemcpyAsync(&status, e->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CU(e, cudaStreamSynchronize(st));
+  CU(e, cudaMemcpyAsync(sl.h_status, sl.d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(e, cudaEventRecord(sl.done, st));
   CU(e, cudaGetLastError());
-  CU(e, cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
-  e->last_launches = launches;
-  if (e->profile) {
-    for (size_t i = 0; i < e->prof_used; ++i) {
+  sl.launches = launches;
+  sl.busy = true;
+  sl.used = true;
+  *ticket_out = e->next_ticket++;
+  return DCB_OK;
+}
+
+int dcb_wait(dcb_engine* e, int64_t ticket) {
+  if (!e) return DCB_ERR_INVALID;
+  dcb_engine::Slot& sl = e->slots[ticket & 1];
+  if (ticket < 0 || !sl.busy || sl.ticket != ticket) return fail(e, DCB_ERR_STATE, "dcb_wait: ticket %lld is not in flight", (long long)ticket);
+  sl.busy = false;
+  if (!sl.used) { e->last_ms = 0.f; e->last_launches = 0; return DCB_OK; }   // empty batch
+  CU(e, cudaSetDevice(e->cfg.device));
+  CU(e, cudaEventSynchronize(sl.done));
+  CU(e, cudaGetLastError());
+  CU(e, cudaEventElapsedTime(&e->last_ms, sl.ev0, sl.ev1));
+  e->last_launches = sl.launches;
+  const int status = *sl.h_status;
+  {
+    for (size_t i = 0; i < sl.prof_used; ++i) {
       float ms = 0.f;
-      CU(e, cudaEventElapsedTime(&ms, e->prof_events[i].first, e->prof_events[i].second));
-      const int kind = e->prof_kind[i];
+      CU(e, cudaEventElapsedTime(&ms, sl.prof_events[i].first, sl.prof_events[i].second));
+      const int kind = sl.prof_kind[i];
       e->prof_ms[kind] += ms;
       ++e->prof_n[kind];
       if (kind == 4) { e->prof_ffn_ms += ms; ++e->prof_ffn_launches; }
     }
-    e->prof_used = 0;
+    sl.prof_used = 0;
   }
   if (status & 1) return fail(e, DCB_ERR_INPUT_RANGE, "embedding id out of range in the input rows (clamped)");
   return DCB_OK;
+}
+
+int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, uint8_t* bases_out,
+                uint8_t* quals_out, float* probs_out, float* logits_out) {
+  int64_t ticket = -1;
+  int rc = dcb_submit(e, rows, batch, flags, bases_out, quals_out, probs_out, logits_out, &ticket);
+  if (rc) return rc;
+  return dcb_wait(e, ticket);
 }
 
 int dcb_last_forward_ms(dcb_engine* e, float* ms) {
@@ -729,7 +827,7 @@ int dcb_set_profile(dcb_engine* e, int32_t enabled) {
   e->prof_ffn_ms = 0.f;
   e->prof_ffn_launches = 0;
   e->prof_ffn_tokens = 0;
-  e->prof_used = 0;
+  for (auto& sl : e->slots) sl.prof_used = 0;
   for (int i = 0; i < 6; ++i) { e->prof_ms[i] = 0.f; e->prof_n[i] = 0; }
   return DCB_OK;
 }
@@ -745,7 +843,7 @@ int dcb_get_profile(dcb_engine* e, float* ffn_ms_total, int32_t* ffn_launches, i
 int dcb_get_profile_kernels(dcb_engine* e, float* ms6, int32_t* n6, int32_t* fused_oproj) {
   if (!e || !ms6 || !n6 || !fused_oproj) return DCB_ERR_INVALID;
   for (int i = 0; i < 6; ++i) { ms6[i] = e->prof_ms[i]; n6[i] = e->prof_n[i]; }
-  *fused_oproj = e->fused_last ? 1 : 0;
+  *fused_oproj = e->stack_last ? 2 : (e->fused_last ? 1 : 0);   // 2: whole stack in one kernel
   return DCB_OK;
 }
 

@@ -936,7 +936,7 @@ ffn_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ 
       constexpr uint32_t idesc_y = make_idesc_bf16(kTileM, kNC);
       const uint32_t a_addr = smem_u32(sA);
       uint32_t slot = 0, phase = 0, n = 0;  // n: global hidden-chunk counter
-      long long t_hfree = 0, t_full = 0, t_hsfull = 0, t_issue = 0, t_afull = 0, t_yempty = 0;
+      long long t_hfree = 0, t_full = 0, t_hsfull = 0, t_issue = 0, t_afull = 0, t_yempty = 0, t_oproj = 0, t_a2full = 0;
       const long long t_begin = clock64();
       auto release = [&](uint64_t* bar) {
         if (CS == 1) umma_commit(bar); else umma_commit_multicast(bar, kMask);
@@ -1019,7 +1019,7 @@ ffn_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restrict__ 
       if (blockIdx.x < 256) {
         unsigned long long* tr = g_ffn_trace + blockIdx.x * 16;
         tr[0] = clock64() - t_begin; tr[1] = t_hfree; tr[2] = t_full; tr[3] = t_hsfull;
-        tr[4] = t_issue; tr[5] = t_afull; tr[6] = t_yempty; tr[7] = rounds;
+        tr[4] = t_issue; tr[5] = t_afull; tr[6] = t_yempty; tr[7] = t_a2full; tr[15] = t_oproj;
       }
 #endif
     }
@@ -1255,8 +1255,12 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
       uint32_t slot = 0, phase = 0;
       auto push = [&](const uint8_t* src, uint32_t bytes) {
         mbar_wait(&empty[slot], phase ^ 1);
+#ifdef DCB_EXP_NOW   // timing experiment only (wrong results): no weight bytes move, stages "land" immediately
+        mbar_arrive(&full[slot]);
+#else
         mbar_arrive_expect_tx(&full[slot], bytes);
         bulk_g2s(sRing + slot * C::kSlotBytes, src, bytes, &full[slot]);
+#endif
         if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
       };
       auto half = [&](int c) { return w2img + ((size_t)c * 2 + rank) * C::kHalfChunkBytes; };
@@ -1297,7 +1301,7 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
         const bool g1 = warp == 1;
         const uint32_t a_addr = smem_u32(sA);
         uint32_t slot = 0, phase = 0, n = 0;
-        long long t_hfree = 0, t_full = 0, t_hsfull = 0, t_issue = 0, t_afull = 0, t_yempty = 0;
+        long long t_hfree = 0, t_full = 0, t_hsfull = 0, t_issue = 0, t_afull = 0, t_yempty = 0, t_oproj = 0, t_a2full = 0;
         const long long t_begin = clock64();
         auto skip = [&](int count) {
           for (int s = 0; s < count; ++s)
@@ -1384,7 +1388,9 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
                 if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
               }
               umma_commit_pair(ymid_full, kBoth);
+              TRACE_ADD(t_oproj);
               mbar_wait_cluster(a2_full, ti & 1);   // FFN operand tile written by both CTAs' row warps
+              TRACE_ADD(t_a2full);
               tc_fence_after();
             }
             gemm1(n);
@@ -1412,7 +1418,7 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
         if (g1 && blockIdx.x < 256) {
           unsigned long long* tr = g_ffn_trace + blockIdx.x * 16;
           tr[0] = clock64() - t_begin; tr[1] = t_hfree; tr[2] = t_full; tr[3] = t_hsfull;
-          tr[4] = t_issue; tr[5] = t_afull; tr[6] = t_yempty; tr[7] = rounds;
+          tr[4] = t_issue; tr[5] = t_afull; tr[6] = t_yempty; tr[7] = t_a2full; tr[15] = t_oproj;
         }
 #endif
       } else if (warp == 1) {
@@ -1481,11 +1487,16 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(acc[cc][i]) + bias[cc * 16 + i], 0.f);
+#ifdef DCB_EXP_NOHST   // timing experiment only (wrong results): the hidden tile is not written to shared memory
+            if (v[0] + v[5] + v[9] + v[15] == 12345.678f)
+#endif
+            {
             hrow[(size_t)(cb * 2) * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                                          pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
             hrow[(size_t)(cb * 2 + 1) * kTileM] =
                 make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
                            pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+            }
           }
           fence_proxy_async_smem();
           arrive_leader(&hs_full[b]);
@@ -2363,6 +2374,8 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
   }
 }
 
+#include "stack_kernel.cuh"
+
 // =====================================================================================
 // head: final LayerNorm -> fc1 -> softmax -> argmax / Phred / ASCII
 // =====================================================================================
@@ -2487,6 +2500,8 @@ cudaError_t kernels_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(ffn_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ffn2Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(stack_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StackCfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(ffn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg::kSmemBytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(ffn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg::kSmemBytes);
@@ -2572,6 +2587,25 @@ void launch_qkv_attn(const __nv_bfloat16* a_img, const uint8_t* w_img, int ntile
   cfg.gridDim = dim3(pairs * 2);
   if (win > 0 && win <= 16) cudaLaunchKernelEx(&cfg, qkv_attn_pair_kernel<true>, a_img, w_img, ntiles, L, win, att);
   else cudaLaunchKernelEx(&cfg, qkv_attn_pair_kernel<false>, a_img, w_img, ntiles, L, win, att);
+}
+
+void launch_stack(float* x, int ntiles, int L, int win, const StackParams& p, cudaStream_t st) {
+  static int max_pairs = 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(StackCfg::kThreads);
+  cfg.dynamicSmemBytes = StackCfg::kSmemBytes;
+  cfg.stream = st;
+  if (!max_pairs) {
+    cfg.gridDim = dim3(num_sms() / 2 * 2);
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, stack_pair_kernel, &cfg) != cudaSuccess || nc <= 0) nc = num_sms() / 2;
+    max_pairs = nc;
+    if (getenv("DCB_VERBOSE")) fprintf(stderr, "[dcb200] stack kernel: %d co-resident CTA pairs\n", nc);
+  }
+  int pairs = (ntiles + 1) / 2;
+  if (pairs > max_pairs) pairs = max_pairs;
+  cfg.gridDim = dim3(pairs * 2);
+  cudaLaunchKernelEx(&cfg, stack_pair_kernel, x, ntiles, L, win, p);
 }
 
 void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int Lw, int win, int nwindows,

@@ -1,0 +1,709 @@
+// The whole encoder stack in ONE launch (included by kernels.cu after the helpers it uses).
+//
+// A CTA pair (tcgen05 cta_group::2, M = 256) owns two window-aligned 128-token tiles and walks them through ALL
+// layers; the fp32 residual tile never leaves the SM: it lives in the 288 TMEM columns "Y" from the first layer to the
+// last, and every sub-layer accumulates onto it in place (residual-in-accumulator):
+//
+//   per layer   P1  workers: Y (+= b2 of the previous FFN) -> [LayerNorm] -> bf16 operand tile sA
+//               per head h: 3 UMMA blocks (N = 144: q, k, v of the head; K = 288) into ACC (TMEM 288..431),
+//                           workers move each block as bf16 into padded shared-memory rows,
+//                           banded softmax attention per 16-query block (mma.sync, two-pass) -> att_h (bf16, KC16)
+//                           Y += att_h * Wo_h^T                     (encoder_stack.py:72-93, attention_layer.py:218)
+//               P5  workers: Y (= x_mid) -> [LayerNorm] -> sA
+//               16 hidden chunks: H = sA*W1c (TMEM 288..415) -> +b1, ReLU, bf16 -> shared -> Y += Hc*W2c
+//   per tile    once: Y <- x (global), and after the last layer Y + b2 -> x (global) for the head kernel.
+//
+// Against the per-layer kernels this removes, per tile and layer, the fp32 residual round trip through HBM (294 KB),
+// the attention-output and operand images (296 KB), and both tile hand-over phases in which the tensor pipe idled
+// (measured 16 k + 11 k of 83 k cycles per tile in ffn_pair_kernel<true>).
+//
+// Weights stream through a ring of 13,824-byte slots in exactly the order they are consumed (a static program that
+// producer, UMMA issuers and the peer's relay thread all walk): three dedicated slots, plus three more that live in the
+// tail of the q/k/v staging area and are used only while that area holds the (smaller) hidden tiles of the FFN phase.
+//
+// Cross-CTA protocol as in ffn_pair_kernel: the leader (cluster rank 0) issues every UMMA; tcgen05.commit multicasts
+// completion to both CTAs; what the peer's warps produce is signalled with one default-semantics remote arrive per
+// warp on the leader's barrier; the peer's relay thread forwards "my half of this stage has landed".
+#pragma once
+
+struct StackCfg {
+  static constexpr int kABytes = (kDP / 8) * kTileM * 16;              // 73728: bf16 operand tile
+  static constexpr int kStride = 152;                                  // padded q/k/v row (304 B, conflict-free)
+  static constexpr int kMatBytes = kTileM * kStride * 2;               // 38912
+  static constexpr int kStageBytes = 3 * kMatBytes;                    // 116736: q | k | v of one head
+  static constexpr int kHBytes = (kFFChunk / 8) * kTileM * 16;         // 32768: one hidden chunk tile
+  static constexpr int kSlotBytes = 13824;
+  static constexpr int kSlotsA = 3, kSlotsF = 6;
+  static constexpr int kQkvStepBytes = 2 * (kDHP / 2) * 16;            // 2304: one k-step of a q/k/v block (72 rows)
+  static constexpr int kQkvStageK = 6, kQkvStages = 3;                 // 18 k-steps per block
+  static constexpr int kQkvBlockBytes = (kDP / 16) * kQkvStepBytes;    // 41472
+  static constexpr int kWoStepBytes = 2 * (kDP / 2) * 16;              // 4608: one k-step of Wo / W2 (144 rows)
+  static constexpr int kWoStageK = 3, kWoStages = 3;                   // 9 k-steps per head
+  static constexpr int kW1StepBytes = 2 * (kFFChunk / 2) * 16;         // 2048 (64 rows)
+  static constexpr int kW1StageK = 6, kW1Stages = 3;
+  static constexpr int kW2StageK = 2, kW2Stages = 4;
+  static constexpr int kHalfChunkBytes = (kDP / 16) * kW1StepBytes + (kFFChunk / 16) * kWoStepBytes;   // 73728
+  static constexpr int kOffA = 0;
+  static constexpr int kOffS = kABytes;                                // staging: q|k|v, att_h, hidden tiles, LN stats
+  static constexpr int kOffTail = kOffS + 2 * kHBytes;                 // ring slots 3..5 (FFN phase only)
+  static constexpr int kOffRing = kOffS + kStageBytes;                 // ring slots 0..2
+  static constexpr int kOffBars = kOffRing + kSlotsA * kSlotBytes;
+  static constexpr int kSmemBytes = kOffBars + 256;
+  static constexpr int kThreads = 384;   // warp 0 producer, 1 UMMA issuer A / relay, 2 UMMA issuer B, 3 prefetch, 4-11 workers
+  static constexpr int kTmemY = 0, kTmemAcc = kDP, kTmemH = kDP, kTmemCols = 512;
+};
+static_assert(StackCfg::kSmemBytes <= 232448, "stack kernel shared memory budget");
+static_assert(StackCfg::kOffTail + 3 * StackCfg::kSlotBytes <= StackCfg::kOffRing, "tail slots fit behind the hidden tiles");
+static_assert(StackCfg::kQkvStageK * StackCfg::kQkvStepBytes == StackCfg::kSlotBytes, "qkv stage");
+static_assert(StackCfg::kWoStageK * StackCfg::kWoStepBytes == StackCfg::kSlotBytes, "wo stage");
+static_assert(StackCfg::kW1StageK * StackCfg::kW1StepBytes <= StackCfg::kSlotBytes, "w1 stage");
+static_assert(StackCfg::kW2StageK * StackCfg::kWoStepBytes <= StackCfg::kSlotBytes, "w2 stage");
+static_assert(StackCfg::kTmemAcc + kNC <= 512 && StackCfg::kTmemH + kFFChunk <= 512, "TMEM map");
+
+// Debug aid (-DDCB_WATCHDOG): every mbarrier wait gives up after ~50 M cycles, records (tag, parity) of EVERY waiting
+// warp in g_ffn_trace[block*16 + warp] and lets the kernel run to completion (garbage results) so the host can read
+// who was waiting on what (scripts/gpu_stack_check.py prints it).
+#ifdef DCB_WATCHDOG
+__device__ unsigned int g_stack_abort = 0;
+template <bool kCluster>
+__device__ __forceinline__ void stack_wait(uint64_t* bar, uint32_t parity, int tag) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    if (kCluster) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } else {
+      ok = mbar_try_wait(bar, parity) ? 1u : 0u;
+    }
+    if (ok) return;
+    if (clock64() - t0 > 50000000ll || *reinterpret_cast<volatile unsigned int*>(&g_stack_abort)) {
+      g_stack_abort = 1;
+      if (blockIdx.x < 256) {
+        unsigned long long* tr = g_ffn_trace + blockIdx.x * 16 + (threadIdx.x >> 5);
+        if (*tr == 0) *tr = 0x8000000000000000ull | ((unsigned long long)(clock64() - t0) << 24) | ((unsigned long long)parity << 16) | (unsigned long long)tag;
+      }
+      return;
+    }
+  }
+}
+#define SW(bar, par, tag) stack_wait<false>(bar, par, tag)
+#define SWC(bar, par, tag) stack_wait<true>(bar, par, tag)
+#else
+#define SW(bar, par, tag) mbar_wait(bar, par)
+#define SWC(bar, par, tag) mbar_wait_cluster(bar, par)
+#endif
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(StackCfg::kThreads, 1)
+stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __grid_constant__ StackParams P) {
+  using C = StackCfg;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem + C::kOffA;
+  uint8_t* sS = smem + C::kOffS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
+  uint64_t* full = bars;             // [6]
+  uint64_t* empty = bars + 6;        // [6]
+  uint64_t* a_ready = bars + 12;     // operand tile sA written by all workers of both CTAs (leader)
+  uint64_t* acc_full = bars + 13;    // a q/k/v block landed in ACC (commit)
+  uint64_t* acc_free = bars + 14;    // ... and has been read out by the workers (leader)
+  uint64_t* att_ready = bars + 15;   // att_h written to the staging area (leader)
+  uint64_t* s_free = bars + 16;      // out-proj of a head done: staging reusable / Y = x_mid after head 1 (commit)
+  uint64_t* tail_free = bars + 17;   // attention part of the layer done: ring slots 3..5 usable (commit)
+  uint64_t* h_full = bars + 18;
+  uint64_t* h_free = bars + 19;
+  uint64_t* hs_full = bars + 20;     // [2]
+  uint64_t* hs_free = bars + 22;     // [2]
+  uint64_t* y_full = bars + 24;      // FFN of the layer done (commit)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 25);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int npairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
+  const int tile_pairs = (ntiles + 1) >> 1;
+  const int rounds = (tile_pairs + npairs - 1) / npairs;
+  const int NL = P.num_layers;
+  const int nchunks = P.ff / kFFChunk;
+  auto tile_of = [&](int ti) { return ((ti * npairs + pair) << 1) + (int)rank; };
+  auto slot_ptr = [&](int s) -> uint8_t* {
+    return s < C::kSlotsA ? smem + C::kOffRing + s * C::kSlotBytes : smem + C::kOffTail + (s - C::kSlotsA) * C::kSlotBytes;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::kSlotsF; ++i) { mbar_init(&full[i], leader ? 2 : 1); mbar_init(&empty[i], 1); }
+    mbar_init(a_ready, 16);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_free, 16);
+    mbar_init(att_ready, 16);
+    mbar_init(s_free, 1);
+    mbar_init(tail_free, 1);
+    mbar_init(h_full, 1);
+    mbar_init(h_free, 16);
+    mbar_init(&hs_full[0], 16);
+    mbar_init(&hs_full[1], 16);
+    mbar_init(&hs_free[0], 1);
+    mbar_init(&hs_free[1], 1);
+    mbar_init(y_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_holder, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp < 4) {
+    setmaxnreg_dec<56>();   // 128 x (168 - 56) registers released == 256 x (224 - 168) acquired by the workers
+    if (warp == 0) {
+      // ------------------------------------------------------------------ producer (both CTAs, own halves)
+      if (lane == 0) {
+        uint32_t par = 0;   // bit s: parity of the number of stages pushed into slot s
+        auto push = [&](int s, const uint8_t* src, uint32_t bytes) {
+          SW(&empty[s], ((par >> s) & 1) ^ 1, 701);
+          mbar_arrive_expect_tx(&full[s], bytes);
+          bulk_g2s(slot_ptr(s), src, bytes, &full[s]);
+          par ^= 1u << s;
+        };
+        uint32_t li = 0;
+        for (int ti = 0; ti < rounds; ++ti) {
+          for (int n = 0; n < NL; ++n, ++li) {
+            int sa = 0;
+            for (int h = 0; h < kHeads; ++h) {
+              const uint8_t* wq = P.wq3[n] + (size_t)(h * 2 + rank) * 3 * C::kQkvBlockBytes;
+              for (int m = 0; m < 3; ++m)
+                for (int s = 0; s < C::kQkvStages; ++s) {
+                  push(sa, wq + (size_t)m * C::kQkvBlockBytes + s * C::kSlotBytes, C::kSlotBytes);
+                  sa = sa + 1 == C::kSlotsA ? 0 : sa + 1;
+                }
+              const uint8_t* wo = P.wo2[n] + ((size_t)rank * kHeads + h) * C::kWoStages * C::kSlotBytes;
+              for (int s = 0; s < C::kWoStages; ++s) {
+                push(sa, wo + s * C::kSlotBytes, C::kSlotBytes);
+                sa = sa + 1 == C::kSlotsA ? 0 : sa + 1;
+              }
+            }
+            int sf = 0;
+            bool tail_ok = false;
+            auto pushf = [&](const uint8_t* src, uint32_t bytes) {
+              if (sf >= C::kSlotsA && !tail_ok) { SW(tail_free, li & 1, 802); tail_ok = true; }
+              push(sf, src, bytes);
+              sf = sf + 1 == C::kSlotsF ? 0 : sf + 1;
+            };
+            auto half = [&](int c) { return P.wffn2[n] + ((size_t)c * 2 + rank) * C::kHalfChunkBytes; };
+            auto push_w1 = [&](int c) {
+              for (int s = 0; s < C::kW1Stages; ++s)
+                pushf(half(c) + s * (C::kW1StageK * C::kW1StepBytes), C::kW1StageK * C::kW1StepBytes);
+            };
+            auto push_w2 = [&](int c) {
+              const uint8_t* src = half(c) + (kDP / 16) * C::kW1StepBytes;
+              for (int s = 0; s < C::kW2Stages; ++s)
+                pushf(src + s * (C::kW2StageK * C::kWoStepBytes), C::kW2StageK * C::kWoStepBytes);
+            };
+            push_w1(0);
+            for (int c = 0; c < nchunks; ++c) {
+              if (c + 1 < nchunks) push_w1(c + 1);
+              push_w2(c);
+            }
+          }
+        }
+      }
+    } else if (warp == 1 || warp == 2) {
+      if (lane == 0) {
+        if (leader) {
+          // ---------------------------------------------------------------- UMMA issuers (leader only)
+          // warp 1: q/k/v blocks, out-projections and every GEMM1; warp 2: every GEMM2 (the two share the tensor
+          // pipe; causality between them runs through the workers: hs_full follows h_full follows GEMM1).
+          constexpr uint32_t idesc_h = make_idesc_bf16(2 * kTileM, kFFChunk);
+          constexpr uint32_t idesc_y = make_idesc_bf16(2 * kTileM, kNC);
+          constexpr uint16_t kBoth = 3;
+          const uint32_t a_addr = smem_u32(sA);
+          const uint32_t s_addr = smem_u32(sS);
+          uint32_t cpar = 0;   // bit s: parity of the number of stages consumed from slot s (by either issuer)
+          auto use = [&](int s) -> uint32_t {
+            SWC(&full[s], (cpar >> s) & 1, 103);
+            tc_fence_after();
+            return smem_u32(slot_ptr(s));
+          };
+          auto release = [&](int s) {
+            umma_commit_pair(&empty[s], kBoth);
+            cpar ^= 1u << s;
+          };
+          uint32_t nn0 = 0;
+          if (warp == 1) {
+            uint32_t kblk = 0, katt = 0, kar = 0;
+            for (int ti = 0; ti < rounds; ++ti) {
+              for (int n = 0; n < NL; ++n) {
+                SWC(a_ready, kar & 1, 204); ++kar;
+                tc_fence_after();
+                int sa = 0;
+                for (int h = 0; h < kHeads; ++h) {
+                  for (int m = 0; m < 3; ++m) {
+                    SWC(acc_free, (kblk & 1) ^ 1, 305); ++kblk;
+                    tc_fence_after();
+                    for (int s = 0; s < C::kQkvStages; ++s) {
+                      const uint32_t sb = use(sa);
+#pragma unroll
+                      for (int kk = 0; kk < C::kQkvStageK; ++kk) {
+                        const int kstep = s * C::kQkvStageK + kk;
+                        const uint64_t adesc = make_kc16_desc(a_addr + kstep * 4096, kTileM * 16, 128);
+                        const uint64_t bdesc = make_kc16_desc(sb + kk * C::kQkvStepBytes, (kDHP / 2) * 16, 128);
+                        umma_bf16_ss_pair(tmem_base + C::kTmemAcc, adesc, bdesc, idesc_y, kstep != 0);
+                      }
+                      release(sa);
+                      sa = sa + 1 == C::kSlotsA ? 0 : sa + 1;
+                    }
+                    umma_commit_pair(acc_full, kBoth);
+                  }
+                  // Y += att_h * Wo_h^T
+                  SWC(att_ready, katt & 1, 406); ++katt;
+                  tc_fence_after();
+                  for (int s = 0; s < C::kWoStages; ++s) {
+                    const uint32_t sb = use(sa);
+#pragma unroll
+                    for (int kk = 0; kk < C::kWoStageK; ++kk) {
+                      const int kstep = s * C::kWoStageK + kk;
+                      const uint64_t adesc = make_kc16_desc(s_addr + kstep * 4096, kTileM * 16, 128);
+#pragma unroll
+                      for (int j = 0; j < 2; ++j) {
+                        const uint64_t bdesc = make_kc16_desc(sb + kk * C::kWoStepBytes + j * (kNC / 2) * 16, (kDP / 2) * 16, 128);
+                        umma_bf16_ss_pair(tmem_base + C::kTmemY + j * kNC, adesc, bdesc, idesc_y, true);
+                      }
+                    }
+                    release(sa);
+                    sa = sa + 1 == C::kSlotsA ? 0 : sa + 1;
+                  }
+                  umma_commit_pair(s_free, kBoth);
+                  if (h == kHeads - 1) umma_commit_pair(tail_free, kBoth);
+                }
+                // ---- FFN: GEMM1 of every chunk
+                SWC(a_ready, kar & 1, 207); ++kar;
+                tc_fence_after();
+                int sf = 0;
+                auto gemm1 = [&](uint32_t nn) {
+                  SWC(h_free, (nn & 1) ^ 1, 508);
+                  tc_fence_after();
+                  for (int s = 0; s < C::kW1Stages; ++s) {
+                    const uint32_t sb = use(sf);
+#pragma unroll
+                    for (int kk = 0; kk < C::kW1StageK; ++kk) {
+                      const int kstep = s * C::kW1StageK + kk;
+                      const uint64_t adesc = make_kc16_desc(a_addr + kstep * 4096, kTileM * 16, 128);
+                      const uint64_t bdesc = make_kc16_desc(sb + kk * C::kW1StepBytes, (kFFChunk / 2) * 16, 128);
+                      umma_bf16_ss_pair(tmem_base + C::kTmemH, adesc, bdesc, idesc_h, kstep != 0);
+                    }
+                    release(sf);
+                    sf = sf + 1 == C::kSlotsF ? 0 : sf + 1;
+                  }
+                  umma_commit_pair(h_full, kBoth);
+                };
+                auto skipf = [&](int count) {
+                  for (int s = 0; s < count; ++s) { cpar ^= 1u << sf; sf = sf + 1 == C::kSlotsF ? 0 : sf + 1; }
+                };
+                gemm1(nn0);
+                for (int c = 0; c < nchunks; ++c) {
+                  if (c + 1 < nchunks) gemm1(nn0 + c + 1);
+                  skipf(C::kW2Stages);
+                }
+                nn0 += nchunks;
+              }
+            }
+          } else {
+            for (int ti = 0; ti < rounds; ++ti) {
+              for (int n = 0; n < NL; ++n) {
+                // the attention part uses each of slots 0..2 an even number of times: parities unchanged
+                int sf = 0;
+                auto skipf = [&](int count) {
+                  for (int s = 0; s < count; ++s) { cpar ^= 1u << sf; sf = sf + 1 == C::kSlotsF ? 0 : sf + 1; }
+                };
+                skipf(C::kW1Stages);
+                for (int c = 0; c < nchunks; ++c) {
+                  if (c + 1 < nchunks) skipf(C::kW1Stages);
+                  const uint32_t nn = nn0 + c, b = nn & 1;
+                  SWC(&hs_full[b], (nn >> 1) & 1, 609);
+                  tc_fence_after();
+                  const uint32_t h_addr = s_addr + b * C::kHBytes;
+                  for (int s = 0; s < C::kW2Stages; ++s) {
+                    const uint32_t sb = use(sf);
+#pragma unroll
+                    for (int kk = 0; kk < C::kW2StageK; ++kk) {
+                      const int kstep = s * C::kW2StageK + kk;
+                      const uint64_t adesc = make_kc16_desc(h_addr + kstep * 4096, kTileM * 16, 128);
+#pragma unroll
+                      for (int j = 0; j < 2; ++j) {
+                        const uint64_t bdesc = make_kc16_desc(sb + kk * C::kWoStepBytes + j * (kNC / 2) * 16, (kDP / 2) * 16, 128);
+                        umma_bf16_ss_pair(tmem_base + C::kTmemY + j * kNC, adesc, bdesc, idesc_y, true);
+                      }
+                    }
+                    release(sf);
+                    sf = sf + 1 == C::kSlotsF ? 0 : sf + 1;
+                  }
+                  umma_commit_pair(&hs_free[b], kBoth);
+                }
+                umma_commit_pair(y_full, kBoth);
+                nn0 += nchunks;
+              }
+            }
+          }
+        } else if (warp == 1) {
+          // ---------------------------------------------------------------- relay (peer): forward "my half of
+          // this stage has landed" to the leader's barrier, in consumption order
+          uint32_t cpar = 0;
+          auto relay = [&](int s) {
+            SW(&full[s], (cpar >> s) & 1, 110);
+            mbar_arrive_cluster(&full[s], 0);
+            cpar ^= 1u << s;
+          };
+          for (int ti = 0; ti < rounds; ++ti)
+            for (int n = 0; n < NL; ++n) {
+              int sa = 0;
+              for (int i = 0; i < kHeads * (3 * C::kQkvStages + C::kWoStages); ++i) { relay(sa); sa = sa + 1 == C::kSlotsA ? 0 : sa + 1; }
+              int sf = 0;
+              const int nf = C::kW1Stages * nchunks + C::kW2Stages * nchunks;
+              for (int i = 0; i < nf; ++i) { relay(sf); sf = sf + 1 == C::kSlotsF ? 0 : sf + 1; }
+            }
+        }
+      }
+    } else {
+      // warp 3: pull the next tile's residual image into L2 (it is read once per tile, by the workers' init pass)
+      for (int ti = 0; ti + 1 < rounds; ++ti) {
+        const int tile = min(tile_of(ti + 1), ntiles - 1);
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(xg + (size_t)tile * x_image_elems());
+        for (int ln = lane; ln < (int)(x_image_elems() * 4 / 128); ln += 32)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)ln * 128));
+        // pace: one tile ahead -- wait for the last layer of this round's tile to finish
+        for (int n = 0; n < NL; ++n) SW(y_full, (uint32_t)(ti * NL + n) & 1, 911);
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- workers (8 warps, both CTAs)
+    setmaxnreg_inc<224>();
+    const int ew = warp - 4;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                  // token row (TMEM lane) of this thread
+    const int halfsel = ew >> 2;                  // which half of the columns this thread handles in row passes
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int g = lane >> 2, t = lane & 3;
+    const int band = win;
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr int kS = C::kStride;
+    constexpr int kChunkElems = kTileM * 8;
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(sS);
+    __nv_bfloat16* sK = sQ + kTileM * kS;
+    __nv_bfloat16* sV = sK + kTileM * kS;
+    float4* sStat = reinterpret_cast<float4*>(sS);   // [2][128] LayerNorm partial statistics
+    const int cb0 = halfsel * 9;                  // this thread's 9 column blocks (of 16) of Y
+    auto arrive_leader = [&](uint64_t* bar) {     // one arrive per warp on the leader's barrier
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(bar); else mbar_arrive_cluster(bar, 0);
+      }
+    };
+
+    // Row pass: Y (+= bias, written back) -> [LayerNorm] -> bf16 operand tile sA.  Two threads per row.
+    auto row_pass = [&](const float* __restrict__ bias, const float* __restrict__ lg, const float* __restrict__ lb) {
+      float mean = 0.f, rstd = 1.f;
+      if (lg) {
+        float s1 = 0.f, s2 = 0.f, shift = 0.f;
+#pragma unroll 1
+        for (int cb = 0; cb < 9; ++cb) {
+          uint32_t acc[16];
+          tmem_ld16(tmem_row + C::kTmemY + (cb0 + cb) * 16, acc);
+          tmem_ld_wait();
+          if (bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __ldg(bias + (cb0 + cb) * 16 + i));
+            tmem_st16(tmem_row + C::kTmemY + (cb0 + cb) * 16, acc);
+          }
+          if (cb == 0) shift = __uint_as_float(acc[0]);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float dlt = ((cb0 + cb) * 16 + i < kD) ? __uint_as_float(acc[i]) - shift : 0.f;
+            s1 += dlt;
+            s2 += dlt * dlt;
+          }
+        }
+        if (bias) tmem_st_wait();
+        sStat[halfsel * kTileM + r] = make_float4(shift, s1, s2, 0.f);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float4 o = sStat[(1 - halfsel) * kTileM + r];
+        const float n_me = halfsel ? (float)(kD - 144) : 144.f, n_o = halfsel ? 144.f : (float)(kD - 144);
+        mean = (n_me * shift + s1 + n_o * o.x + o.y) * (1.f / kD);
+        const float d_me = mean - shift, d_o = mean - o.x;
+        const float ss = (s2 - 2.f * d_me * s1 + n_me * d_me * d_me) + (o.z - 2.f * d_o * o.y + n_o * d_o * d_o);
+        rstd = rsqrtf(fmaxf(ss * (1.f / kD), 0.f) + 1e-6f);
+      }
+      uint4* arow = reinterpret_cast<uint4*>(sA) + r;
+      const bool add_here = bias && !lg;
+#pragma unroll 1
+      for (int cb = 0; cb < 9; ++cb) {
+        uint32_t acc[16];
+        tmem_ld16(tmem_row + C::kTmemY + (cb0 + cb) * 16, acc);
+        tmem_ld_wait();
+        if (add_here) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __ldg(bias + (cb0 + cb) * 16 + i));
+          tmem_st16(tmem_row + C::kTmemY + (cb0 + cb) * 16, acc);
+        }
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int col = (cb0 + cb) * 16 + i;
+          float x = __uint_as_float(acc[i]);
+          if (lg) x = (x - mean) * rstd * __ldg(lg + col) + __ldg(lb + col);
+          v[i] = col < kD ? x : 0.f;
+        }
+        arow[(size_t)((cb0 + cb) * 2) * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                             pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        arow[(size_t)((cb0 + cb) * 2 + 1) * kTileM] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                                                                 pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+      }
+      if (add_here) tmem_st_wait();
+      tc_fence_before();
+      fence_proxy_async_smem();
+      arrive_leader(a_ready);
+    };
+
+    uint32_t k_acc = 0, k_sfree = 0, k_y = 0, nchunk = 0;
+    for (int ti = 0; ti < rounds; ++ti) {
+      const int tile_raw = tile_of(ti);
+      const bool valid = tile_raw < ntiles;
+      const int tile = min(tile_raw, ntiles - 1);
+      float4* xrow = reinterpret_cast<float4*>(xg + (size_t)tile * x_image_elems()) + r;
+      // ---- Y <- x (this thread's half row)
+#pragma unroll 3
+      for (int cb = 0; cb < 9; ++cb) {
+        uint32_t v[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 x4 = xrow[(size_t)((cb0 + cb) * 4 + i) * kTileM];
+          v[4 * i + 0] = __float_as_uint(x4.x); v[4 * i + 1] = __float_as_uint(x4.y);
+          v[4 * i + 2] = __float_as_uint(x4.z); v[4 * i + 3] = __float_as_uint(x4.w);
+        }
+        tmem_st16(tmem_row + C::kTmemY + (cb0 + cb) * 16, v);
+      }
+      tmem_st_wait();
+
+      for (int n = 0; n < NL; ++n) {
+        // ---- P1: operand tile of the attention sub-layer (+ b2 of the previous layer's FFN)
+        if (n > 0) {
+          SW(y_full, k_y & 1, 912); ++k_y;
+          tc_fence_after();
+        }
+        row_pass(n > 0 ? P.b2[n - 1] : nullptr, P.ln_g0[n], P.ln_b0[n]);
+
+        for (int h = 0; h < kHeads; ++h) {
+          if (h > 0) { SW(s_free, k_sfree & 1, 1013); ++k_sfree; }   // att_{h-1} consumed by its out-projection
+          // ---- q, k, v blocks: TMEM -> bf16 -> padded shared-memory rows
+          for (int m = 0; m < 3; ++m) {
+            SW(acc_full, k_acc & 1, 1114); ++k_acc;
+            tc_fence_after();
+            const int b0 = halfsel ? 5 : 0, nb = halfsel ? 4 : 5;
+            uint32_t acc[5][16];
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+              if (j < nb) tmem_ld16(tmem_row + C::kTmemAcc + (b0 + j) * 16, acc[j]);
+            tmem_ld_wait();
+            tc_fence_before();
+            arrive_leader(acc_free);
+            __nv_bfloat16* dst = sQ + (size_t)m * kTileM * kS + (size_t)r * kS;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              if (j < nb) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[j][i]);
+                *reinterpret_cast<uint4*>(dst + (2 * (b0 + j)) * 8) =
+                    make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                *reinterpret_cast<uint4*>(dst + (2 * (b0 + j) + 1) * 8) =
+                    make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+              }
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+
+          // ---- banded attention of query block `ew` (rows 16*ew .. +15), two-pass softmax (win <= 16)
+          {
+            const int i0 = ew * 16;
+            const int r0 = i0 + g, r1 = r0 + 8;
+            const __nv_bfloat16* q0 = sQ + (size_t)r0 * kS + 2 * t;
+            const __nv_bfloat16* q1 = sQ + (size_t)r1 * kS + 2 * t;
+            uint32_t qa[kDHP / 16][4];
+#pragma unroll
+            for (int ks = 0; ks < kDHP / 16; ++ks) {
+              qa[ks][0] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16);
+              qa[ks][1] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16);
+              qa[ks][2] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + 8);
+              qa[ks][3] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + 8);
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");   // every warp holds its q fragments: the q area may be overwritten
+            float o[kDHP / 8][4];
+#pragma unroll
+            for (int nt = 0; nt < kDHP / 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+            float l0 = 0.f, l1 = 0.f;
+            int jlo = i0 - band; if (jlo < 0) jlo = 0; jlo &= ~15;
+            int jhi = i0 + 15 + band + 1; if (jhi > L) jhi = L;
+            const int nkt = (jhi - jlo + 15) >> 4;
+            constexpr int kMaxKT = 3;
+            float sc[kMaxKT][2][4];
+#pragma unroll
+            for (int kt = 0; kt < kMaxKT; ++kt)
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) sc[kt][nt][0] = sc[kt][nt][1] = sc[kt][nt][2] = sc[kt][nt][3] = 0.f;
+#pragma unroll
+            for (int kt = 0; kt < kMaxKT; ++kt) {
+              if (kt < nkt) {
+                const int krow0 = jlo + kt * 16 + g, krow1 = krow0 + 8;
+                const __nv_bfloat16* kr0 = sK + (size_t)krow0 * kS + 2 * t;
+                const __nv_bfloat16* kr1 = sK + (size_t)krow1 * kS + 2 * t;
+#pragma unroll
+                for (int ks = 0; ks < kDHP / 16; ++ks) {
+                  const uint32_t a0 = *reinterpret_cast<const uint32_t*>(kr0 + ks * 16);
+                  const uint32_t a1 = *reinterpret_cast<const uint32_t*>(kr0 + ks * 16 + 8);
+                  const uint32_t c0 = *reinterpret_cast<const uint32_t*>(kr1 + ks * 16);
+                  const uint32_t c1 = *reinterpret_cast<const uint32_t*>(kr1 + ks * 16 + 8);
+                  mma_bf16_16816(sc[kt][0], qa[ks], a0, a1);
+                  mma_bf16_16816(sc[kt][1], qa[ks], c0, c1);
+                }
+              }
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int kt = 0; kt < kMaxKT; ++kt)
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int i = (e < 2) ? r0 : r1;
+                  const int j = jlo + kt * 16 + nt * 8 + 2 * t + (e & 1);
+                  const int dlt = i - j;
+                  const bool ok = (kt < nkt) && (j < L) && (dlt <= band) && (dlt >= -band);
+                  const float v = ok ? sc[kt][nt][e] : -INFINITY;
+                  sc[kt][nt][e] = v;
+                  if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+                }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float base0 = mx0 == -INFINITY ? 0.f : mx0 * kLog2e, base1 = mx1 == -INFINITY ? 0.f : mx1 * kLog2e;
+            uint32_t pa[kMaxKT][4];
+#pragma unroll
+            for (int kt = 0; kt < kMaxKT; ++kt) {
+              float p[2][4];
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) {
+                p[nt][0] = exp2f(fmaf(sc[kt][nt][0], kLog2e, -base0));
+                p[nt][1] = exp2f(fmaf(sc[kt][nt][1], kLog2e, -base0));
+                p[nt][2] = exp2f(fmaf(sc[kt][nt][2], kLog2e, -base1));
+                p[nt][3] = exp2f(fmaf(sc[kt][nt][3], kLog2e, -base1));
+                l0 += p[nt][0] + p[nt][1];
+                l1 += p[nt][2] + p[nt][3];
+              }
+              pa[kt][0] = pack_bf16x2(p[0][0], p[0][1]);
+              pa[kt][1] = pack_bf16x2(p[0][2], p[0][3]);
+              pa[kt][2] = pack_bf16x2(p[1][0], p[1][1]);
+              pa[kt][3] = pack_bf16x2(p[1][2], p[1][3]);
+            }
+#pragma unroll
+            for (int kt = 0; kt < kMaxKT; ++kt) {
+              if (kt < nkt) {
+                const int vrow = jlo + kt * 16 + (lane & 15);
+                const uint32_t vbase = smem_u32(sV + (size_t)vrow * kS);
+#pragma unroll
+                for (int nt = 0; nt < kDHP / 8; ++nt) {
+                  uint32_t b0, b1;
+                  ldmatrix_x2_trans(b0, b1, vbase + nt * 16);
+                  mma_bf16_16816(o[nt], pa[kt], b0, b1);
+                }
+              }
+            }
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+            // rows beyond the window (layout padding) contribute nothing to the out-projection
+            const float inv0 = r0 < L ? 1.f / l0 : 0.f, inv1 = r1 < L ? 1.f / l1 : 0.f;
+            // att_h as a KC16 operand tile [18 chunks][128 rows][8] over the (consumed) q area
+            __nv_bfloat16* obase = sQ + 2 * t;
+#pragma unroll
+            for (int nt = 0; nt < kDHP / 8; ++nt) {
+              *reinterpret_cast<uint32_t*>(obase + (size_t)nt * kChunkElems + r0 * 8) = pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
+              *reinterpret_cast<uint32_t*>(obase + (size_t)nt * kChunkElems + r1 * 8) = pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
+            }
+          }
+          fence_proxy_async_smem();
+          arrive_leader(att_ready);
+        }
+        SW(s_free, k_sfree & 1, 1015); ++k_sfree;   // out-projection of the last head done: Y = x_mid
+        tc_fence_after();
+
+        // ---- P5: operand tile of the FFN
+        row_pass(nullptr, P.ln_g1[n], P.ln_b1[n]);
+
+        // ---- hidden-chunk epilogue: H (+b1, ReLU) -> bf16 -> shared memory operand of GEMM2
+        const float* __restrict__ b1 = P.b1[n];
+        for (int c = 0; c < nchunks; ++c, ++nchunk) {
+          const uint32_t b = nchunk & 1;
+          SW(h_full, nchunk & 1, 1216);
+          tc_fence_after();
+          SW(&hs_free[b], ((nchunk >> 1) & 1) ^ 1, 1317);
+          uint4* hrow = reinterpret_cast<uint4*>(sS + b * C::kHBytes) + r;
+          const float* bias = b1 + c * kFFChunk + halfsel * (kFFChunk / 2);
+          uint32_t acc[kFFChunk / 32][16];
+#pragma unroll
+          for (int cc = 0; cc < kFFChunk / 32; ++cc)
+            tmem_ld16(tmem_row + C::kTmemH + (halfsel * (kFFChunk / 32) + cc) * 16, acc[cc]);
+          tmem_ld_wait();
+          tc_fence_before();
+          arrive_leader(h_free);
+#pragma unroll
+          for (int cc = 0; cc < kFFChunk / 32; ++cc) {
+            const int cb = halfsel * (kFFChunk / 32) + cc;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(acc[cc][i]) + __ldg(bias + cc * 16 + i), 0.f);
+            hrow[(size_t)(cb * 2) * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                         pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            hrow[(size_t)(cb * 2 + 1) * kTileM] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                                                             pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+          }
+          fence_proxy_async_smem();
+          arrive_leader(&hs_full[b]);
+        }
+      }
+
+      // ---- after the last layer: x <- Y + b2 (global, for the head kernel)
+      SW(y_full, k_y & 1, 918); ++k_y;
+      tc_fence_after();
+      {
+        const float* __restrict__ b2 = P.b2[NL - 1];
+#pragma unroll 3
+        for (int cb = 0; cb < 9; ++cb) {
+          uint32_t acc[16];
+          tmem_ld16(tmem_row + C::kTmemY + (cb0 + cb) * 16, acc);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int col = (cb0 + cb) * 16 + 4 * i;
+              float4 o4;
+              o4.x = col + 0 < kD ? __uint_as_float(acc[4 * i + 0]) + __ldg(b2 + col + 0) : 0.f;
+              o4.y = col + 1 < kD ? __uint_as_float(acc[4 * i + 1]) + __ldg(b2 + col + 1) : 0.f;
+              o4.z = col + 2 < kD ? __uint_as_float(acc[4 * i + 2]) + __ldg(b2 + col + 2) : 0.f;
+              o4.w = col + 3 < kD ? __uint_as_float(acc[4 * i + 3]) + __ldg(b2 + col + 3) : 0.f;
+              xrow[(size_t)((cb0 + cb) * 4 + i) * kTileM] = o4;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, C::kTmemCols);
+  }
+}

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from typing import Dict, Optional, Tuple
+from typing import Any, Dict, Optional, Tuple
 
 import numpy as np
 
@@ -23,7 +23,9 @@ from deepconsensus_b200 import calibration as calibration_lib
 from deepconsensus_b200 import params as params_lib
 from deepconsensus_b200 import weights as weights_lib
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libdcb200.so")
+# DCB200_LIB: developer override to load an experiment build of the same library (never a different implementation)
+_LIB_PATH = os.environ.get("DCB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc",
+                                                         "libdcb200.so")
 _lib = None
 
 DCB_ROWS_ON_DEVICE = 1
@@ -65,7 +67,7 @@ class DcbTensor(ctypes.Structure):
 
 # Every symbol include/dcb200.h declares; tests check the built library exports all of them.
 ABI_SYMBOLS = (
-    "dcb_create", "dcb_load_weights", "dcb_forward", "dcb_last_forward_ms",
+    "dcb_create", "dcb_load_weights", "dcb_forward", "dcb_submit", "dcb_wait", "dcb_last_forward_ms",
     "dcb_last_forward_launches", "dcb_set_profile", "dcb_get_profile", "dcb_get_profile_kernels", "dcb_set_debug", "dcb_debug_residual", "dcb_debug_trace", "dcb_alloc_host",
     "dcb_free_host", "dcb_alloc_device", "dcb_free_device", "dcb_memcpy_h2d", "dcb_memcpy_d2h",
     "dcb_synchronize", "dcb_last_error", "dcb_version", "dcb_destroy",
@@ -90,6 +92,8 @@ def load_library() -> ctypes.CDLL:
   lib.dcb_create.argtypes = [ctypes.POINTER(DcbConfig), ctypes.POINTER(vp)]
   lib.dcb_load_weights.argtypes = [vp, ctypes.POINTER(DcbTensor), i32]
   lib.dcb_forward.argtypes = [vp, vp, i32, u32, vp, vp, vp, vp]
+  lib.dcb_submit.argtypes = [vp, vp, i32, u32, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int64)]
+  lib.dcb_wait.argtypes = [vp, ctypes.c_int64]
   lib.dcb_last_forward_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
   lib.dcb_last_forward_launches.argtypes = [vp, ctypes.POINTER(i32)]
   lib.dcb_set_debug.argtypes = [vp, i32]
@@ -184,6 +188,10 @@ class B200Model:
     if getattr(self, "_handle", None) and self._handle.value:
       self._lib.dcb_destroy(self._handle)
       self._handle = ctypes.c_void_p()
+      for st in getattr(self, "_stage", {}).values():
+        for addr in st["addrs"]:
+          free_pinned(addr)
+      self._stage = {}
 
   def __del__(self):
     try:
@@ -248,6 +256,97 @@ class B200Model:
     self.last_ms, self.last_launches = ms, launches
     return out
 
+  # -- the hot path, pipelined over a stream of batches ----------------------------------------
+  # dcb_submit / dcb_wait: the host->device copy of batch i+1 overlaps the kernels of batch i.  Page-locked staging
+  # (two sets, allocated on first use) is owned here so that callers can stack their windows straight into it.
+  def staging_rows(self, slot: int) -> np.ndarray:
+    """Pinned float32 [max_batch, R, L] buffer of pipeline slot 0/1 (fill [:batch], then submit(slot=...))."""
+    st = self._staging(slot)
+    return st["rows"]
+
+  def _staging(self, slot: int) -> Dict[str, Any]:
+    if not hasattr(self, "_stage"):
+      self._stage = {}
+    if slot not in self._stage:
+      mb, R, L = self.max_batch, self.total_rows, self.max_length
+      def pinned(shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        addr, raw = alloc_pinned(max(n, 1))
+        return addr, raw[:n].view(dtype).reshape(shape)
+      st = {"addrs": []}
+      for key, shape, dt in (("rows", (mb, R, L), np.float32), ("bases", (mb, L), np.uint8),
+                             ("quals", (mb, L), np.uint8)):
+        addr, st[key] = pinned(shape, dt)
+        st["addrs"].append(addr)
+      self._stage[slot] = st
+    return self._stage[slot]
+
+  def _staging_opt(self, slot: int, key: str) -> np.ndarray:
+    st = self._staging(slot)
+    if key not in st:
+      n = self.max_batch * self.max_length * 5 * 4
+      addr, raw = alloc_pinned(n)
+      st[key] = raw.view(np.float32).reshape(self.max_batch, self.max_length, 5)
+      st["addrs"].append(addr)
+    return st[key]
+
+  def submit(self, rows: Optional[np.ndarray] = None, batch: Optional[int] = None, slot: Optional[int] = None,
+             want_probs: bool = False, want_logits: bool = False) -> Dict[str, Any]:
+    """Enqueue one batch (<= max_batch windows) and return a handle for wait().  Either pass `rows` (copied into the
+    slot's pinned staging) or fill staging_rows(slot)[:batch] yourself and pass `batch`.  At most two handles may be
+    outstanding and they must be waited for in submission order."""
+    busy = self.__dict__.setdefault("_slot_busy", {0: False, 1: False})
+    if slot is None:
+      slot = 1 - getattr(self, "_last_slot", 1)
+    if busy[slot]:   # its pinned staging may still be read by the copy engine: refuse before touching it
+      raise DcbError(-4, "two submissions in flight: wait() for the oldest first")
+    self._last_slot = slot
+    st = self._staging(slot)
+    if rows is not None:
+      rows = self._rows3(rows)
+      batch = rows.shape[0]
+      if batch > self.max_batch:
+        raise ValueError("submit(): batch %d > max_batch %d" % (batch, self.max_batch))
+      st["rows"][:batch] = rows
+    elif batch is None:
+      raise ValueError("submit(): rows or batch required")
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    probs = self._staging_opt(slot, "probs") if want_probs else None
+    logits = self._staging_opt(slot, "logits") if want_logits else None
+    ticket = ctypes.c_int64(-1)
+    self._check(self._lib.dcb_submit(self._handle, vp(st["rows"]), batch, 0, vp(st["bases"]), vp(st["quals"]),
+                                     vp(probs) if want_probs else None, vp(logits) if want_logits else None,
+                                     ctypes.byref(ticket)))
+    busy[slot] = True
+    return dict(ticket=int(ticket.value), slot=slot, batch=batch, probs=want_probs, logits=want_logits)
+
+  def wait(self, handle: Dict[str, Any], strict_input: bool = True) -> Dict[str, np.ndarray]:
+    """Block until the submission's results are on the host; returns the same dict as forward()."""
+    rc = self._lib.dcb_wait(self._handle, handle["ticket"])
+    if rc != -4:   # anything but "not in flight" retires the slot
+      self._slot_busy[handle["slot"]] = False
+    self._check(rc, tolerate=() if strict_input else (-5,))
+    st, b = self._stage[handle["slot"]], handle["batch"]
+    out = dict(bases=st["bases"][:b].copy(), quals=st["quals"][:b].copy())
+    if handle["probs"]:
+      out["probs"] = st["probs"][:b].copy()
+    if handle["logits"]:
+      out["logits"] = st["logits"][:b].copy()
+    self.last_ms, self.last_launches = self.last_forward_ms(), self.last_forward_launches()
+    return out
+
+  def forward_batches(self, batches, want_probs: bool = False, want_logits: bool = False,
+                      strict_input: bool = True):
+    """Pipelined forward over an iterable of row batches; yields one output dict per batch, in order."""
+    pending = None
+    for rows in batches:
+      h = self.submit(rows, want_probs=want_probs, want_logits=want_logits)
+      if pending is not None:
+        yield self.wait(pending, strict_input)
+      pending = h
+    if pending is not None:
+      yield self.wait(pending, strict_input)
+
   def predict(self, rows: np.ndarray) -> _Prediction:
     """Softmax output [B, L, 5], shaped like `EncoderOnlyTransformer.predict` (networks.py:357-365)."""
     return _Prediction(self.forward(rows, want_probs=True)["probs"])
@@ -303,6 +402,19 @@ class B200Model:
   def memcpy_d2h(self, dst: np.ndarray, src: int) -> None:
     self._check(self._lib.dcb_memcpy_d2h(self._handle, dst.ctypes.data_as(ctypes.c_void_p),
                                          ctypes.c_void_p(src), dst.nbytes))
+
+  def submit_raw(self, rows_ptr: int, batch: int, flags: int, bases_ptr: int, quals_ptr: int,
+                 probs_ptr: int = 0, logits_ptr: int = 0) -> int:
+    """dcb_submit on caller-managed pointers; returns the ticket for wait_raw()."""
+    ticket = ctypes.c_int64(-1)
+    self._check(self._lib.dcb_submit(self._handle, ctypes.c_void_p(rows_ptr), batch, flags,
+                                     ctypes.c_void_p(bases_ptr), ctypes.c_void_p(quals_ptr),
+                                     ctypes.c_void_p(probs_ptr) if probs_ptr else None,
+                                     ctypes.c_void_p(logits_ptr) if logits_ptr else None, ctypes.byref(ticket)))
+    return int(ticket.value)
+
+  def wait_raw(self, ticket: int) -> None:
+    self._check(self._lib.dcb_wait(self._handle, ticket))
 
   def forward_raw(self, rows_ptr: int, batch: int, flags: int, bases_ptr: int, quals_ptr: int,
                   probs_ptr: int = 0, logits_ptr: int = 0) -> None:

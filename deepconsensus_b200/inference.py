@@ -86,8 +86,8 @@ def run_model_on_examples(feature_dicts: List[Dict[str, Any]], model: engine_lib
                           options: InferenceOptions) -> List[stitch_utils.DCModelOutput]:
   """Runs the model over windows and returns one DCModelOutput per window (quick_inference.py:341-415)."""
   predictions: List[stitch_utils.DCModelOutput] = []
-  for data in batch_examples(feature_dicts, model_params, options):
-    out = model.forward(data["rows"])
+
+  def collect(data, out):
     bases, quals = out["bases"], out["quals"]
     for i in range(bases.shape[0]):
       predictions.append(stitch_utils.DCModelOutput(
@@ -95,6 +95,16 @@ def run_model_on_examples(feature_dicts: List[Dict[str, Any]], model: engine_lib
           np_num_passes=data["np_num_passes"][i], rq=data["rq"][i], rg=data["rg"][i],
           sequence=bases[i].tobytes().decode("ascii"),
           quality_string=quals[i].tobytes().decode("ascii")))
+
+  # Two batches in flight: while the device scores batch i, batch i+1 is stacked and copied (dcb_submit / dcb_wait).
+  pending = None
+  for data in batch_examples(feature_dicts, model_params, options):
+    handle = model.submit(data["rows"])
+    if pending is not None:
+      collect(pending[0], model.wait(pending[1]))
+    pending = (data, handle)
+  if pending is not None:
+    collect(pending[0], model.wait(pending[1]))
   return predictions
 
 

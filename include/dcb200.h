@@ -98,6 +98,17 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n);
 int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
                 uint8_t* bases_out, uint8_t* quals_out, float* probs_out, float* logits_out);
 
+/* Pipelined form of dcb_forward for a stream of batches (the `for batch in batches: model.predict(batch)` loop of
+ * quick_inference.py:352-368): dcb_submit enqueues the host->device copy of `rows` on a copy stream, the kernels and
+ * the device->host copy of the results, and returns a ticket without waiting; dcb_wait(ticket) blocks until that
+ * batch's outputs are in the caller's buffers and returns its status (DCB_ERR_INPUT_RANGE etc.).  At most TWO
+ * submissions may be in flight, so the copy of batch i+1 overlaps the kernels of batch i; tickets must be waited for in
+ * order.  `rows` and the output buffers must stay valid (and should be page-locked, dcb_alloc_host) until dcb_wait
+ * returns.  dcb_forward == dcb_submit + dcb_wait. */
+int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
+               uint8_t* bases_out, uint8_t* quals_out, float* probs_out, float* logits_out, int64_t* ticket);
+int dcb_wait(dcb_engine* e, int64_t ticket);
+
 /* Device time of the last dcb_forward (milliseconds, CUDA events on the engine's stream). */
 int dcb_last_forward_ms(dcb_engine* e, float* ms);
 /* Number of engine kernels launched by the last dcb_forward. */

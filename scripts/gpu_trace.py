@@ -14,9 +14,9 @@ buf = (ctypes.c_uint64 * (256 * 16))()
 lib.dcb_debug_trace(buf, 256 * 16)
 a = np.array(buf[:], dtype=np.float64).reshape(256, 16)[:148]
 a = a[a[:, 0] > 0]
-names = ["mma_total", "mma_wait_hfree", "mma_wait_full", "mma_wait_hsfull", "mma_issue", "mma_wait_afull", "mma_wait_yempty", "rounds",
-         "hepi_wait_hfull", "hepi_wait_hsfree", "hepi_body", "row_wait_yfull", "row_body", "row_ldtm_in_body", "row_phaseA"]
-rounds = a[:, 7].max()
+names = ["mma_total", "mma_wait_hfree", "mma_wait_full", "mma_wait_hsfull", "mma_issue", "mma_wait_afull", "mma_wait_yempty", "mma_wait_a2full",
+         "hepi_wait_hfull", "hepi_wait_hsfree", "hepi_body", "row_wait_yfull", "row_body", "row_ldtm_in_body", "row_phaseA", "mma_oproj_loop"]
+rounds = float(os.environ.get('TRACE_ROUNDS', '7'))
 print("rounds", rounds, "chunks", rounds * 16)
 for i, nme in enumerate(names):
     col = a[:, i]

@@ -161,14 +161,15 @@ def test_run_model_on_examples_and_stitch(engine_mod, golden_dir):
 
 
 def test_unfused_fallback_paths_agree_with_fused(engine_mod):
-  """DCB_FUSE_OPROJ / DCB_FUSE_EMBED / DCB_FUSE_QA / DCB_ALIGN / DCB_FFN_PAIR select measured alternatives of the same math;
+  """DCB_STACK / DCB_FUSE_OPROJ / DCB_FUSE_EMBED / DCB_FUSE_QA / DCB_ALIGN / DCB_FFN_PAIR select measured alternatives of the same math;
   they are read when an engine is created, so flip them around model construction."""
   p = params_lib.synthetic_params(20, 120, num_hidden_layers=2)
   w = weights_lib.init_weights(p, seed=21)
   rows = synthetic.make_rows(p, 5, seed=22)
   ref = omodel.forward(rows, p, w)["logits"]
   outs = {}
-  for name, env in (("fused", {}),
+  for name, env in (("fused", {}),                                     # default: whole stack in one kernel
+                    ("per_layer", {"DCB_STACK": "0"}),                  # QKV+attention and out-proj+FFN kernels per layer
                     ("unfused", {"DCB_FUSE_OPROJ": "0", "DCB_FUSE_EMBED": "0", "DCB_FUSE_QA": "0"}),
                     ("packed", {"DCB_ALIGN": "0"}),                     # windows packed back to back, separate QKV / attention
                     ("single_cta", {"DCB_FFN_PAIR": "0", "DCB_FUSE_QA": "0"}),
@@ -186,6 +187,7 @@ def test_unfused_fallback_paths_agree_with_fused(engine_mod):
         else:
           os.environ[k] = v
     assert np.abs(outs[name] - ref).max() <= LOGIT_TOL_FP32, name
+  assert np.abs(outs["fused"] - outs["per_layer"]).max() < 0.05
   assert np.abs(outs["fused"] - outs["unfused"]).max() < 0.05
   assert np.abs(outs["fused"] - outs["packed"]).max() < 0.05
   assert np.abs(outs["qkv2"] - outs["unfused"]).max() < 0.05
@@ -213,3 +215,34 @@ def test_engine_against_reference_code_goldens(engine_mod, golden_dir, name):
   assert (out["bases"][safe] == rb[safe]).all()
   assert (out["bases"] == rb).mean() > 0.98
   assert np.abs(out["probs"] - z["probs"]).max() < 0.05
+
+
+def test_pipelined_submit_wait_matches_blocking_forward(engine_mod):
+  """dcb_submit / dcb_wait (two batches in flight, H2D of batch i+1 under the kernels of batch i) returns exactly what
+  dcb_forward returns, keeps order, reports per-ticket input errors and refuses a third outstanding submission."""
+  p = params_lib.synthetic_params(20, 120)
+  w = weights_lib.init_weights(p, seed=31)
+  model = engine_mod.B200Model(p, w, max_batch=16)
+  batches = [synthetic.make_rows(p, n, seed=40 + i) for i, n in enumerate((16, 7, 16, 1, 12))]
+  blocking = [model.forward(b, want_probs=True) for b in batches]
+  piped = list(model.forward_batches(batches, want_probs=True))
+  assert len(piped) == len(blocking)
+  for a, b in zip(blocking, piped):
+    assert np.array_equal(a["bases"], b["bases"]) and np.array_equal(a["quals"], b["quals"])
+    assert np.array_equal(a["probs"], b["probs"])
+  # a bad batch between two good ones: only its own ticket reports the range error
+  bad = batches[1].copy()
+  bad[0, 0, 0] = 9.0
+  h0 = model.submit(batches[0])
+  h1 = model.submit(bad)
+  with pytest.raises(engine_mod.DcbError):
+    model.submit(batches[2])                      # two already in flight
+  o0 = model.wait(h0)
+  with pytest.raises(engine_mod.DcbError):
+    model.wait(h1)
+  with pytest.raises(engine_mod.DcbError):
+    model.wait(h1)                                # not in flight any more
+  h2 = model.submit(batches[2])
+  o2 = model.wait(h2)
+  assert np.array_equal(o0["bases"], blocking[0]["bases"]) and np.array_equal(o2["quals"], blocking[2]["quals"])
+  model.close()
