@@ -202,6 +202,28 @@ __device__ __forceinline__ void umma_bf16_ss_pair(uint32_t d_tmem, uint64_t a_de
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
       : "memory");
 }
+// Warp-collective forms: the WHOLE (converged) warp calls them and one elected lane issues.  With the issuing code
+// under `if (lane == 0)` ptxas cannot prove uniformity and wraps every UTCHMMA in an ELECT / BRA.U.ANY loop plus
+// R2UR moves (~100 issue cycles per UMMA, more than the 64-72 cycles the instruction occupies the tensor pipe).
+__device__ __forceinline__ void umma_bf16_ss_pair_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                       uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_warp(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
 // Completion of all prior pair-MMAs -> arrive on the barrier at this offset in the CTAs of cta_mask.
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(

@@ -208,7 +208,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
         }
       }
     } else if (warp == 1 || warp == 2) {
-      if (lane == 0) {
+      if (leader || lane == 0) {   // leader: the whole warp walks the issue program (elected lane issues); peer: one relay thread
         if (leader) {
           // ---------------------------------------------------------------- UMMA issuers (leader only)
           // warp 1: q/k/v blocks, out-projections and every GEMM1; warp 2: every GEMM2 (the two share the tensor
@@ -216,85 +216,98 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
           constexpr uint32_t idesc_h = make_idesc_bf16(2 * kTileM, kFFChunk);
           constexpr uint32_t idesc_y = make_idesc_bf16(2 * kTileM, kNC);
           constexpr uint16_t kBoth = 3;
-          const uint32_t a_addr = smem_u32(sA);
           const uint32_t s_addr = smem_u32(sS);
+          // descriptors differ only in their 14-bit start-address field (bytes >> 4): build each family once and add
+          const uint64_t adesc_a = make_kc16_desc(smem_u32(sA), kTileM * 16, 128);        // operand tile sA, + kstep * 256
+          const uint64_t adesc_s = make_kc16_desc(s_addr, kTileM * 16, 128);              // att_h / hidden tiles in the staging area
+          const uint64_t bdesc_72 = make_kc16_desc(0, (kDHP / 2) * 16, 128);              // + slot address >> 4
+          const uint64_t bdesc_144 = make_kc16_desc(0, (kDP / 2) * 16, 128);
+          const uint64_t bdesc_64 = make_kc16_desc(0, (kFFChunk / 2) * 16, 128);
           uint32_t cpar = 0;   // bit s: parity of the number of stages consumed from slot s (by either issuer)
+          // Plain (CTA-scope) waits also on barriers the peer arrives on, as CUTLASS' ClusterBarrier::wait does: a
+          // cluster-scope acquire makes ptxas put CCTL.IVALL (invalidate L1) into every poll, which evicted the
+          // workers' bias / LayerNorm vectors continuously.
           auto use = [&](int s) -> uint32_t {
-            SWC(&full[s], (cpar >> s) & 1, 103);
+            SW(&full[s], (cpar >> s) & 1, 103);
             tc_fence_after();
-            return smem_u32(slot_ptr(s));
+            return smem_u32(slot_ptr(s)) >> 4;   // in descriptor address units
           };
           auto release = [&](int s) {
-            umma_commit_pair(&empty[s], kBoth);
+            umma_commit_pair_warp(&empty[s], kBoth);
             cpar ^= 1u << s;
           };
           uint32_t nn0 = 0;
           if (warp == 1) {
             uint32_t kblk = 0, katt = 0, kar = 0;
+            long long t_ar1 = 0, t_accfree = 0, t_qkv = 0, t_attw = 0, t_oproj = 0, t_ar2 = 0, t_ffn = 0;
+            const long long t_begin = clock64();
             for (int ti = 0; ti < rounds; ++ti) {
               for (int n = 0; n < NL; ++n) {
-                SWC(a_ready, kar & 1, 204); ++kar;
+                TRACE_T0();
+                SW(a_ready, kar & 1, 204); ++kar;
+                TRACE_ADD(t_ar1);
                 tc_fence_after();
                 int sa = 0;
                 for (int h = 0; h < kHeads; ++h) {
                   for (int m = 0; m < 3; ++m) {
-                    SWC(acc_free, (kblk & 1) ^ 1, 305); ++kblk;
+                    SW(acc_free, (kblk & 1) ^ 1, 305); ++kblk;
+                    TRACE_ADD(t_accfree);
                     tc_fence_after();
                     for (int s = 0; s < C::kQkvStages; ++s) {
                       const uint32_t sb = use(sa);
 #pragma unroll
                       for (int kk = 0; kk < C::kQkvStageK; ++kk) {
                         const int kstep = s * C::kQkvStageK + kk;
-                        const uint64_t adesc = make_kc16_desc(a_addr + kstep * 4096, kTileM * 16, 128);
-                        const uint64_t bdesc = make_kc16_desc(sb + kk * C::kQkvStepBytes, (kDHP / 2) * 16, 128);
-                        umma_bf16_ss_pair(tmem_base + C::kTmemAcc, adesc, bdesc, idesc_y, kstep != 0);
+                        umma_bf16_ss_pair_warp(tmem_base + C::kTmemAcc, adesc_a + kstep * 256,
+                                               bdesc_72 + (sb + kk * (C::kQkvStepBytes >> 4)), idesc_y, kstep != 0);
                       }
                       release(sa);
                       sa = sa + 1 == C::kSlotsA ? 0 : sa + 1;
                     }
-                    umma_commit_pair(acc_full, kBoth);
+                    umma_commit_pair_warp(acc_full, kBoth);
+                    TRACE_ADD(t_qkv);
                   }
                   // Y += att_h * Wo_h^T
-                  SWC(att_ready, katt & 1, 406); ++katt;
+                  SW(att_ready, katt & 1, 406); ++katt;
+                    TRACE_ADD(t_attw);
                   tc_fence_after();
                   for (int s = 0; s < C::kWoStages; ++s) {
                     const uint32_t sb = use(sa);
 #pragma unroll
                     for (int kk = 0; kk < C::kWoStageK; ++kk) {
                       const int kstep = s * C::kWoStageK + kk;
-                      const uint64_t adesc = make_kc16_desc(s_addr + kstep * 4096, kTileM * 16, 128);
 #pragma unroll
-                      for (int j = 0; j < 2; ++j) {
-                        const uint64_t bdesc = make_kc16_desc(sb + kk * C::kWoStepBytes + j * (kNC / 2) * 16, (kDP / 2) * 16, 128);
-                        umma_bf16_ss_pair(tmem_base + C::kTmemY + j * kNC, adesc, bdesc, idesc_y, true);
-                      }
+                      for (int j = 0; j < 2; ++j)
+                        umma_bf16_ss_pair_warp(tmem_base + C::kTmemY + j * kNC, adesc_s + kstep * 256,
+                                               bdesc_144 + (sb + kk * (C::kWoStepBytes >> 4) + j * (kNC / 2)), idesc_y, true);
                     }
                     release(sa);
                     sa = sa + 1 == C::kSlotsA ? 0 : sa + 1;
                   }
-                  umma_commit_pair(s_free, kBoth);
-                  if (h == kHeads - 1) umma_commit_pair(tail_free, kBoth);
+                  umma_commit_pair_warp(s_free, kBoth);
+                  if (h == kHeads - 1) umma_commit_pair_warp(tail_free, kBoth);
+                  TRACE_ADD(t_oproj);
                 }
                 // ---- FFN: GEMM1 of every chunk
-                SWC(a_ready, kar & 1, 207); ++kar;
+                SW(a_ready, kar & 1, 207); ++kar;
+                    TRACE_ADD(t_ar2);
                 tc_fence_after();
                 int sf = 0;
                 auto gemm1 = [&](uint32_t nn) {
-                  SWC(h_free, (nn & 1) ^ 1, 508);
+                  SW(h_free, (nn & 1) ^ 1, 508);
                   tc_fence_after();
                   for (int s = 0; s < C::kW1Stages; ++s) {
                     const uint32_t sb = use(sf);
 #pragma unroll
                     for (int kk = 0; kk < C::kW1StageK; ++kk) {
                       const int kstep = s * C::kW1StageK + kk;
-                      const uint64_t adesc = make_kc16_desc(a_addr + kstep * 4096, kTileM * 16, 128);
-                      const uint64_t bdesc = make_kc16_desc(sb + kk * C::kW1StepBytes, (kFFChunk / 2) * 16, 128);
-                      umma_bf16_ss_pair(tmem_base + C::kTmemH, adesc, bdesc, idesc_h, kstep != 0);
+                      umma_bf16_ss_pair_warp(tmem_base + C::kTmemH, adesc_a + kstep * 256,
+                                             bdesc_64 + (sb + kk * (C::kW1StepBytes >> 4)), idesc_h, kstep != 0);
                     }
                     release(sf);
                     sf = sf + 1 == C::kSlotsF ? 0 : sf + 1;
                   }
-                  umma_commit_pair(h_full, kBoth);
+                  umma_commit_pair_warp(h_full, kBoth);
                 };
                 auto skipf = [&](int count) {
                   for (int s = 0; s < count; ++s) { cpar ^= 1u << sf; sf = sf + 1 == C::kSlotsF ? 0 : sf + 1; }
@@ -305,8 +318,16 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
                   skipf(C::kW2Stages);
                 }
                 nn0 += nchunks;
+                TRACE_ADD(t_ffn);
               }
             }
+#ifdef DCB_TRACE
+            if (blockIdx.x < 256) {
+              unsigned long long* tr = g_ffn_trace + blockIdx.x * 16;
+              tr[0] = clock64() - t_begin; tr[1] = t_ar1; tr[2] = t_accfree; tr[3] = t_qkv; tr[4] = t_attw; tr[5] = t_oproj;
+              tr[6] = t_ar2; tr[7] = t_ffn;
+            }
+#endif
           } else {
             for (int ti = 0; ti < rounds; ++ti) {
               for (int n = 0; n < NL; ++n) {
@@ -319,27 +340,25 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
                 for (int c = 0; c < nchunks; ++c) {
                   if (c + 1 < nchunks) skipf(C::kW1Stages);
                   const uint32_t nn = nn0 + c, b = nn & 1;
-                  SWC(&hs_full[b], (nn >> 1) & 1, 609);
+                  SW(&hs_full[b], (nn >> 1) & 1, 609);
                   tc_fence_after();
-                  const uint32_t h_addr = s_addr + b * C::kHBytes;
+                  const uint64_t adesc_h = adesc_s + b * (C::kHBytes >> 4);
                   for (int s = 0; s < C::kW2Stages; ++s) {
                     const uint32_t sb = use(sf);
 #pragma unroll
                     for (int kk = 0; kk < C::kW2StageK; ++kk) {
                       const int kstep = s * C::kW2StageK + kk;
-                      const uint64_t adesc = make_kc16_desc(h_addr + kstep * 4096, kTileM * 16, 128);
 #pragma unroll
-                      for (int j = 0; j < 2; ++j) {
-                        const uint64_t bdesc = make_kc16_desc(sb + kk * C::kWoStepBytes + j * (kNC / 2) * 16, (kDP / 2) * 16, 128);
-                        umma_bf16_ss_pair(tmem_base + C::kTmemY + j * kNC, adesc, bdesc, idesc_y, true);
-                      }
+                      for (int j = 0; j < 2; ++j)
+                        umma_bf16_ss_pair_warp(tmem_base + C::kTmemY + j * kNC, adesc_h + kstep * 256,
+                                               bdesc_144 + (sb + kk * (C::kWoStepBytes >> 4) + j * (kNC / 2)), idesc_y, true);
                     }
                     release(sf);
                     sf = sf + 1 == C::kSlotsF ? 0 : sf + 1;
                   }
-                  umma_commit_pair(&hs_free[b], kBoth);
+                  umma_commit_pair_warp(&hs_free[b], kBoth);
                 }
-                umma_commit_pair(y_full, kBoth);
+                umma_commit_pair_warp(y_full, kBoth);
                 nn0 += nchunks;
               }
             }
@@ -661,7 +680,13 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
             const int cb = halfsel * (kFFChunk / 32) + cc;
             float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(acc[cc][i]) + __ldg(bias + cc * 16 + i), 0.f);
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cc * 16) + i);
+              v[4 * i + 0] = fmaxf(__uint_as_float(acc[cc][4 * i + 0]) + b4.x, 0.f);
+              v[4 * i + 1] = fmaxf(__uint_as_float(acc[cc][4 * i + 1]) + b4.y, 0.f);
+              v[4 * i + 2] = fmaxf(__uint_as_float(acc[cc][4 * i + 2]) + b4.z, 0.f);
+              v[4 * i + 3] = fmaxf(__uint_as_float(acc[cc][4 * i + 3]) + b4.w, 0.f);
+            }
             hrow[(size_t)(cb * 2) * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                                          pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
             hrow[(size_t)(cb * 2 + 1) * kTileM] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),

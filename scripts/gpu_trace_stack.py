@@ -1,0 +1,20 @@
+"""Cycle trace of stack_pair_kernel's UMMA issuer (needs a -DDCB_TRACE build)."""
+import ctypes, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from deepconsensus_b200 import params as P, weights as W, synthetic, engine
+p = P.synthetic_params(20, 120); w = W.init_weights(p, seed=1)
+B = 1024
+rows = synthetic.make_rows(p, B, seed=7)
+m = engine.B200Model(p, w, max_batch=B)
+for _ in range(3): m.forward(rows)
+print("device ms", m.last_ms)
+lib = engine.load_library()
+buf = (ctypes.c_uint64 * (256 * 16))()
+lib.dcb_debug_trace(buf, 256 * 16)
+a = np.array(buf[:], dtype=np.float64).reshape(256, 16)[:148:2]
+names = ["total", "wait_a_ready_P1", "wait_acc_free", "qkv_issue", "wait_att_ready", "oproj_issue", "wait_a_ready_P5", "ffn_g1_loop"]
+units = 7 * 6
+for i, nme in enumerate(names):
+    col = a[:, i]
+    print("%-18s mean %10.0f  per tile-layer %8.0f   min %10.0f max %10.0f" % (nme, col.mean(), col.mean() / units, col.min(), col.max()))
