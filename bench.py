@@ -285,9 +285,17 @@ def main():
   e2e_value = total_windows / dt_e2e
   F = flops_per_window(p)
   peaks = measured_peaks()
-  # dominant kernel: fused FFN (+ attention out-projection when fused into it).
-  # Algorithmic FLOPs per launch = tokens * (4*d*ff [+ 2*d*d]).
-  per_token = 4.0 * p.hidden_size * p.filter_size + (2.0 * p.hidden_size * p.hidden_size if prof["fused_oproj"] else 0.0)
+  # dominant kernel.  fused_oproj == 2: the whole encoder stack runs in ONE kernel (stack_pair_kernel) -- algorithmic
+  # FLOPs per launch = tokens * layers * (8 d^2 + 4 d ff) + banded attention pairs; otherwise the per-layer fused
+  # out-proj + FFN kernel: tokens * (4 d ff [+ 2 d d]).
+  d, ff, wdw, Lp = p.hidden_size, p.filter_size, p.attn_win_size, p.max_length
+  if prof["fused_oproj"] == 2:
+    pairs = Lp * (2 * wdw + 1) - wdw * (wdw + 1)
+    per_token = p.num_hidden_layers * (8.0 * d * d + 4.0 * d * ff + 4.0 * pairs * d / Lp)
+    kname = "stack_pair_kernel (all %d layers: QKV + banded attention + out-proj + FFN, residual in TMEM)" % p.num_hidden_layers
+  else:
+    per_token = 4.0 * d * ff + (2.0 * d * d if prof["fused_oproj"] else 0.0)
+    kname = "ffn_pair_kernel<fused out-proj>" if prof["fused_oproj"] else "ffn_pair_kernel"
   ffn_flops = prof["ffn_tokens"] * per_token
   ffn_tflops = ffn_flops / (prof["ffn_ms_total"] * 1e-3) / 1e12 if prof["ffn_ms_total"] > 0 else None
   traffic = None
@@ -296,15 +304,21 @@ def main():
     with open(tpath) as f:
       traffic = json.load(f).get("dram_bytes_per_launch")
   kshare = {k: round(v["ms"] / max(sum(x["ms"] for x in prof["kernels"].values()), 1e-9), 4) for k, v in prof["kernels"].items()}
-  roof = dict(bound="tensor", kernel="ffn_pair_kernel<fused out-proj>" if prof["fused_oproj"] else "ffn_pair_kernel",
+  # the stack kernel is ~90 % of a long back-to-back step: the sustained cuBLAS figure is its denominator; a per-layer
+  # kernel timed between others is compared with the burst figure
+  if prof["fused_oproj"] == 2 and peaks.get("bf16_tflops_sustained"):
+    peak_used, peak_src = peaks["bf16_tflops_sustained"], peaks["source"] + " (sustained bf16: kernel timed inside a long step)"
+  else:
+    peak_used, peak_src = peaks["bf16_tflops"], peaks["source"] + " (burst bf16)"
+  roof = dict(bound="tensor", kernel=kname,
               achieved=ffn_tflops, flops_per_token=per_token, kernel_time_share=kshare,
-              kernel_ms_per_step={k: round(v["ms"] / args.steps, 4) for k, v in prof["kernels"].items()}, peak=peaks["bf16_tflops"],
-              unit="TFLOP/s", frac=(ffn_tflops / peaks["bf16_tflops"]) if ffn_tflops else None,
-              traffic=traffic, peak_source=peaks["source"] + " (burst bf16)",
+              kernel_ms_per_step={k: round(v["ms"] / args.steps, 4) for k, v in prof["kernels"].items()}, peak=peak_used,
+              unit="TFLOP/s", frac=(ffn_tflops / peak_used) if ffn_tflops else None,
+              traffic=traffic, peak_source=peak_src, peak_burst=peaks["bf16_tflops"],
               launches_timed=prof["ffn_launches"],
               avg_launch_ms=prof["ffn_ms_total"] / max(prof["ffn_launches"], 1),
               model_tflops_whole_step=value / world * F / 1e12,
-              model_frac_of_peak=value / world * F / 1e12 / peaks["bf16_tflops"])
+              model_frac_of_peak=value / world * F / 1e12 / peak_used)
   line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
               ms_per_step=dt / args.steps * 1e3, device_ms_per_step=dev_ms / args.steps,
               higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",

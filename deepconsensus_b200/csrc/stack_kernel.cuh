@@ -60,6 +60,12 @@ static_assert(StackCfg::kW1StageK * StackCfg::kW1StepBytes <= StackCfg::kSlotByt
 static_assert(StackCfg::kW2StageK * StackCfg::kWoStepBytes <= StackCfg::kSlotBytes, "w2 stage");
 static_assert(StackCfg::kTmemAcc + kNC <= 512 && StackCfg::kTmemH + kFFChunk <= 512, "TMEM map");
 
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+
 // Debug aid (-DDCB_WATCHDOG): every mbarrier wait gives up after ~50 M cycles, records (tag, parity) of EVERY waiting
 // warp in g_ffn_trace[block*16 + warp] and lets the kernel run to completion (garbage results) so the host can read
 // who was waiting on what (scripts/gpu_stack_check.py prints it).
@@ -169,18 +175,27 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
         for (int ti = 0; ti < rounds; ++ti) {
           for (int n = 0; n < NL; ++n, ++li) {
             int sa = 0;
-            for (int h = 0; h < kHeads; ++h) {
+            // order of consumption: head 0 q,k,v | head 1 q (computed while the workers run the attention of head 0) |
+            // Wo_0 | head 1 k,v | Wo_1
+            auto push_blocks = [&](int h, int m_lo, int m_hi) {
               const uint8_t* wq = P.wq3[n] + (size_t)(h * 2 + rank) * 3 * C::kQkvBlockBytes;
-              for (int m = 0; m < 3; ++m)
-                for (int s = 0; s < C::kQkvStages; ++s) {
-                  push(sa, wq + (size_t)m * C::kQkvBlockBytes + s * C::kSlotBytes, C::kSlotBytes);
+              for (int m = m_lo; m < m_hi; ++m)
+                for (int st = 0; st < C::kQkvStages; ++st) {
+                  push(sa, wq + (size_t)m * C::kQkvBlockBytes + st * C::kSlotBytes, C::kSlotBytes);
                   sa = sa + 1 == C::kSlotsA ? 0 : sa + 1;
                 }
+            };
+            auto push_wo = [&](int h) {
               const uint8_t* wo = P.wo2[n] + ((size_t)rank * kHeads + h) * C::kWoStages * C::kSlotBytes;
-              for (int s = 0; s < C::kWoStages; ++s) {
-                push(sa, wo + s * C::kSlotBytes, C::kSlotBytes);
+              for (int st = 0; st < C::kWoStages; ++st) {
+                push(sa, wo + st * C::kSlotBytes, C::kSlotBytes);
                 sa = sa + 1 == C::kSlotsA ? 0 : sa + 1;
               }
+            };
+#pragma unroll 1
+            for (int step = 0; step < 5; ++step) {
+              if (step == 2 || step == 4) push_wo(step == 4 ? 1 : 0);
+              else push_blocks(step == 0 ? 0 : 1, step == 3 ? 1 : 0, step == 1 ? 1 : 3);
             }
             int sf = 0;
             bool tail_ok = false;
@@ -248,16 +263,16 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
                 TRACE_ADD(t_ar1);
                 tc_fence_after();
                 int sa = 0;
-                for (int h = 0; h < kHeads; ++h) {
-                  for (int m = 0; m < 3; ++m) {
+                auto qkv_blocks = [&](int count) {
+                  for (int m = 0; m < count; ++m) {
                     SW(acc_free, (kblk & 1) ^ 1, 305); ++kblk;
                     TRACE_ADD(t_accfree);
                     tc_fence_after();
-                    for (int s = 0; s < C::kQkvStages; ++s) {
+                    for (int st = 0; st < C::kQkvStages; ++st) {
                       const uint32_t sb = use(sa);
 #pragma unroll
                       for (int kk = 0; kk < C::kQkvStageK; ++kk) {
-                        const int kstep = s * C::kQkvStageK + kk;
+                        const int kstep = st * C::kQkvStageK + kk;
                         umma_bf16_ss_pair_warp(tmem_base + C::kTmemAcc, adesc_a + kstep * 256,
                                                bdesc_72 + (sb + kk * (C::kQkvStepBytes >> 4)), idesc_y, kstep != 0);
                       }
@@ -267,15 +282,17 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
                     umma_commit_pair_warp(acc_full, kBoth);
                     TRACE_ADD(t_qkv);
                   }
+                };
+                auto out_proj = [&](int h) {
                   // Y += att_h * Wo_h^T
                   SW(att_ready, katt & 1, 406); ++katt;
-                    TRACE_ADD(t_attw);
+                  TRACE_ADD(t_attw);
                   tc_fence_after();
-                  for (int s = 0; s < C::kWoStages; ++s) {
+                  for (int st = 0; st < C::kWoStages; ++st) {
                     const uint32_t sb = use(sa);
 #pragma unroll
                     for (int kk = 0; kk < C::kWoStageK; ++kk) {
-                      const int kstep = s * C::kWoStageK + kk;
+                      const int kstep = st * C::kWoStageK + kk;
 #pragma unroll
                       for (int j = 0; j < 2; ++j)
                         umma_bf16_ss_pair_warp(tmem_base + C::kTmemY + j * kNC, adesc_s + kstep * 256,
@@ -287,6 +304,13 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
                   umma_commit_pair_warp(s_free, kBoth);
                   if (h == kHeads - 1) umma_commit_pair_warp(tail_free, kBoth);
                   TRACE_ADD(t_oproj);
+                };
+                // head 0: q,k,v | head 1: q (its block sits in ACC while the workers run the attention of head 0) | Wo_0 |
+                // head 1: k,v | Wo_1 -- one call site each
+#pragma unroll 1
+                for (int step = 0; step < 5; ++step) {
+                  if (step == 2 || step == 4) out_proj(step == 4 ? 1 : 0);
+                  else qkv_blocks(step == 0 ? 3 : (step == 1 ? 1 : 2));
                 }
                 // ---- FFN: GEMM1 of every chunk
                 SW(a_ready, kar & 1, 207); ++kar;
@@ -430,7 +454,13 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
           tmem_ld_wait();
           if (bias) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __ldg(bias + (cb0 + cb) * 16 + i));
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + (cb0 + cb) * 16) + i);
+              acc[4 * i + 0] = __float_as_uint(__uint_as_float(acc[4 * i + 0]) + b4.x);
+              acc[4 * i + 1] = __float_as_uint(__uint_as_float(acc[4 * i + 1]) + b4.y);
+              acc[4 * i + 2] = __float_as_uint(__uint_as_float(acc[4 * i + 2]) + b4.z);
+              acc[4 * i + 3] = __float_as_uint(__uint_as_float(acc[4 * i + 3]) + b4.w);
+            }
             tmem_st16(tmem_row + C::kTmemY + (cb0 + cb) * 16, acc);
           }
           if (cb == 0) shift = __uint_as_float(acc[0]);
@@ -544,16 +574,11 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
           {
             const int i0 = ew * 16;
             const int r0 = i0 + g, r1 = r0 + 8;
-            const __nv_bfloat16* q0 = sQ + (size_t)r0 * kS + 2 * t;
-            const __nv_bfloat16* q1 = sQ + (size_t)r1 * kS + 2 * t;
+            // A fragments of the 16 query rows: one ldmatrix.x4 per 16 dims (matrices: rows 0-7 | 8-15 x dims 0-7 | 8-15)
+            const uint32_t qaddr = smem_u32(sQ + (size_t)(i0 + (lane & 7) + ((lane >> 3) & 1) * 8) * kS + (lane >> 4) * 8);
             uint32_t qa[kDHP / 16][4];
 #pragma unroll
-            for (int ks = 0; ks < kDHP / 16; ++ks) {
-              qa[ks][0] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16);
-              qa[ks][1] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16);
-              qa[ks][2] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + 8);
-              qa[ks][3] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + 8);
-            }
+            for (int ks = 0; ks < kDHP / 16; ++ks) ldmatrix_x4(qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], qaddr + ks * 32);
             asm volatile("bar.sync 2, 256;" ::: "memory");   // every warp holds its q fragments: the q area may be overwritten
             float o[kDHP / 8][4];
 #pragma unroll
@@ -571,15 +596,12 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
 #pragma unroll
             for (int kt = 0; kt < kMaxKT; ++kt) {
               if (kt < nkt) {
-                const int krow0 = jlo + kt * 16 + g, krow1 = krow0 + 8;
-                const __nv_bfloat16* kr0 = sK + (size_t)krow0 * kS + 2 * t;
-                const __nv_bfloat16* kr1 = sK + (size_t)krow1 * kS + 2 * t;
+                // B fragments of 16 keys: one ldmatrix.x4 per 16 dims (keys 0-7 x dims 0-7 | 8-15, keys 8-15 x dims 0-7 | 8-15)
+                const uint32_t kaddr = smem_u32(sK + (size_t)(jlo + kt * 16 + (lane & 7) + (lane >> 4) * 8) * kS + ((lane >> 3) & 1) * 8);
 #pragma unroll
                 for (int ks = 0; ks < kDHP / 16; ++ks) {
-                  const uint32_t a0 = *reinterpret_cast<const uint32_t*>(kr0 + ks * 16);
-                  const uint32_t a1 = *reinterpret_cast<const uint32_t*>(kr0 + ks * 16 + 8);
-                  const uint32_t c0 = *reinterpret_cast<const uint32_t*>(kr1 + ks * 16);
-                  const uint32_t c1 = *reinterpret_cast<const uint32_t*>(kr1 + ks * 16 + 8);
+                  uint32_t a0, a1, c0, c1;
+                  ldmatrix_x4(a0, a1, c0, c1, kaddr + ks * 32);
                   mma_bf16_16816(sc[kt][0], qa[ks], a0, a1);
                   mma_bf16_16816(sc[kt][1], qa[ks], c0, c1);
                 }
