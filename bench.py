@@ -299,7 +299,7 @@ def main():
   ffn_flops = prof["ffn_tokens"] * per_token
   ffn_tflops = ffn_flops / (prof["ffn_ms_total"] * 1e-3) / 1e12 if prof["ffn_ms_total"] > 0 else None
   traffic = None
-  tpath = os.path.join(ROOT, "profiles", "ffn_dram_traffic.json")
+  tpath = os.path.join(ROOT, "profiles", "stack_dram_traffic.json" if prof["fused_oproj"] == 2 else "ffn_dram_traffic.json")
   if os.path.exists(tpath):
     with open(tpath) as f:
       traffic = json.load(f).get("dram_bytes_per_launch")

@@ -373,7 +373,7 @@ class B200Model:
     self._check(self._lib.dcb_get_profile_kernels(self._handle, ms6, n6, ctypes.byref(fused)))
     names = ("embed", "row_gemm", "qkv_gemm", "attention", "ffn", "head")
     return dict(ffn_ms_total=float(ms.value), ffn_launches=int(n.value), ffn_tokens=int(tok.value),
-                fused_oproj=bool(fused.value),
+                fused_oproj=int(fused.value),   # 0: separate out-proj, 1: fused into the FFN kernel, 2: whole stack in one kernel
                 kernels={k: dict(ms=float(ms6[i]), launches=int(n6[i])) for i, k in enumerate(names)})
 
   def set_debug(self, enabled: bool = True) -> None:
