@@ -641,12 +641,15 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
       if (e->debug) cudaMemcpyAsync(e->d_dbg + (size_t)stage * e->chunk_tiles * ximg, e->d_x, (size_t)T * ximg * sizeof(float), cudaMemcpyDeviceToDevice, st);
       ++stage;
     };
+    const bool use_stack = e->stack && e->fuse_qa && e->ffn_pair && e->fuse_oproj && e->fuse_embed && !e->debug && Lw == kTileM &&
+                           c.attn_win_size > 0 && c.attn_win_size <= 16 && c.num_hidden_layers <= kMaxLayers;
     {
       RowEpi epi{};
-      epi.x = e->d_x; epi.xb = e->d_xb; epi.bias = nullptr;
+      // the one-kernel stack builds every operand tile from the residual in TMEM: no bf16 operand image needed
+      epi.x = e->d_x; epi.xb = use_stack ? nullptr : e->d_xb; epi.bias = nullptr;
       epi.pe = c.add_pos_encoding ? e->d_pe : nullptr;
-      epi.ln_g = c.rezero ? nullptr : e->layers[0].ln_g[0];
-      epi.ln_b = c.rezero ? nullptr : e->layers[0].ln_b[0];
+      epi.ln_g = (c.rezero || use_stack) ? nullptr : e->layers[0].ln_g[0];
+      epi.ln_b = (c.rezero || use_stack) ? nullptr : e->layers[0].ln_b[0];
       epi.has_xold = 0; epi.L = Lw;
       bool fused_embed = false;
       if (e->fuse_embed) {
@@ -667,8 +670,6 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
       }
       snap();
     }
-    const bool use_stack = e->stack && e->fuse_qa && e->ffn_pair && e->fuse_oproj && !e->debug && Lw == kTileM &&
-                           c.attn_win_size > 0 && c.attn_win_size <= 16 && c.num_hidden_layers <= kMaxLayers;
     if (use_stack) {
       StackParams sp{};
       sp.num_layers = c.num_hidden_layers;

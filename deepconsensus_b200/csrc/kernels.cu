@@ -468,8 +468,8 @@ embed_condense_kernel(const float* __restrict__ rows, int R, int L, int Lw, int 
         }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------- UMMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------- UMMA issuer (whole warp, elected lane issues)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, kNC);
       uint32_t n = 0, it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -488,14 +488,33 @@ embed_condense_kernel(const float* __restrict__ rows, int R, int L, int Lw, int 
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const uint64_t bdesc = make_kc16_desc(sb + kk * (2 * kDP * 16) + j * kNC * 16, kDP * 16, 128);
-              umma_bf16_ss(tmem_base + j * kNC, adesc, bdesc, idesc, (sl | kk) != 0);
+              umma_bf16_ss_warp(tmem_base + j * kNC, adesc, bdesc, idesc, (sl | kk) != 0);
             }
           }
-          umma_commit(&a_empty[b]);
-          umma_commit(&b_empty[b]);
+          umma_commit_warp(&a_empty[b]);
+          umma_commit_warp(&b_empty[b]);
         }
-        umma_commit(acc_full);
+        umma_commit_warp(acc_full);
       }
+    }
+   } else {
+    // warps 2-3 (otherwise idle): pull the NEXT tile's input rows into L2 -- the builders' id phase is a chain of
+    // dependent global-load batches and runs at L2 instead of HBM latency that way.  One tile ahead (paced by acc_full).
+    const int pt = threadIdx.x - 64;   // 0..63
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int nxt = tile + gridDim.x;
+      if (nxt < ntiles) {
+        const int w_lo = (nxt * kTileM) / Lw;
+        int w_hi = (nxt * kTileM + kTileM - 1) / Lw;
+        const int nwin = (M + Lw - 1) / Lw;
+        if (w_hi > nwin - 1) w_hi = nwin - 1;
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(rows + (size_t)w_lo * R * L);
+        const size_t bytes = (size_t)(w_hi - w_lo + 1) * R * L * sizeof(float);
+        for (size_t off = (size_t)pt * 128; off < bytes; off += 64 * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+      }
+      mbar_wait(acc_full, it & 1);
     }
    }
   } else if (warp < 12) {
