@@ -68,6 +68,8 @@ struct dcb_engine {
   bool fuse_oproj = true;
   bool fuse_embed = true;
   bool fuse_qa = true;
+  bool fuse_head = false;  // head in the tail of the stack kernel: measured 1 % SLOWER than the separate kernel (the five
+                           // 280-long dot products per token are LDS-bound and the tensor pipe idles meanwhile); DCB_FUSE_HEAD=1
   bool stack = true;   // whole encoder stack in one launch (stack_pair_kernel) when the configuration allows it
   bool qkv2 = false;   // measured: not faster than gemm_kernel<3,QKV> (both sit on the per-SM L2 port), kept as an option
   bool fused_last = false;
@@ -231,6 +233,7 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   if (const char* env = getenv("DCB_FUSE_EMBED")) e->fuse_embed = atoi(env) != 0;
   if (const char* env = getenv("DCB_FUSE_QA")) e->fuse_qa = atoi(env) != 0;
   if (const char* env = getenv("DCB_STACK")) e->stack = atoi(env) != 0;
+  if (const char* env = getenv("DCB_FUSE_HEAD")) e->fuse_head = atoi(env) != 0;
   int ct = cfg->chunk_tiles;
   if (const char* env = getenv("DCB_CHUNK_TILES")) ct = atoi(env);
   if (ct <= 0) ct = 8 * e->num_sms;   // measured: larger chunks win (kernels are not DRAM-bound)
@@ -641,6 +644,21 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
       if (e->debug) cudaMemcpyAsync(e->d_dbg + (size_t)stage * e->chunk_tiles * ximg, e->d_x, (size_t)T * ximg * sizeof(float), cudaMemcpyDeviceToDevice, st);
       ++stage;
     };
+    auto make_head = [&]() {
+      HeadParams hp{};
+      hp.x = e->d_x; hp.ln_g = e->d_fln_g; hp.ln_b = e->d_fln_b; hp.wfc = e->d_wfc; hp.bfc = e->d_bfc;
+      const size_t t0 = (size_t)w0 * L;
+      hp.bases = (out_dev ? bases_out : e->d_bases) + t0;
+      hp.quals = (out_dev ? quals_out : e->d_quals) + t0;
+      hp.probs = probs_out ? ((out_dev ? probs_out : e->d_probs) + t0 * kVocab) : nullptr;
+      hp.logits = logits_out ? ((out_dev ? logits_out : e->d_logits) + t0 * kVocab) : nullptr;
+      hp.M = M; hp.L = L; hp.Lw = Lw;
+      hp.calib_enabled = c.calibration_enabled;
+      hp.calib_thr = (float)c.calibration_threshold; hp.calib_w = (float)c.calibration_w; hp.calib_b = (float)c.calibration_b;
+      hp.calib_thr64 = c.calibration_threshold; hp.calib_w64 = c.calibration_w; hp.calib_b64 = c.calibration_b;
+      hp.max_q = (float)c.max_base_quality;
+      return hp;
+    };
     const bool use_stack = e->stack && e->fuse_qa && e->ffn_pair && e->fuse_oproj && e->fuse_embed && !e->debug && Lw == kTileM &&
                            c.attn_win_size > 0 && c.attn_win_size <= 16 && c.num_hidden_layers <= kMaxLayers;
     {
@@ -681,8 +699,10 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
         sp.ln_g0[n_] = c.rezero ? nullptr : ld.ln_g[0]; sp.ln_b0[n_] = c.rezero ? nullptr : ld.ln_b[0];
         sp.ln_g1[n_] = c.rezero ? nullptr : ld.ln_g[1]; sp.ln_b1[n_] = c.rezero ? nullptr : ld.ln_b[1];
       }
+      HeadParams hs{};
+      if (e->fuse_head) { hs = make_head(); }
       pbegin(4);
-      launch_stack(e->d_x, T, L, c.attn_win_size, sp, st);
+      launch_stack(e->d_x, T, L, c.attn_win_size, sp, hs, st);
       pend();
       if (e->profile) e->prof_ffn_tokens += (long long)bw * L;
       e->fused_last = true;
@@ -739,22 +759,13 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
       e->fused_last = fused;
       launches += 3;
     }
-    HeadParams hp{};
-    hp.x = e->d_x; hp.ln_g = e->d_fln_g; hp.ln_b = e->d_fln_b; hp.wfc = e->d_wfc; hp.bfc = e->d_bfc;
-    const size_t t0 = (size_t)w0 * L;
-    hp.bases = (out_dev ? bases_out : e->d_bases) + t0;
-    hp.quals = (out_dev ? quals_out : e->d_quals) + t0;
-    hp.probs = probs_out ? ((out_dev ? probs_out : e->d_probs) + t0 * kVocab) : nullptr;
-    hp.logits = logits_out ? ((out_dev ? logits_out : e->d_logits) + t0 * kVocab) : nullptr;
-    hp.M = M; hp.L = L; hp.Lw = Lw;
-    hp.calib_enabled = c.calibration_enabled;
-    hp.calib_thr = (float)c.calibration_threshold; hp.calib_w = (float)c.calibration_w; hp.calib_b = (float)c.calibration_b;
-    hp.calib_thr64 = c.calibration_threshold; hp.calib_w64 = c.calibration_w; hp.calib_b64 = c.calibration_b;
-    hp.max_q = (float)c.max_base_quality;
-    pbegin(5);
-    launch_head(hp, T, st);
-    pend();
-    ++launches;
+    const bool head_done = use_stack && e->fuse_head;
+    if (!head_done) {
+      pbegin(5);
+      launch_head(make_head(), T, st);
+      pend();
+      ++launches;
+    }
     e->last_chunk_tokens = M;
   }
   CU(e, cudaEventRecord(sl.ev1, st));

@@ -2393,6 +2393,51 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
   }
 }
 
+// logits (+ fc1 bias) -> softmax -> argmax -> Phred -> calibration -> cap / round -> ASCII, for one token
+// (networks.py:238, quick_inference.py:377-414).  Shared by head_kernel and the fused tail of stack_pair_kernel.
+__device__ __forceinline__ void head_finish(const HeadParams& p, float (&lg)[kVocab], size_t oidx) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kVocab; ++j) { lg[j] += p.bfc[j]; mx = fmaxf(mx, lg[j]); }
+  // softmax (networks.py:238), float32
+  float ex[kVocab], sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kVocab; ++j) { ex[j] = expf(lg[j] - mx); sum += ex[j]; }
+  float pr[kVocab], pmax = -1.f;
+  int arg = 0;
+#pragma unroll
+  for (int j = 0; j < kVocab; ++j) {
+    pr[j] = ex[j] / sum;
+    if (pr[j] > pmax) { pmax = pr[j]; arg = j; }  // first maximum wins (np.argmax)
+  }
+  // quick_inference.py:378-389
+  const float err = 1.f - pmax;
+  float qf = -10.f * log10f(err);  // err == 0 -> +inf
+  int qi;
+  if (p.calib_enabled && p.calib_thr != 0.f) {
+    // np.where branch of calibrate_quality_scores promotes to float64 (calibration_lib.py:93-99)
+    const double qd = (double)qf;
+    const bool above = qd > p.calib_thr64;
+    const double qc = qd * (above ? p.calib_w64 : 1.0) + (above ? p.calib_b64 : 0.0);
+    qi = (int)rint(fmin(qc, (double)p.max_q));
+  } else {
+    if (p.calib_enabled) qf = qf * p.calib_w + p.calib_b;    // float32 path (threshold == 0)
+    qi = (int)rintf(fminf(qf, p.max_q));                     // np.round: half to even
+  }
+  qi = qi < 0 ? 0 : qi;
+  const char vocab[kVocab] = {' ', 'A', 'T', 'C', 'G'};
+  p.bases[oidx] = (uint8_t)vocab[arg];
+  p.quals[oidx] = (uint8_t)(qi + 33);
+  if (p.probs) {
+#pragma unroll
+    for (int j = 0; j < kVocab; ++j) p.probs[oidx * kVocab + j] = pr[j];
+  }
+  if (p.logits) {
+#pragma unroll
+    for (int j = 0; j < kVocab; ++j) p.logits[oidx * kVocab + j] = lg[j];
+  }
+}
+
 #include "stack_kernel.cuh"
 
 // =====================================================================================
@@ -2451,46 +2496,7 @@ head_kernel(HeadParams p) {
       }
     }
   }
-  float mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < kVocab; ++j) { lg[j] += p.bfc[j]; mx = fmaxf(mx, lg[j]); }
-  // softmax (networks.py:238), float32
-  float ex[kVocab], sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < kVocab; ++j) { ex[j] = expf(lg[j] - mx); sum += ex[j]; }
-  float pr[kVocab], pmax = -1.f;
-  int arg = 0;
-#pragma unroll
-  for (int j = 0; j < kVocab; ++j) {
-    pr[j] = ex[j] / sum;
-    if (pr[j] > pmax) { pmax = pr[j]; arg = j; }  // first maximum wins (np.argmax)
-  }
-  // quick_inference.py:378-389
-  const float err = 1.f - pmax;
-  float qf = -10.f * log10f(err);  // err == 0 -> +inf
-  int qi;
-  if (p.calib_enabled && p.calib_thr != 0.f) {
-    // np.where branch of calibrate_quality_scores promotes to float64 (calibration_lib.py:93-99)
-    const double qd = (double)qf;
-    const bool above = qd > p.calib_thr64;
-    const double qc = qd * (above ? p.calib_w64 : 1.0) + (above ? p.calib_b64 : 0.0);
-    qi = (int)rint(fmin(qc, (double)p.max_q));
-  } else {
-    if (p.calib_enabled) qf = qf * p.calib_w + p.calib_b;    // float32 path (threshold == 0)
-    qi = (int)rintf(fminf(qf, p.max_q));                     // np.round: half to even
-  }
-  qi = qi < 0 ? 0 : qi;
-  const char vocab[kVocab] = {' ', 'A', 'T', 'C', 'G'};
-  p.bases[oidx] = (uint8_t)vocab[arg];
-  p.quals[oidx] = (uint8_t)(qi + 33);
-  if (p.probs) {
-#pragma unroll
-    for (int j = 0; j < kVocab; ++j) p.probs[oidx * kVocab + j] = pr[j];
-  }
-  if (p.logits) {
-#pragma unroll
-    for (int j = 0; j < kVocab; ++j) p.logits[oidx * kVocab + j] = lg[j];
-  }
+  head_finish(p, lg, oidx);
 }
 
 // =====================================================================================
@@ -2608,7 +2614,7 @@ void launch_qkv_attn(const __nv_bfloat16* a_img, const uint8_t* w_img, int ntile
   else cudaLaunchKernelEx(&cfg, qkv_attn_pair_kernel<false>, a_img, w_img, ntiles, L, win, att);
 }
 
-void launch_stack(float* x, int ntiles, int L, int win, const StackParams& p, cudaStream_t st) {
+void launch_stack(float* x, int ntiles, int L, int win, const StackParams& p, const HeadParams& hp, cudaStream_t st) {
   static int max_pairs = 0;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(StackCfg::kThreads);
@@ -2624,7 +2630,7 @@ void launch_stack(float* x, int ntiles, int L, int win, const StackParams& p, cu
   int pairs = (ntiles + 1) / 2;
   if (pairs > max_pairs) pairs = max_pairs;
   cfg.gridDim = dim3(pairs * 2);
-  cudaLaunchKernelEx(&cfg, stack_pair_kernel, x, ntiles, L, win, p);
+  cudaLaunchKernelEx(&cfg, stack_pair_kernel, x, ntiles, L, win, p, hp);
 }
 
 void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int Lw, int win, int nwindows,

@@ -42,8 +42,10 @@ void launch_ffn_pair(const __nv_bfloat16* a_img, const uint8_t* w2img, const flo
 void launch_ffn(const __nv_bfloat16* a_img, const uint8_t* w_img, const float* b1, int ff, int ntiles,
                 const RowEpi& epi, cudaStream_t st);
 // The whole encoder stack in one launch (window-aligned tiles, attn_win_size in [1,16]): x is the fp32 residual
-// image written by the embedding kernel; on return it holds the output of the last layer (input of launch_head).
-void launch_stack(float* x, int ntiles, int L, int win, const StackParams& p, cudaStream_t st);
+// image written by the embedding kernel.  hp.bases != null: the head (final LayerNorm, fc1, softmax, argmax, Phred,
+// calibration, ASCII) runs in the kernel's tail and x is not written back; otherwise x returns the output of the last
+// layer for launch_head.
+void launch_stack(float* x, int ntiles, int L, int win, const StackParams& p, const HeadParams& hp, cudaStream_t st);
 int read_ffn_trace(unsigned long long* out, int n);
 void launch_head(const HeadParams& p, int ntiles, cudaStream_t st);
 

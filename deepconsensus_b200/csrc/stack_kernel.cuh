@@ -101,7 +101,8 @@ __device__ __forceinline__ void stack_wait(uint64_t* bar, uint32_t parity, int t
 #endif
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(StackCfg::kThreads, 1)
-stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __grid_constant__ StackParams P) {
+stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __grid_constant__ StackParams P,
+                  const __grid_constant__ HeadParams HP) {
   using C = StackCfg;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem + C::kOffA;
@@ -719,11 +720,12 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
         }
       }
 
-      // ---- after the last layer: x <- Y + b2 (global, for the head kernel)
-      SW(y_full, k_y & 1, 918); ++k_y;
+      // ---- after the last layer
+      SW(y_full, k_y & 1, 917); ++k_y;
       tc_fence_after();
-      {
-        const float* __restrict__ b2 = P.b2[NL - 1];
+      const float* __restrict__ b2 = P.b2[NL - 1];
+      if (HP.bases == nullptr) {
+        // x <- Y + b2 (global), for a separate head kernel
 #pragma unroll 3
         for (int cb = 0; cb < 9; ++cb) {
           uint32_t acc[16];
@@ -742,6 +744,72 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
             }
           }
         }
+      } else {
+        // ---- fused head (encoder_stack.py:197, networks.py:342,238, quick_inference.py:377-414): final LayerNorm of
+        // Y + b2, the five fc1 logits, then head_finish.  Two threads per row: statistics and partial logits are
+        // exchanged through the (now idle) staging area, which also holds gamma | beta | Wfc for broadcast reads.
+        float* sG = reinterpret_cast<float*>(sS + 8192);          // [288] gamma, [288] beta, [280*5] Wfc
+        float* sBt = sG + kDP;
+        float* sW = sBt + kDP;
+        for (int i = threadIdx.x - 128; i < kD; i += 256) { sG[i] = __ldg(HP.ln_g + i); sBt[i] = __ldg(HP.ln_b + i); }
+        for (int i = threadIdx.x - 128; i < kD * kVocab; i += 256) sW[i] = __ldg(HP.wfc + i);
+        float s1 = 0.f, s2 = 0.f, shift = 0.f;
+#pragma unroll 1
+        for (int cb = 0; cb < 9; ++cb) {
+          uint32_t acc[16];
+          tmem_ld16(tmem_row + C::kTmemY + (cb0 + cb) * 16, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = (cb0 + cb) * 16 + i;
+            if (col < kD) {
+              const float v = __uint_as_float(acc[i]) + __ldg(b2 + col);
+              if (cb == 0 && i == 0) shift = v;
+              const float dlt = v - shift;
+              s1 += dlt;
+              s2 += dlt * dlt;
+            }
+          }
+        }
+        sStat[halfsel * kTileM + r] = make_float4(shift, s1, s2, 0.f);
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // also: gamma / beta / Wfc staged
+        const float4 o = sStat[(1 - halfsel) * kTileM + r];
+        const float n_me = halfsel ? (float)(kD - 144) : 144.f, n_o = halfsel ? 144.f : (float)(kD - 144);
+        const float mean = (n_me * shift + s1 + n_o * o.x + o.y) * (1.f / kD);
+        const float d_me = mean - shift, d_o = mean - o.x;
+        const float ss = (s2 - 2.f * d_me * s1 + n_me * d_me * d_me) + (o.z - 2.f * d_o * o.y + n_o * d_o * d_o);
+        const float rstd = rsqrtf(fmaxf(ss * (1.f / kD), 0.f) + 1e-6f);
+        float lg[kVocab];
+#pragma unroll
+        for (int j = 0; j < kVocab; ++j) lg[j] = 0.f;
+#pragma unroll 1
+        for (int cb = 0; cb < 9; ++cb) {
+          uint32_t acc[16];
+          tmem_ld16(tmem_row + C::kTmemY + (cb0 + cb) * 16, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = (cb0 + cb) * 16 + i;
+            if (col < kD) {
+              const float z = (__uint_as_float(acc[i]) + __ldg(b2 + col) - mean) * rstd * sG[col] + sBt[col];
+#pragma unroll
+              for (int j = 0; j < kVocab; ++j) lg[j] = fmaf(z, sW[col * kVocab + j], lg[j]);
+            }
+          }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");     // everyone has read the statistics
+        float* sL = reinterpret_cast<float*>(sS);          // partial logits of the upper column half: [128][8]
+        if (halfsel) {
+#pragma unroll
+          for (int j = 0; j < kVocab; ++j) sL[r * 8 + j] = lg[j];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (!halfsel && valid && r < L) {
+#pragma unroll
+          for (int j = 0; j < kVocab; ++j) lg[j] += sL[r * 8 + j];
+          head_finish(HP, lg, (size_t)tile * L + r);       // window-aligned layout: tile == window, row == position
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");     // staging area free for the next tile
       }
       tc_fence_before();
     }

@@ -161,7 +161,7 @@ def test_run_model_on_examples_and_stitch(engine_mod, golden_dir):
 
 
 def test_unfused_fallback_paths_agree_with_fused(engine_mod):
-  """DCB_STACK / DCB_FUSE_OPROJ / DCB_FUSE_EMBED / DCB_FUSE_QA / DCB_ALIGN / DCB_FFN_PAIR select measured alternatives of the same math;
+  """DCB_STACK / DCB_FUSE_HEAD / DCB_FUSE_OPROJ / DCB_FUSE_EMBED / DCB_FUSE_QA / DCB_ALIGN / DCB_FFN_PAIR select measured alternatives of the same math;
   they are read when an engine is created, so flip them around model construction."""
   p = params_lib.synthetic_params(20, 120, num_hidden_layers=2)
   w = weights_lib.init_weights(p, seed=21)
@@ -170,6 +170,7 @@ def test_unfused_fallback_paths_agree_with_fused(engine_mod):
   outs = {}
   for name, env in (("fused", {}),                                     # default: whole stack in one kernel
                     ("per_layer", {"DCB_STACK": "0"}),                  # QKV+attention and out-proj+FFN kernels per layer
+                    ("fused_head", {"DCB_FUSE_HEAD": "1"}),             # head in the tail of the stack kernel
                     ("unfused", {"DCB_FUSE_OPROJ": "0", "DCB_FUSE_EMBED": "0", "DCB_FUSE_QA": "0"}),
                     ("packed", {"DCB_ALIGN": "0"}),                     # windows packed back to back, separate QKV / attention
                     ("single_cta", {"DCB_FFN_PAIR": "0", "DCB_FUSE_QA": "0"}),
@@ -188,6 +189,7 @@ def test_unfused_fallback_paths_agree_with_fused(engine_mod):
           os.environ[k] = v
     assert np.abs(outs[name] - ref).max() <= LOGIT_TOL_FP32, name
   assert np.abs(outs["fused"] - outs["per_layer"]).max() < 0.05
+  assert np.abs(outs["fused"] - outs["fused_head"]).max() < 1e-3
   assert np.abs(outs["fused"] - outs["unfused"]).max() < 0.05
   assert np.abs(outs["fused"] - outs["packed"]).max() < 0.05
   assert np.abs(outs["qkv2"] - outs["unfused"]).max() < 0.05
@@ -246,3 +248,42 @@ def test_pipelined_submit_wait_matches_blocking_forward(engine_mod):
   o2 = model.wait(h2)
   assert np.array_equal(o0["bases"], blocking[0]["bases"]) and np.array_equal(o2["quals"], blocking[2]["quals"])
   model.close()
+
+
+def test_full_size_properties_c2_batch_1024(engine_mod):
+  """BASELINE configs[1] at its full size (1024 windows, 20 x 120, 6 layers): too big for the oracle in test time, so the
+  CUDA path is checked through size-independent properties -- windows are independent units, hence
+  (a) permuting the batch permutes the outputs bit-exactly, (b) any sub-batch reproduces its rows of the full batch
+  bit-exactly (different tile -> SM assignment, different pairing), (c) probabilities sum to one, (d) the device epilogue
+  (argmax / Phred / calibration / ASCII) is exact integer work on the device's own probabilities, (e) a 16-window slice
+  agrees with the oracle."""
+  p = params_lib.synthetic_params(20, 120)
+  w = weights_lib.init_weights(p, seed=101)
+  B = 1024
+  rows = synthetic.make_rows(p, B, seed=102)
+  cal = calibration.parse_calibration_string(CAL)
+  model = engine_mod.B200Model(p, w, max_batch=B, calibration=cal)
+  full = model.forward(rows, want_probs=True, strict_input=False)
+  again = model.forward(rows, want_probs=True, strict_input=False)
+  assert np.array_equal(full["probs"], again["probs"]) and np.array_equal(full["quals"], again["quals"])
+  rng = np.random.default_rng(7)
+  perm = rng.permutation(B)
+  permuted = model.forward(rows[perm], want_probs=True, strict_input=False)
+  assert np.array_equal(permuted["probs"], full["probs"][perm])
+  assert np.array_equal(permuted["bases"], full["bases"][perm]) and np.array_equal(permuted["quals"], full["quals"][perm])
+  for lo, hi in ((0, 1), (5, 12), (300, 811), (1023, 1024)):
+    sub = model.forward(rows[lo:hi], want_probs=True, strict_input=False)
+    assert np.array_equal(sub["probs"], full["probs"][lo:hi]), (lo, hi)
+    assert np.array_equal(sub["bases"], full["bases"][lo:hi]) and np.array_equal(sub["quals"], full["quals"][lo:hi])
+  assert np.isfinite(full["probs"]).all() and np.abs(full["probs"].sum(-1) - 1).max() < 1e-5
+  y, q = opost.quality_from_probs(full["probs"], 93, (cal.threshold, cal.w, cal.b))
+  sb, sq = opost.to_ascii(y, q)
+  assert np.array_equal(sb, full["bases"])
+  assert (sq == full["quals"]).mean() > 0.999 and np.abs(sq.astype(int) - full["quals"].astype(int)).max() <= 1
+  ref = omodel.forward(rows[500:516], p, w)
+  model.close()
+  m2 = engine_mod.B200Model(p, w, max_batch=16, calibration=cal)
+  o16 = m2.forward(rows[500:516], want_probs=True, want_logits=True, strict_input=False)
+  m2.close()
+  assert np.array_equal(o16["probs"], full["probs"][500:516])
+  assert np.abs(o16["logits"] - ref["logits"]).max() <= LOGIT_TOL_FP32
