@@ -58,6 +58,7 @@ struct RowEpi {
   __nv_bfloat16* xb;     // bf16 operand image for the next GEMM (may be null: skip)
   const float* bias;     // [288] or null
   const float* pe;       // [Lw][288] or null (rows >= max_length are zero)
+  const float* pe_img;   // the same table as a residual image [72][128][4] (tile == window), or null
   const float* ln_g;     // [288] or null  (null => xb = bf16(x_new))
   const float* ln_b;     // [288]
   int has_xold;

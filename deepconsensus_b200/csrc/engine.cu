@@ -90,6 +90,7 @@ struct dcb_engine {
   __nv_bfloat16* d_tables = nullptr;
   __nv_bfloat16* d_wc = nullptr;
   float* d_pe = nullptr;
+  float* d_pe_img = nullptr;   // same table in residual-image order (window-aligned layout only)
   std::vector<LayerDev> layers;
   float *d_fln_g = nullptr, *d_fln_b = nullptr, *d_wfc = nullptr, *d_bfc = nullptr;
   // workspace
@@ -392,6 +393,14 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
         }
     }
     if ((rc = upload(e, &e->d_pe, pe))) return rc;
+    if (e->Lw == kTileM) {
+      // window-aligned layout: every tile sees positions 0..127, so the table can also be laid out like the residual
+      // image [72][128][4] -- a warp of the row epilogue then reads 512 contiguous bytes instead of 32 scattered rows
+      std::vector<float> img((size_t)kTileM * kDP, 0.f);
+      for (int l = 0; l < kTileM; ++l)
+        for (int col = 0; col < kDP; ++col) img[((size_t)(col / 4) * kTileM + l) * 4 + (col & 3)] = pe[(size_t)l * kDP + col];
+      if ((rc = upload(e, &e->d_pe_img, img))) return rc;
+    }
   }
   // ---- encoder layers
   const int ff = c.filter_size;
@@ -666,6 +675,7 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
       // the one-kernel stack builds every operand tile from the residual in TMEM: no bf16 operand image needed
       epi.x = e->d_x; epi.xb = use_stack ? nullptr : e->d_xb; epi.bias = nullptr;
       epi.pe = c.add_pos_encoding ? e->d_pe : nullptr;
+      epi.pe_img = c.add_pos_encoding ? e->d_pe_img : nullptr;
       epi.ln_g = (c.rezero || use_stack) ? nullptr : e->layers[0].ln_g[0];
       epi.ln_b = (c.rezero || use_stack) ? nullptr : e->layers[0].ln_b[0];
       epi.has_xold = 0; epi.L = Lw;

@@ -22,6 +22,17 @@
 
 namespace dcb {
 
+// cycle-trace hooks (-DDCB_TRACE) and the device buffer scripts/gpu_trace*.py read back
+__device__ unsigned long long g_ffn_trace[256 * 16];
+#ifdef DCB_TRACE
+#define TRACE_T0() long long _t0 = clock64()
+#define TRACE_ADD(var) do { long long _t1 = clock64(); (var) += _t1 - _t0; _t0 = _t1; } while (0)
+#else
+#define TRACE_T0() do {} while (0)
+#define TRACE_ADD(var) do {} while (0)
+#endif
+
+
 // =====================================================================================
 // embed
 // =====================================================================================
@@ -145,6 +156,22 @@ __device__ __forceinline__ void row_prefetch_start(const RowEpi& e, int tile, in
   if (e.has_xold) {
 #pragma unroll
     for (int k = 0; k < kRowPF; ++k) row_prefetch_issue(e, tile, r, k, pf.buf[k]);
+  } else if (e.pe) {
+    // no residual input (the condenser GEMM): the registers carry the token's positional-encoding row instead
+    if (e.pe_img) {
+      const float4* pi = reinterpret_cast<const float4*>(e.pe_img) + r;
+#pragma unroll
+      for (int k = 0; k < kRowPF; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pf.buf[k][i] = __ldg(pi + (size_t)(k * 4 + i) * kTileM);
+    } else {
+      const int l = (tile * kTileM + r) % e.L;
+      const float4* pr = reinterpret_cast<const float4*>(e.pe + (size_t)l * kDP);
+#pragma unroll
+      for (int k = 0; k < kRowPF; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pf.buf[k][i] = __ldg(pr + k * 4 + i);
+    }
   }
 }
 
@@ -183,12 +210,32 @@ __device__ __forceinline__ RowStats row_epilogue_pass1(const RowEpi& e, uint32_t
 #endif
     float pev[16];
     if (e.pe) {
-      // one token's 16 positional values are 64 contiguous bytes: 4 x 128-bit loads (rows differ per lane)
+      // one token's 16 positional values are 64 contiguous bytes: 4 x 128-bit loads (rows differ per lane, so every
+      // load is its own L2 round trip).  Without a residual to read (the embedding GEMM) the RowPrefetch registers
+      // carry the positional rows instead, kRowPF blocks ahead (row_prefetch_start).
       const float4* pr = reinterpret_cast<const float4*>(e.pe + (size_t)l * kDP + cb * 16);
+      if (!e.has_xold) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 t = __ldg(pr + i);
-        pev[4 * i + 0] = t.x; pev[4 * i + 1] = t.y; pev[4 * i + 2] = t.z; pev[4 * i + 3] = t.w;
+        for (int i = 0; i < 4; ++i) {
+          const float4 t = pf.buf[cb % kRowPF][i];
+          pev[4 * i + 0] = t.x; pev[4 * i + 1] = t.y; pev[4 * i + 2] = t.z; pev[4 * i + 3] = t.w;
+        }
+        if (cb + kRowPF < kDP / 16) {
+          if (e.pe_img) {
+            const float4* pi = reinterpret_cast<const float4*>(e.pe_img) + r;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pf.buf[cb % kRowPF][i] = __ldg(pi + (size_t)((cb + kRowPF) * 4 + i) * kTileM);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pf.buf[cb % kRowPF][i] = __ldg(pr + kRowPF * 4 + i);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 t = __ldg(pr + i);
+          pev[4 * i + 0] = t.x; pev[4 * i + 1] = t.y; pev[4 * i + 2] = t.z; pev[4 * i + 3] = t.w;
+        }
       }
     }
 #pragma unroll
@@ -522,11 +569,56 @@ embed_condense_kernel(const float* __restrict__ rows, int R, int L, int Lw, int 
     // ------------------------------------------------------------- builders (256 threads)
     const int bt = threadIdx.x - 128;   // 0..255
     uint32_t n = 0;
+    long long t_ids = 0, t_aempty = 0, t_build = 0;
+    const long long t_begin = clock64();
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      TRACE_T0();
       // every slab of the previous tile has been built (program order), but its last reads of s_ids
       // happen in other builder threads: synchronise the builders before overwriting the ids
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      {
+      if (Lw == kTileM && (L & 3) == 0) {
+        // window-aligned layout (tile == window): the tile's input is one contiguous [R][L] block.  Item = (row ru,
+        // 4 consecutive positions): all of a thread's ~11 float4 loads are issued before the first is used (one
+        // exposed memory latency instead of six dependent batches), a warp reads 512 contiguous bytes.
+        const bool wvalid = (size_t)tile * kTileM < (size_t)M;
+        const float4* base4 = reinterpret_cast<const float4*>(rows + (size_t)(wvalid ? tile : 0) * R * L);
+        constexpr int kMaxItems = 12;                      // ceil(R * 32 / 256) for R <= 96
+        const int nitems = (R * 32 + 255) / 256;
+        float4 f[kMaxItems];
+#pragma unroll
+        for (int k = 0; k < kMaxItems; ++k) {
+          const int item = bt + k * 256;
+          const int ru = item >> 5, g = item & 31;
+          f[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < nitems && ru < R && wvalid && 4 * g < L) f[k] = __ldg(base4 + ((size_t)ru * L + 4 * g) / 4);
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxItems; ++k) {
+          const int item = bt + k * 256;
+          const int ru = item >> 5, g = item & 31;
+          if (k < nitems && ru < R) {
+            const EmbedRow m = rowmeta[ru];
+            const float vals[4] = {f[k].x, f[k].y, f[k].z, f[k].w};
+            uint32_t ids[4];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              int id = 0;
+              if (wvalid && 4 * g + q4 < L) {
+                float v = vals[q4];
+                if (m.clip_hi > 0.f) v = fminf(fmaxf(v, 0.f), m.clip_hi);  // format_rows (data_providers.py:151-162)
+                v += (float)m.shift;                                         // networks.py:495
+                id = (int)v;                                                 // tf.cast(float32 -> int32) truncates
+                if (id < 0 || id >= m.vocab) {
+                  atomicOr(status, 1);
+                  id = id < 0 ? 0 : m.vocab - 1;
+                }
+              }
+              ids[q4] = (uint32_t)id;
+            }
+            *reinterpret_cast<uint2*>(&s_ids[ru * kTileM + 4 * g]) = make_uint2(ids[0] | (ids[1] << 16), ids[2] | (ids[3] << 16));
+          }
+        }
+      } else {
         // thread = (token r, input rows rr0, rr0+2, ...): 8 independent global loads in flight per batch
         const int r = bt & (kTileM - 1), rr0 = bt >> 7;
         const int tok = tile * kTileM + r;
@@ -563,10 +655,12 @@ embed_condense_kernel(const float* __restrict__ rows, int R, int L, int Lw, int 
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      TRACE_ADD(t_ids);
       for (int sl = 0; sl < nslabs; ++sl, ++n) {
         const uint32_t b = n & 1;
         const int kh = min(C::kSlabK, ksteps - sl * C::kSlabK);
         mbar_wait(&a_empty[b], ((n >> 1) & 1) ^ 1);
+        TRACE_ADD(t_aempty);
         uint4* dst = reinterpret_cast<uint4*>(sAslab + b * C::kASlabBytes);
         for (int idx = bt; idx < kh * 2 * kTileM; idx += 256) {
           const int kcl = idx / kTileM, r = idx % kTileM;
@@ -599,8 +693,15 @@ embed_condense_kernel(const float* __restrict__ rows, int R, int L, int Lw, int 
         }
         fence_proxy_async_smem();
         mbar_arrive(&a_full[b]);
+        TRACE_ADD(t_build);
       }
     }
+#ifdef DCB_TRACE
+    if (bt == 0 && blockIdx.x < 256) {
+      unsigned long long* tr = g_ffn_trace + blockIdx.x * 16;
+      tr[0] = clock64() - t_begin; tr[1] = t_ids; tr[2] = t_aempty; tr[3] = t_build;
+    }
+#endif
   } else {
     setmaxnreg_inc<216>();
     // ------------------------------------------------------------- row epilogue (4 warps)
@@ -608,13 +709,21 @@ embed_condense_kernel(const float* __restrict__ rows, int R, int L, int Lw, int 
     const int r = q * 32 + lane;
     const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t it = 0;
+    long long t_accfull = 0, t_epi = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       RowPrefetch pf;
+      row_prefetch_start(epi, tile, r, pf);        // positional rows in flight while the GEMM finishes
+      TRACE_T0();
       mbar_wait(acc_full, it & 1);
+      TRACE_ADD(t_accfull);
       tc_fence_after();
       const RowStats st = row_epilogue_pass1(epi, tmem_row, tile, r, pf);
       tc_fence_before();
       mbar_arrive(acc_empty);
+      TRACE_ADD(t_epi);
+#ifdef DCB_TRACE
+      if (warp == 12 && lane == 0 && blockIdx.x < 256) { unsigned long long* tr = g_ffn_trace + blockIdx.x * 16; tr[4] = t_accfull; tr[5] = t_epi; }
+#endif
       if (epi.ln_g && epi.xb) row_epilogue_pass2<false>(epi, tile, r, st.mean, st.rstd);
     }
   }
@@ -841,14 +950,7 @@ constexpr int kFfnThreads = 512;
 
 // Optional cycle trace (build with -DDCB_TRACE): per CTA, cycles the MMA thread and one
 // hidden-epilogue warp spend in each wait.  Read back with dcb_debug_trace().
-__device__ unsigned long long g_ffn_trace[256 * 16];
-#ifdef DCB_TRACE
-#define TRACE_T0() long long _t0 = clock64()
-#define TRACE_ADD(var) do { long long _t1 = clock64(); (var) += _t1 - _t0; _t0 = _t1; } while (0)
-#else
-#define TRACE_T0() do {} while (0)
-#define TRACE_ADD(var) do {} while (0)
-#endif
+
 
 template <int CS>
 __global__ void __launch_bounds__(kFfnThreads, 1)
