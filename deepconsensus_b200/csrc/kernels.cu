@@ -357,8 +357,8 @@ gemm_kernel(const __nv_bfloat16* __restrict__ a_img, const __nv_bfloat16* __rest
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------- MMA issuer (whole warp; the elected lane issues)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, kNC);
       uint32_t slot = 0, phase = 0, it = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
@@ -376,13 +376,13 @@ gemm_kernel(const __nv_bfloat16* __restrict__ a_img, const __nv_bfloat16* __rest
             for (int j = 0; j < NCH; ++j) {
               const uint64_t bdesc = make_kc16_desc(sb + kk * Cfg::kBBytesPerK + j * kNC * 16,
                                                     Cfg::kNItem * 16, 128);
-              umma_bf16_ss(tmem_base + j * kNC, adesc, bdesc, idesc, (s | kk) != 0);
+              umma_bf16_ss_warp(tmem_base + j * kNC, adesc, bdesc, idesc, (s | kk) != 0);
             }
           }
-          umma_commit(&empty[slot]);
+          umma_commit_warp(&empty[slot]);
           if (++slot == Cfg::kStages) { slot = 0; phase ^= 1; }
         }
-        umma_commit(acc_full);
+        umma_commit_warp(acc_full);
       }
     }
   } else {
@@ -1409,7 +1409,7 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
       }
     }
    } else if (warp == 1 || warp == 2) {
-    if (lane == 0) {
+    if (leader || lane == 0) {   // leader: whole warp walks the issue program (elected lane issues); peer: relay thread
       if (leader) {
         // ----------------------------------------------------------- UMMA issuers (leader only)
         // Two issuing threads share the tensor pipe: warp 1 issues the out-proj and every GEMM1,
@@ -1430,11 +1430,11 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
         };
         auto gemm1 = [&](uint32_t nn) {
           TRACE_T0();
-          mbar_wait_cluster(h_free, (nn & 1) ^ 1);
+          mbar_wait(h_free, (nn & 1) ^ 1);
           TRACE_ADD(t_hfree);
           tc_fence_after();
           for (int s = 0; s < C::kW1Stages; ++s) {
-            mbar_wait_cluster(&full[slot], phase);
+            mbar_wait(&full[slot], phase);
             TRACE_ADD(t_full);
             tc_fence_after();
             const uint32_t sb = smem_u32(sRing + slot * C::kSlotBytes);
@@ -1443,23 +1443,23 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
               const int kstep = s * C::kW1StageK + kk;
               const uint64_t adesc = make_kc16_desc(a_addr + kstep * 4096, kTileM * 16, 128);
               const uint64_t bdesc = make_kc16_desc(sb + kk * (2 * C::kW1Rows * 16), C::kW1Rows * 16, 128);
-              umma_bf16_ss_pair(tmem_base + C::kTmemH, adesc, bdesc, idesc_h, kstep != 0);
+              umma_bf16_ss_pair_warp(tmem_base + C::kTmemH, adesc, bdesc, idesc_h, kstep != 0);
             }
-            umma_commit_pair(&empty[slot], kBoth);
+            umma_commit_pair_warp(&empty[slot], kBoth);
             if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
             TRACE_ADD(t_issue);
           }
-          umma_commit_pair(h_full, kBoth);
+          umma_commit_pair_warp(h_full, kBoth);
         };
         auto gemm2 = [&](uint32_t nn) {
           const uint32_t b = nn & 1;
           TRACE_T0();
-          mbar_wait_cluster(&hs_full[b], (nn >> 1) & 1);
+          mbar_wait(&hs_full[b], (nn >> 1) & 1);
           TRACE_ADD(t_hsfull);
           tc_fence_after();
           const uint32_t h_addr = smem_u32(sH + b * C::kHBytes);
           for (int s = 0; s < C::kW2Stages; ++s) {
-            mbar_wait_cluster(&full[slot], phase);
+            mbar_wait(&full[slot], phase);
             TRACE_ADD(t_full);
             tc_fence_after();
             const uint32_t sb = smem_u32(sRing + slot * C::kSlotBytes);
@@ -1471,27 +1471,27 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
               for (int j = 0; j < 2; ++j) {
                 const uint64_t bdesc = make_kc16_desc(sb + kk * (2 * C::kW2Rows * 16) + j * (kNC / 2) * 16,
                                                       C::kW2Rows * 16, 128);
-                umma_bf16_ss_pair(tmem_base + C::kTmemY + j * kNC, adesc, bdesc, idesc_y, true);
+                umma_bf16_ss_pair_warp(tmem_base + C::kTmemY + j * kNC, adesc, bdesc, idesc_y, true);
               }
             }
-            umma_commit_pair(&empty[slot], kBoth);
+            umma_commit_pair_warp(&empty[slot], kBoth);
             if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
             TRACE_ADD(t_issue);
           }
-          umma_commit_pair(&hs_free[b], kBoth);
+          umma_commit_pair_warp(&hs_free[b], kBoth);
         };
         for (int ti = 0; ti < rounds; ++ti) {
           if (g1) {
-            { TRACE_T0(); mbar_wait_cluster(a_full, ti & 1); TRACE_ADD(t_afull); }
+            { TRACE_T0(); mbar_wait(a_full, ti & 1); TRACE_ADD(t_afull); }
             tc_fence_after();
             if constexpr (kFuse) {
               // Y (= x_old, stored by the row warps) += att * Wo^T
               TRACE_T0();
-              mbar_wait_cluster(y_empty, ti & 1);
+              mbar_wait(y_empty, ti & 1);
               TRACE_ADD(t_yempty);
               tc_fence_after();
               for (int s = 0; s < C::kWoStages; ++s) {
-                mbar_wait_cluster(&full[slot], phase);
+                mbar_wait(&full[slot], phase);
                 tc_fence_after();
                 const uint32_t sb = smem_u32(sRing + slot * C::kSlotBytes);
 #pragma unroll
@@ -1502,22 +1502,22 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
                   for (int j = 0; j < 2; ++j) {
                     const uint64_t bdesc = make_kc16_desc(sb + kk * (2 * C::kW2Rows * 16) + j * (kNC / 2) * 16,
                                                           C::kW2Rows * 16, 128);
-                    umma_bf16_ss_pair(tmem_base + C::kTmemY + j * kNC, adesc, bdesc, idesc_y, true);
+                    umma_bf16_ss_pair_warp(tmem_base + C::kTmemY + j * kNC, adesc, bdesc, idesc_y, true);
                   }
                 }
-                umma_commit_pair(&empty[slot], kBoth);
+                umma_commit_pair_warp(&empty[slot], kBoth);
                 if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
               }
-              umma_commit_pair(ymid_full, kBoth);
+              umma_commit_pair_warp(ymid_full, kBoth);
               TRACE_ADD(t_oproj);
-              mbar_wait_cluster(a2_full, ti & 1);   // FFN operand tile written by both CTAs' row warps
+              mbar_wait(a2_full, ti & 1);   // FFN operand tile written by both CTAs' row warps
               TRACE_ADD(t_a2full);
               tc_fence_after();
             }
             gemm1(n);
             for (int c = 0; c < nchunks; ++c) {
               if (c + 1 < nchunks) gemm1(n + c + 1);
-              else umma_commit_pair(a_empty, kBoth);   // every UMMA that reads sA has been issued
+              else umma_commit_pair_warp(a_empty, kBoth);   // every UMMA that reads sA has been issued
               skip(C::kW2Stages);
             }
           } else {
@@ -1526,17 +1526,17 @@ ffn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __restri
             for (int c = 0; c < nchunks; ++c) {
               if (c + 1 < nchunks) skip(C::kW1Stages);
               if (!kFuse && c == 0) {
-                mbar_wait_cluster(y_empty, ti & 1);   // "Y holds x_old": both CTAs' row warps initialised it
+                mbar_wait(y_empty, ti & 1);   // "Y holds x_old": both CTAs' row warps initialised it
                 tc_fence_after();
               }
               gemm2(n + c);
             }
-            umma_commit_pair(y_full, kBoth);
+            umma_commit_pair_warp(y_full, kBoth);
           }
           n += nchunks;
         }
 #ifdef DCB_TRACE
-        if (g1 && blockIdx.x < 256) {
+        if (g1 && lane == 0 && blockIdx.x < 256) {
           unsigned long long* tr = g_ffn_trace + blockIdx.x * 16;
           tr[0] = clock64() - t_begin; tr[1] = t_hfree; tr[2] = t_full; tr[3] = t_hsfull;
           tr[4] = t_issue; tr[5] = t_afull; tr[6] = t_yempty; tr[7] = t_a2full; tr[15] = t_oproj;
@@ -2168,7 +2168,7 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (leader || lane == 0) {   // leader: whole warp, elected lane issues; peer: relay thread
       uint32_t slot = 0, phase = 0;
       if (leader) {
         constexpr uint32_t idesc = make_idesc_bf16(2 * kTileM, kNC);
@@ -2178,15 +2178,15 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
         long long t_afull = 0, t_accfree = 0, t_full = 0, t_issue = 0;
         const long long t_begin = clock64();
         for (int ti = 0; ti < rounds; ++ti) {
-          { TRACE_T0(); mbar_wait_cluster(a_full, ti & 1); TRACE_ADD(t_afull); }
+          { TRACE_T0(); mbar_wait(a_full, ti & 1); TRACE_ADD(t_afull); }
           tc_fence_after();
           for (int h = 0; h < kHeads; ++h, ++hi) {
             TRACE_T0();
-            mbar_wait_cluster(acc_free, (hi & 1) ^ 1);
+            mbar_wait(acc_free, (hi & 1) ^ 1);
             TRACE_ADD(t_accfree);
             tc_fence_after();
             for (int ks = 0; ks < kDP / 16; ++ks) {
-              mbar_wait_cluster(&full[slot], phase);
+              mbar_wait(&full[slot], phase);
               TRACE_ADD(t_full);
               tc_fence_after();
               const uint32_t sb = smem_u32(sRing + slot * C::kStageBytes);
@@ -2194,18 +2194,18 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
 #pragma unroll
               for (int m = 0; m < 3; ++m) {
                 const uint64_t bdesc = make_kc16_desc(sb + m * (kDHP / 2) * 16, C::kRows * 16, 128);
-                umma_bf16_ss_pair(tmem_base + m * kDHP, adesc, bdesc, idesc, ks != 0);
+                umma_bf16_ss_pair_warp(tmem_base + m * kDHP, adesc, bdesc, idesc, ks != 0);
               }
-              umma_commit_pair(&empty[slot], kBoth);
+              umma_commit_pair_warp(&empty[slot], kBoth);
               if (++slot == C::kSlots) { slot = 0; phase ^= 1; }
               TRACE_ADD(t_issue);
             }
-            umma_commit_pair(acc_full, kBoth);
+            umma_commit_pair_warp(acc_full, kBoth);
           }
-          umma_commit_pair(a_empty, kBoth);
+          umma_commit_pair_warp(a_empty, kBoth);
         }
 #ifdef DCB_TRACE
-        if (blockIdx.x < 108) {
+        if (lane == 0 && blockIdx.x < 108) {
           unsigned long long* tr = g_ffn_trace + (blockIdx.x % 108 + 148) * 16;
           tr[0] = clock64() - t_begin; tr[1] = t_afull; tr[2] = t_accfree; tr[3] = t_full; tr[4] = t_issue; tr[7] = rounds;
         }
