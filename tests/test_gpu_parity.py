@@ -287,3 +287,24 @@ def test_full_size_properties_c2_batch_1024(engine_mod):
   m2.close()
   assert np.array_equal(o16["probs"], full["probs"][500:516])
   assert np.abs(o16["logits"] - ref["logits"]).max() <= LOGIT_TOL_FP32
+
+
+@pytest.mark.parametrize("layers,ff,rezero,win,L,B", [
+    (1, 128, True, 12, 120, 3),      # one layer, one hidden chunk: the FFN stage program never reaches the tail slots
+    (3, 640, False, 16, 128, 4),     # pre-LN, band at the two-pass limit, window exactly one tile
+    (8, 256, True, 1, 64, 5),        # deepest stack the one-kernel path takes, narrowest band, short windows
+    (9, 256, True, 12, 100, 2),      # deeper than kMaxLayers: falls back to the per-layer kernels
+])
+def test_stack_kernel_corner_shapes(engine_mod, layers, ff, rezero, win, L, B):
+  p = params_lib.synthetic_params(20, L, num_hidden_layers=layers, rezero=rezero, attn_win_size=win)
+  p.filter_size = ff
+  w = weights_lib.init_weights(p, seed=50 + layers)
+  rows = synthetic.make_rows(p, B, seed=60 + layers)
+  model = engine_mod.B200Model(p, w, max_batch=B)
+  out = model.forward(rows, want_logits=True, strict_input=False)
+  launches = model.last_launches
+  model.close()
+  assert launches == (3 if layers <= 8 else 2 + 2 * layers)
+  ref = omodel.forward(rows, p, w)
+  assert np.isfinite(out["logits"]).all()
+  assert np.abs(out["logits"] - ref["logits"]).max() <= LOGIT_TOL_FP32
