@@ -154,6 +154,32 @@ def run_reference(args, rank, world):
                         e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
 
 
+def bind_to_gpu_numa_node(index: int):
+  """Best effort: run this rank (and therefore allocate its page-locked staging buffers) on the CPUs of the NUMA node
+  the GPU hangs off, so the per-step host->device copies of 8 ranks do not cross the socket interconnect."""
+  try:
+    out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                         capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0].strip().lower()
+    if out.startswith("00000000:"):
+      out = out[4:]                      # sysfs uses a 4-digit PCI domain
+    with open("/sys/bus/pci/devices/%s/numa_node" % out) as f:
+      node = int(f.read().strip())
+    if node < 0:
+      return None
+    with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+      cpus = set()
+      for part in f.read().strip().split(","):
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    allowed = os.sched_getaffinity(0) & cpus
+    if allowed:
+      os.sched_setaffinity(0, allowed)
+      return node
+  except Exception:
+    pass
+  return None
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
@@ -178,6 +204,8 @@ def main():
   if not torch.cuda.is_available():
     raise SystemExit("bench.py: no CUDA device (the dcb200 engine has no CPU fallback)")
   torch.cuda.set_device(local)
+  full_affinity = os.sched_getaffinity(0)
+  numa = bind_to_gpu_numa_node(local)
   if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -331,8 +359,9 @@ def main():
                        call="dcb_submit/dcb_wait, 2 batches in flight (as inference.run_model_on_examples)",
                        blocking_value=total_windows / dt_e2e_blocking,
                        blocking_call="dcb_forward, one batch at a time"),
-              gpu_launches=launches, roofline=roof, clocks=sampler.summary())
+              gpu_launches=launches, roofline=roof, clocks=sampler.summary(), numa_node=numa)
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    os.sched_setaffinity(0, full_affinity)   # the CPU arm may use every host core again
     cores = min(os.cpu_count() or 1, 32)   # torch-CPU on these shapes stops scaling (oversubscribes) beyond ~32 threads
     v, secs = cpu_reference_windows_per_sec(p, w, sample_windows=128, reps=2, threads=cores)
     line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=cores, kind="port",
