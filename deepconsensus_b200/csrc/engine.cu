@@ -100,6 +100,10 @@ struct dcb_engine {
   __nv_bfloat16* d_att = nullptr;
   uint8_t *d_bases = nullptr, *d_quals = nullptr;
   float *d_probs = nullptr, *d_logits = nullptr;
+  // stitch scratch (grown on demand)
+  uint8_t *d_st_in = nullptr, *d_st_out = nullptr;   // [2][cap] each: bases|quals, seq|qual
+  int32_t *d_st_start = nullptr, *d_st_len = nullptr;
+  size_t st_cap = 0, st_zcap = 0;
   float* d_dbg = nullptr;  // [stages][chunk_tiles * x_image]
   std::vector<void*> owned;
 };
@@ -280,6 +284,10 @@ void dcb_destroy(dcb_engine* e) {
   if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void* p : e->owned) cudaFree(p);
+  if (e->d_st_in) cudaFree(e->d_st_in);
+  if (e->d_st_out) cudaFree(e->d_st_out);
+  if (e->d_st_start) cudaFree(e->d_st_start);
+  if (e->d_st_len) cudaFree(e->d_st_len);
   for (auto& sl : e->slots)
     for (auto& pr : sl.prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
@@ -887,6 +895,61 @@ int dcb_debug_residual(dcb_engine* e, int32_t stage, float* out, int64_t out_ele
     for (int col = 0; col < kD; ++col)
       out[(size_t)t * kD + col] = img[(((size_t)tile * kXChunks + col / 4) * kTileM + r) * 4 + col % 4];
   }
+  return DCB_OK;
+}
+
+int dcb_stitch(dcb_engine* e, const uint8_t* bases, const uint8_t* quals, int32_t n_windows, int32_t L,
+               const int32_t* zmw_start, int32_t n_zmw, uint32_t flags,
+               uint8_t* seq_out, uint8_t* qual_out, int32_t* len_out) {
+  if (!e) return DCB_ERR_INVALID;
+  if (n_windows < 0 || L <= 0 || n_zmw < 0) return fail(e, DCB_ERR_INVALID, "dcb_stitch: negative size");
+  if (n_zmw == 0 || n_windows == 0) return DCB_OK;
+  if (!bases || !quals || !zmw_start || !seq_out || !qual_out || !len_out) return fail(e, DCB_ERR_INVALID, "dcb_stitch: null pointer");
+  if (zmw_start[0] < 0 || zmw_start[n_zmw] > n_windows) return fail(e, DCB_ERR_INVALID, "dcb_stitch: zmw_start outside [0, n_windows]");
+  for (int z = 0; z < n_zmw; ++z)
+    if (zmw_start[z + 1] < zmw_start[z]) return fail(e, DCB_ERR_INVALID, "dcb_stitch: zmw_start must be non-decreasing");
+  CU(e, cudaSetDevice(e->cfg.device));
+  const size_t nbytes = (size_t)n_windows * L;
+  const bool in_dev = flags & DCB_ROWS_ON_DEVICE, out_dev = flags & DCB_OUT_ON_DEVICE;
+  cudaStream_t st = e->stream;
+  if (nbytes > e->st_cap) {
+    CU(e, cudaStreamSynchronize(st));
+    if (e->d_st_in) cudaFree(e->d_st_in);
+    if (e->d_st_out) cudaFree(e->d_st_out);
+    e->d_st_in = e->d_st_out = nullptr;
+    e->st_cap = 0;
+    CU(e, cudaMalloc(reinterpret_cast<void**>(&e->d_st_in), 2 * nbytes));
+    CU(e, cudaMalloc(reinterpret_cast<void**>(&e->d_st_out), 2 * nbytes));
+    e->st_cap = nbytes;
+  }
+  if ((size_t)n_zmw + 1 > e->st_zcap) {
+    CU(e, cudaStreamSynchronize(st));
+    if (e->d_st_start) cudaFree(e->d_st_start);
+    if (e->d_st_len) cudaFree(e->d_st_len);
+    e->d_st_start = e->d_st_len = nullptr;
+    e->st_zcap = 0;
+    CU(e, cudaMalloc(reinterpret_cast<void**>(&e->d_st_start), ((size_t)n_zmw + 1) * sizeof(int32_t)));
+    CU(e, cudaMalloc(reinterpret_cast<void**>(&e->d_st_len), ((size_t)n_zmw + 1) * sizeof(int32_t)));
+    e->st_zcap = (size_t)n_zmw + 1;
+  }
+  const uint8_t *db = bases, *dq = quals;
+  if (!in_dev) {
+    CU(e, cudaMemcpyAsync(e->d_st_in, bases, nbytes, cudaMemcpyHostToDevice, st));
+    CU(e, cudaMemcpyAsync(e->d_st_in + e->st_cap, quals, nbytes, cudaMemcpyHostToDevice, st));
+    db = e->d_st_in; dq = e->d_st_in + e->st_cap;
+  }
+  CU(e, cudaMemcpyAsync(e->d_st_start, zmw_start, ((size_t)n_zmw + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  uint8_t* ds = out_dev ? seq_out : e->d_st_out;
+  uint8_t* dqo = out_dev ? qual_out : e->d_st_out + e->st_cap;
+  int32_t* dl = out_dev ? len_out : e->d_st_len;
+  launch_stitch(db, dq, L, e->d_st_start, n_zmw, ds, dqo, dl, st);
+  if (!out_dev) {
+    CU(e, cudaMemcpyAsync(seq_out, ds, nbytes, cudaMemcpyDeviceToHost, st));
+    CU(e, cudaMemcpyAsync(qual_out, dqo, nbytes, cudaMemcpyDeviceToHost, st));
+    CU(e, cudaMemcpyAsync(len_out, dl, (size_t)n_zmw * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
+  CU(e, cudaStreamSynchronize(st));
+  CU(e, cudaGetLastError());
   return DCB_OK;
 }
 

@@ -2819,6 +2819,73 @@ int read_ffn_trace(unsigned long long* out, int n) {
   return cudaMemcpyFromSymbol(out, g_ffn_trace, (size_t)n * sizeof(unsigned long long)) == cudaSuccess ? 0 : -1;
 }
 
+// =====================================================================================
+// stitch: per-read concatenation of windows + gap compaction (stitch_utils.py:51-98)
+// =====================================================================================
+// One CTA per read (ZMW).  Its windows are contiguous in the batch, so the read's input is one span of
+// (w1 - w0) * L bytes in `bases` / `quals`; the gap character ' ' and the quality character under it are dropped
+// (order preserving: ballot-free block prefix sum over 1024-character tiles) and the compacted read is written at the
+// same offset of seq_out / qual_out.  Integer / byte work only: bit-exact against the reference's string loops.
+__global__ void __launch_bounds__(256)
+stitch_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, int L,
+              const int32_t* __restrict__ zmw_start, uint8_t* __restrict__ seq_out, uint8_t* __restrict__ qual_out,
+              int32_t* __restrict__ len_out) {
+  __shared__ int s_warp[8];
+  __shared__ int s_total;
+  const int z = blockIdx.x;
+  const size_t off = (size_t)zmw_start[z] * L;
+  const int n = (zmw_start[z + 1] - zmw_start[z]) * L;
+  const uint8_t* in_b = bases + off;
+  const uint8_t* in_q = quals + off;
+  uint8_t* out_b = seq_out + off;
+  uint8_t* out_q = qual_out + off;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int running = 0;
+  for (int t0 = 0; t0 < n; t0 += 1024) {
+    uint8_t b[4], q[4];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = t0 + threadIdx.x * 4 + k;
+      b[k] = idx < n ? in_b[idx] : (uint8_t)' ';
+      q[k] = idx < n ? in_q[idx] : (uint8_t)0;
+      cnt += b[k] != (uint8_t)' ';
+    }
+    // inclusive scan inside the warp, then across the 8 warps
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      for (int w = 0; w < 8; ++w) { const int v = s_warp[w]; s_warp[w] = acc; acc += v; }
+      s_total = acc;
+    }
+    __syncthreads();
+    int pos = running + s_warp[warp] + incl - cnt;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (b[k] != (uint8_t)' ') {
+        out_b[pos] = b[k];
+        out_q[pos] = q[k];
+        ++pos;
+      }
+    }
+    running += s_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) len_out[z] = running;
+}
+
+void launch_stitch(const uint8_t* bases, const uint8_t* quals, int L, const int32_t* zmw_start, int n_zmw,
+                   uint8_t* seq_out, uint8_t* qual_out, int32_t* len_out, cudaStream_t st) {
+  if (n_zmw > 0) stitch_kernel<<<n_zmw, 256, 0, st>>>(bases, quals, L, zmw_start, seq_out, qual_out, len_out);
+}
+
 void launch_head(const HeadParams& p, int ntiles, cudaStream_t st) {
   head_kernel<<<ntiles, 128, 0, st>>>(p);
 }

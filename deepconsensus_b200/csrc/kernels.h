@@ -48,5 +48,8 @@ void launch_ffn(const __nv_bfloat16* a_img, const uint8_t* w_img, const float* b
 void launch_stack(float* x, int ntiles, int L, int win, const StackParams& p, const HeadParams& hp, cudaStream_t st);
 int read_ffn_trace(unsigned long long* out, int n);
 void launch_head(const HeadParams& p, int ntiles, cudaStream_t st);
+// per-read window concatenation + gap compaction; read z = windows [zmw_start[z], zmw_start[z+1]) (device pointers)
+void launch_stitch(const uint8_t* bases, const uint8_t* quals, int L, const int32_t* zmw_start, int n_zmw,
+                   uint8_t* seq_out, uint8_t* qual_out, int32_t* len_out, cudaStream_t st);
 
 }  // namespace dcb

@@ -67,7 +67,7 @@ class DcbTensor(ctypes.Structure):
 
 # Every symbol include/dcb200.h declares; tests check the built library exports all of them.
 ABI_SYMBOLS = (
-    "dcb_create", "dcb_load_weights", "dcb_forward", "dcb_submit", "dcb_wait", "dcb_last_forward_ms",
+    "dcb_create", "dcb_load_weights", "dcb_forward", "dcb_submit", "dcb_wait", "dcb_stitch", "dcb_last_forward_ms",
     "dcb_last_forward_launches", "dcb_set_profile", "dcb_get_profile", "dcb_get_profile_kernels", "dcb_set_debug", "dcb_debug_residual", "dcb_debug_trace", "dcb_alloc_host",
     "dcb_free_host", "dcb_alloc_device", "dcb_free_device", "dcb_memcpy_h2d", "dcb_memcpy_d2h",
     "dcb_synchronize", "dcb_last_error", "dcb_version", "dcb_destroy",
@@ -94,6 +94,7 @@ def load_library() -> ctypes.CDLL:
   lib.dcb_forward.argtypes = [vp, vp, i32, u32, vp, vp, vp, vp]
   lib.dcb_submit.argtypes = [vp, vp, i32, u32, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int64)]
   lib.dcb_wait.argtypes = [vp, ctypes.c_int64]
+  lib.dcb_stitch.argtypes = [vp, vp, vp, i32, i32, ctypes.POINTER(i32), i32, u32, vp, vp, vp]
   lib.dcb_last_forward_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
   lib.dcb_last_forward_launches.argtypes = [vp, ctypes.POINTER(i32)]
   lib.dcb_set_debug.argtypes = [vp, i32]
@@ -346,6 +347,35 @@ class B200Model:
       pending = h
     if pending is not None:
       yield self.wait(pending, strict_input)
+
+  # -- stitch: per-read window concatenation + gap compaction on the device -------------------------
+  def stitch(self, bases, quals, zmw_start: np.ndarray, n_windows: Optional[int] = None,
+             on_device: bool = False, length: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """dcb_stitch: bases/quals are uint8 [n_windows, L] arrays (or device addresses when `on_device`); read z is the
+    windows [zmw_start[z], zmw_start[z+1]).  Returns (seq, qual, lengths): read z's compacted characters are
+    seq[zmw_start[z] * L : zmw_start[z] * L + lengths[z]] (same for qual)."""
+    zs = np.ascontiguousarray(zmw_start, dtype=np.int32)
+    nz = int(zs.shape[0]) - 1
+    L = int(length) if length is not None else self.max_length   # characters per window
+    if on_device:
+      if n_windows is None:
+        raise ValueError("stitch(on_device=True) needs n_windows")
+      b_ptr, q_ptr = ctypes.c_void_p(int(bases)), ctypes.c_void_p(int(quals))
+      flags = DCB_ROWS_ON_DEVICE
+    else:
+      bases = np.ascontiguousarray(bases, dtype=np.uint8)
+      quals = np.ascontiguousarray(quals, dtype=np.uint8)
+      n_windows = int(bases.shape[0])
+      b_ptr, q_ptr = bases.ctypes.data_as(ctypes.c_void_p), quals.ctypes.data_as(ctypes.c_void_p)
+      flags = 0
+    seq = np.empty(n_windows * L, np.uint8)
+    qual = np.empty(n_windows * L, np.uint8)
+    lens = np.zeros(max(nz, 0), np.int32)
+    self._check(self._lib.dcb_stitch(self._handle, b_ptr, q_ptr, n_windows, L,
+                                     zs.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), nz, flags,
+                                     seq.ctypes.data_as(ctypes.c_void_p), qual.ctypes.data_as(ctypes.c_void_p),
+                                     lens.ctypes.data_as(ctypes.c_void_p)))
+    return seq, qual, lens
 
   def predict(self, rows: np.ndarray) -> _Prediction:
     """Softmax output [B, L, 5], shaped like `EncoderOnlyTransformer.predict` (networks.py:357-365)."""

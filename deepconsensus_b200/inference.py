@@ -108,6 +108,44 @@ def run_model_on_examples(feature_dicts: List[Dict[str, Any]], model: engine_lib
   return predictions
 
 
+def run_model_and_stitch(feature_dicts: List[Dict[str, Any]], model: engine_lib.B200Model,
+                         model_params: params_lib.Params, options: InferenceOptions,
+                         outcome_counter: stitch_utils.OutcomeCounter) -> List[Optional[str]]:
+  """Windows -> FASTQ records without per-window Python objects: `run_model_on_examples` followed, per read, by
+  `stitch_utils.stitch_to_fastq` (quick_inference.py:341-415 and :721-760), with the byte work on the device.
+
+  `feature_dicts` must be grouped by read (`name`) and sorted by `window_pos` inside a read, as `run()` sorts the
+  model outputs before stitching (quick_inference.py:721-728).  Returns one FASTQ record (or None when a filter
+  drops the read) per read, in input order; `outcome_counter` is updated like the reference's.
+  """
+  from deepconsensus_b200 import stitch_gpu
+  names, positions, bases, quals = [], [], [], []
+  pending = None
+
+  def collect(data, out):
+    bases.append(out["bases"])
+    quals.append(out["quals"])
+    names.extend(_as_str(x) for x in data["name"])
+    positions.extend(int(x) for x in data["window_pos"])
+
+  for data in batch_examples(feature_dicts, model_params, options):
+    handle = model.submit(data["rows"])
+    if pending is not None:
+      collect(pending[0], model.wait(pending[1]))
+    pending = (data, handle)
+  if pending is not None:
+    collect(pending[0], model.wait(pending[1]))
+  if not names:
+    return []
+  return stitch_gpu.stitch_batch_to_fastq(model, np.concatenate(bases), np.concatenate(quals), names, positions,
+                                          model_params.max_length, options.min_quality, options.min_length,
+                                          outcome_counter)
+
+
+def _as_str(x) -> str:
+  return x.decode() if isinstance(x, (bytes, np.bytes_)) else str(x)
+
+
 def load_weights_npz(path: str) -> weights_lib.Weights:
   """Variables exported as an .npz keyed by the checkpoint variable names."""
   with np.load(path) as z:

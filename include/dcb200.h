@@ -109,6 +109,19 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
                uint8_t* bases_out, uint8_t* quals_out, float* probs_out, float* logits_out, int64_t* ticket);
 int dcb_wait(dcb_engine* e, int64_t ticket);
 
+/* The first stage of stitch_utils.stitch_to_fastq for a batch of reads -- get_full_sequence + remove_gaps
+ * (stitch_utils.py:51-98) -- on the device: the windows [zmw_start[z], zmw_start[z+1]) of `bases` / `quals`
+ * ([n_windows, L] bytes exactly as dcb_forward writes them, sorted by window position) are concatenated and the gap
+ * character ' ' is dropped together with the quality character under it.  Read z is written at offset
+ * zmw_start[z] * L of seq_out / qual_out (each n_windows * L bytes) and len_out[z] receives its length.  zmw_start is a
+ * host array of n_zmw + 1 non-decreasing window indices.  flags: DCB_ROWS_ON_DEVICE => bases/quals are device
+ * pointers (e.g. the DCB_OUT_ON_DEVICE outputs of dcb_forward); DCB_OUT_ON_DEVICE => seq_out/qual_out/len_out are
+ * device pointers.  The missing-window check and the empty / quality / length filters stay with the caller
+ * (deepconsensus_b200/stitch_gpu.py), which has the window positions and read names. */
+int dcb_stitch(dcb_engine* e, const uint8_t* bases, const uint8_t* quals, int32_t n_windows, int32_t L,
+               const int32_t* zmw_start, int32_t n_zmw, uint32_t flags,
+               uint8_t* seq_out, uint8_t* qual_out, int32_t* len_out);
+
 /* Device time of the last dcb_forward (milliseconds, CUDA events on the engine's stream). */
 int dcb_last_forward_ms(dcb_engine* e, float* ms);
 /* Number of engine kernels launched by the last dcb_forward. */

@@ -144,6 +144,19 @@ def test_run_model_on_examples_and_stitch(engine_mod, golden_dir):
   fds = [dict(subreads=rows[i][..., None], **{"subreads/num_passes": 3}, window_pos=int(pos[i]), name=str(names[i]),
               ccs_base_quality_scores=np.zeros(100), ec=1.0, np_num_passes=3, rq=0.99, rg="rg") for i in range(len(rows))]
   preds = inference.run_model_on_examples(fds, model, p, opts)
+  # fast path: the same windows, grouped by read and sorted by position, straight to FASTQ records with the byte work
+  # on the device -- must equal stitch_to_fastq over the per-window objects, read for read
+  order = sorted(range(len(fds)), key=lambda i: (fds[i]["name"], fds[i]["window_pos"]))
+  cnt_fast = stitch_utils.OutcomeCounter()
+  fast = inference.run_model_and_stitch([fds[i] for i in order], model, p, opts, cnt_fast)
+  cnt_ref, slow, i = stitch_utils.OutcomeCounter(), [], 0
+  while i < len(order):
+    j = i
+    while j < len(order) and fds[order[j]]["name"] == fds[order[i]]["name"]:
+      j += 1
+    slow.append(stitch_utils.stitch_to_fastq(fds[order[i]]["name"], [preds[k] for k in order[i:j]], 100, 0, 0, cnt_ref))
+    i = j
+  assert fast == slow and cnt_fast.__dict__ == cnt_ref.__dict__
   model.close()
   assert len(preds) == len(rows) and all(len(o.sequence) == 100 and len(o.quality_string) == 100 for o in preds)
   ref = omodel.forward(rows, p, w)
@@ -308,3 +321,104 @@ def test_stack_kernel_corner_shapes(engine_mod, layers, ff, rezero, win, L, B):
   ref = omodel.forward(rows, p, w)
   assert np.isfinite(out["logits"]).all()
   assert np.abs(out["logits"] - ref["logits"]).max() <= LOGIT_TOL_FP32
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# SURVEY section 8(f) "next": stitching.  dcb_stitch does get_full_sequence + remove_gaps on the device (bytes: exact).
+def _tiny_model(engine_mod, L=100):
+  p = params_lib.synthetic_params(20, L, num_hidden_layers=1)
+  return engine_mod.B200Model(p, weights_lib.init_weights(p, seed=1), max_batch=4), p
+
+
+def test_device_stitch_against_executed_reference(engine_mod, golden_dir):
+  """All 120 cases produced by executing the reference's stitch_utils (tests/golden/ref_stitch.json), stitched in
+  batches on the device: FASTQ records and outcome counters must be identical, read for read."""
+  import json
+  from deepconsensus_b200 import stitch_gpu, stitch_utils
+  with open(os.path.join(golden_dir, "ref_stitch.json")) as f:
+    cases = json.load(f)["cases"]
+  model, _ = _tiny_model(engine_mod)
+  groups = {}
+  for c in cases:
+    groups.setdefault((c["max_length"], c["min_quality"], c["min_length"]), []).append(c)
+  checked = 0
+  for (L, min_q, min_len), cs in groups.items():
+    bases, quals, names, pos = [], [], [], []
+    for i, c in enumerate(cs):
+      for w in c["windows"]:
+        if w["dropped"]:
+          continue
+        assert len(w["sequence"]) == L and len(w["quality_string"]) == L
+        bases.append(np.frombuffer(w["sequence"].encode("latin-1"), np.uint8))
+        quals.append(np.frombuffer(w["quality_string"].encode("latin-1"), np.uint8))
+        names.append("%s#%d" % (c["name"], i))          # reads with equal names in different cases stay separate
+        pos.append(w["window_pos"])
+    cnt = stitch_utils.OutcomeCounter()
+    got = stitch_gpu.stitch_batch_to_fastq(model, np.stack(bases), np.stack(quals), names, pos, L, min_q, min_len, cnt)
+    want_cnt = stitch_utils.OutcomeCounter()
+    j = 0
+    for i, c in enumerate(cs):
+      if not any(not w["dropped"] for w in c["windows"]):
+        continue                                          # a read with no windows at all never reaches the batch
+      want = c["fastq"]
+      if want is not None:
+        want = want.replace("@" + c["name"] + "\n", "@%s#%d\n" % (c["name"], i), 1)
+      assert got[j] == want, (c["name"], i)
+      for k, v in c["counter"].items():
+        setattr(want_cnt, k, getattr(want_cnt, k) + v)
+      j += 1
+      checked += 1
+    assert j == len(got)
+    assert cnt.__dict__ == want_cnt.__dict__
+  assert checked >= 100
+  model.close()
+
+
+def test_device_stitch_chain_from_forward_outputs(engine_mod):
+  """forward (outputs left on the device) -> dcb_stitch on those device buffers == forward to host -> Python mirror
+  of stitch_to_fastq, for reads of ragged window counts, including one with a missing window and empty inputs."""
+  from deepconsensus_b200 import stitch_gpu, stitch_utils
+  model, p = _tiny_model(engine_mod, L=100)
+  model.close()
+  p = params_lib.synthetic_params(20, 100, num_hidden_layers=2)
+  w = weights_lib.init_weights(p, seed=77)
+  B, L = 37, 100
+  model = engine_mod.B200Model(p, w, max_batch=B)
+  rows = synthetic.make_rows(p, B, seed=78)
+  host = model.forward(rows, strict_input=False)
+  counts = [1, 5, 2, 9, 3, 7, 10]
+  assert sum(counts) == B
+  names, pos = [], []
+  for z, n in enumerate(counts):
+    for i in range(n):
+      names.append("m/%d/ccs" % z)
+      pos.append(i * L if not (z == 3 and i >= 4) else (i + 1) * L)     # read 3 misses its 5th window
+  # device chain
+  dev_rows = model.alloc_device(rows.nbytes)
+  model.memcpy_h2d(dev_rows, rows[..., 0])
+  db, dq = model.alloc_device(B * L), model.alloc_device(B * L)
+  model.forward_raw(dev_rows, B, engine_mod.DCB_ROWS_ON_DEVICE | engine_mod.DCB_OUT_ON_DEVICE, db, dq)
+  cnt = stitch_utils.OutcomeCounter()
+  got = stitch_gpu.stitch_batch_to_fastq(model, db, dq, names, pos, L, 0, 0, cnt, n_windows=B, on_device=True)
+  # Python mirror, read by read
+  want, want_cnt, k = [], stitch_utils.OutcomeCounter(), 0
+  for z, n in enumerate(counts):
+    preds = []
+    for i in range(n):
+      o = stitch_utils.DCModelOutput(names[k], pos[k], 1.0, 3, 0.99, "rg")
+      o.sequence = host["bases"][k].tobytes().decode("ascii")
+      o.quality_string = host["quals"][k].tobytes().decode("ascii")
+      preds.append(o)
+      k += 1
+    want.append(stitch_utils.stitch_to_fastq(names[k - 1], preds, L, 0, 0, want_cnt))
+  assert got == want and cnt.__dict__ == want_cnt.__dict__
+  assert want[3] is None and cnt.empty_sequence == 1 and cnt.success >= 5
+  # degenerate inputs
+  s, q, l = model.stitch(np.zeros((0, L), np.uint8), np.zeros((0, L), np.uint8), np.array([0], np.int32))
+  assert l.shape == (0,)
+  allgap = np.full((2, L), ord(" "), np.uint8)
+  s, q, l = model.stitch(allgap, allgap, np.array([0, 2], np.int32))
+  assert l.tolist() == [0]
+  for d in (dev_rows, db, dq):
+    model.free_device(d)
+  model.close()
