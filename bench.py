@@ -308,6 +308,26 @@ def main():
   sampler.stop_flag.set()
   sampler.join(timeout=2)
 
+  # ---- the "next" row after the model path: per-read stitching of the outputs on the device (dcb_stitch), timed on
+  # the device buffers the last forward wrote (128 reads of 8 windows), call-to-return including its own sync
+  zs = np.arange(0, B + 1, 8, dtype=np.int32)
+  if zs[-1] != B:
+    zs = np.append(zs, B).astype(np.int32)
+  st_seq, st_qual, st_len = model.alloc_device(B * L), model.alloc_device(B * L), model.alloc_device(4 * len(zs))
+  for _ in range(3):
+    model.stitch_raw(dev_bases, dev_quals, B, zs, FL, st_seq, st_qual, st_len)
+  t0 = time.perf_counter()
+  n_st = 50
+  for _ in range(n_st):
+    model.stitch_raw(dev_bases, dev_quals, B, zs, FL, st_seq, st_qual, st_len)
+  stitch_us = (time.perf_counter() - t0) / n_st * 1e6
+  stitch_info = dict(us_per_batch=stitch_us, windows=B, reads=int(len(zs) - 1), bytes_in=2 * B * L,
+                     achieved_gbps=4 * B * L / (stitch_us * 1e-6) / 1e9,
+                     note="get_full_sequence + remove_gaps for the whole batch; at 0.5 MB per batch the call is launch / "
+                          "synchronisation latency, not HBM bandwidth")
+  for d in (st_seq, st_qual, st_len):
+    model.free_device(d)
+
   total_windows = B * world * args.steps
   value = total_windows / dt
   e2e_value = total_windows / dt_e2e
@@ -359,7 +379,7 @@ def main():
                        call="dcb_submit/dcb_wait, 2 batches in flight (as inference.run_model_on_examples)",
                        blocking_value=total_windows / dt_e2e_blocking,
                        blocking_call="dcb_forward, one batch at a time"),
-              gpu_launches=launches, roofline=roof, clocks=sampler.summary(), numa_node=numa)
+              gpu_launches=launches, roofline=roof, clocks=sampler.summary(), numa_node=numa, stitch=stitch_info)
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     os.sched_setaffinity(0, full_affinity)   # the CPU arm may use every host core again
     cores = min(os.cpu_count() or 1, 32)   # torch-CPU on these shapes stops scaling (oversubscribes) beyond ~32 threads

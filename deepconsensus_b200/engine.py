@@ -377,6 +377,15 @@ class B200Model:
                                      lens.ctypes.data_as(ctypes.c_void_p)))
     return seq, qual, lens
 
+  def stitch_raw(self, bases_ptr: int, quals_ptr: int, n_windows: int, zmw_start: np.ndarray, flags: int,
+                 seq_ptr: int, qual_ptr: int, len_ptr: int, length: Optional[int] = None) -> None:
+    """dcb_stitch on caller-managed pointers (host or device per `flags`)."""
+    zs = np.ascontiguousarray(zmw_start, dtype=np.int32)
+    self._check(self._lib.dcb_stitch(self._handle, ctypes.c_void_p(bases_ptr), ctypes.c_void_p(quals_ptr), n_windows,
+                                     int(length) if length is not None else self.max_length,
+                                     zs.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), int(zs.shape[0]) - 1, flags,
+                                     ctypes.c_void_p(seq_ptr), ctypes.c_void_p(qual_ptr), ctypes.c_void_p(len_ptr)))
+
   def predict(self, rows: np.ndarray) -> _Prediction:
     """Softmax output [B, L, 5], shaped like `EncoderOnlyTransformer.predict` (networks.py:357-365)."""
     return _Prediction(self.forward(rows, want_probs=True)["probs"])
