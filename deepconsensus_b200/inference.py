@@ -23,6 +23,7 @@ from deepconsensus_b200 import constants
 from deepconsensus_b200 import engine as engine_lib
 from deepconsensus_b200 import params as params_lib
 from deepconsensus_b200 import stitch_utils
+from deepconsensus_b200 import utils
 from deepconsensus_b200 import weights as weights_lib
 
 
@@ -106,6 +107,44 @@ def run_model_on_examples(feature_dicts: List[Dict[str, Any]], model: engine_lib
   if pending is not None:
     collect(pending[0], model.wait(pending[1]))
   return predictions
+
+
+def process_skipped_window(feature_dict: Dict[str, Any], options: InferenceOptions) -> stitch_utils.DCModelOutput:
+  """A window that is not sent to the model adopts the CCS bases and (calibrated, capped) CCS base qualities
+  (quick_inference.py:567-594)."""
+  rows = feature_dict["subreads"]
+  ccs_index = params_lib.get_indices(options.max_passes, options.use_ccs_bq)[4]
+  ccs = rows[ccs_index[0], :, 0]
+  ccs_seq = utils.encoded_sequence_to_string(ccs)
+  ccs_quality_scores = feature_dict["ccs_base_quality_scores"]
+  if options.ccs_calibration_values.enabled:
+    ccs_quality_scores = calibration_lib.calibrate_quality_scores(ccs_quality_scores, options.ccs_calibration_values)
+  ccs_quality_scores = np.minimum(ccs_quality_scores, options.max_base_quality)
+  ccs_quality_scores = ccs_quality_scores.astype(dtype=np.int32)
+  return stitch_utils.DCModelOutput(
+      window_pos=feature_dict["window_pos"], molecule_name=feature_dict["name"], sequence=ccs_seq,
+      quality_string=utils.quality_scores_to_string(ccs_quality_scores), ec=feature_dict["ec"],
+      np_num_passes=feature_dict["np_num_passes"], rq=feature_dict["rq"], rg=feature_dict["rg"])
+
+
+def split_skipped_windows(feature_dicts_for_zmws: Iterable[Iterable[Dict[str, Any]]], options: InferenceOptions
+                          ) -> Tuple[List[Dict[str, Any]], List[stitch_utils.DCModelOutput]]:
+  """The skip decision of `inference_on_n_zmws` (quick_inference.py:657-676): overflowing windows, and windows whose
+  CCS already averages above `skip_windows_above`, bypass the model and adopt the CCS call."""
+  for_model, skipped = [], []
+  for one_zmw in feature_dicts_for_zmws:
+    for window in one_zmw:
+      skip_example = False
+      if window["overflow"]:
+        skipped.append(process_skipped_window(window, options))
+        skip_example = True
+      if options.skip_windows_above and not skip_example:
+        if utils.avg_phred(window["ccs_base_quality_scores"]) > options.skip_windows_above:
+          skipped.append(process_skipped_window(window, options))
+          skip_example = True
+      if not skip_example:
+        for_model.append(window)
+  return for_model, skipped
 
 
 def run_model_and_stitch(feature_dicts: List[Dict[str, Any]], model: engine_lib.B200Model,

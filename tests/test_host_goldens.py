@@ -153,3 +153,39 @@ def test_config_derived_hidden_sizes():
   assert p.hidden_size == 86                                            # 85 rows padded to even (model_utils.py:335-336)
   assert params_lib.embedded_width(params_lib.synthetic_params(20, 100, use_ccs_bq=True)) == 568
   assert params_lib.embedded_width(params_lib.synthetic_params(32, 200)) == 872
+
+
+# ---- skipped windows (reference: quick_inference.py:567-594 and the skip loop :657-676, executed by
+# scripts/make_skipped_golden.py from the reference's own source text)
+def test_skipped_windows_against_executed_reference(golden_dir):
+  import dataclasses
+  from deepconsensus_b200 import calibration, inference
+  g = _load(golden_dir, "ref_skipped.json")
+  assert len(g["cases"]) >= 40
+  n_skipped = 0
+  for case in g["cases"]:
+    o = case["options"]
+    opts = inference.InferenceOptions(
+        max_length=case["L"], example_height=4 * o["max_passes"] + 5 + int(o["use_ccs_bq"]), max_passes=o["max_passes"],
+        min_quality=0, min_length=0, batch_size=8, use_ccs_bq=o["use_ccs_bq"], cpus=0,
+        skip_windows_above=o["skip_windows_above"], use_saved_model=False, max_base_quality=o["max_base_quality"],
+        dc_calibration_values=calibration.parse_calibration_string("skip"),
+        ccs_calibration_values=calibration.parse_calibration_string(o["ccs_calibration"]))
+    P, L = o["max_passes"], case["L"]
+    R = 4 * P + 5 + int(o["use_ccs_bq"])
+    zmws, cur = [], None
+    for w in case["windows"]:
+      rows = np.zeros((R, L, 1), np.float32)
+      rows[4 * P, :, 0] = w["ccs_row"]
+      fd = dict(subreads=rows, ccs_base_quality_scores=np.asarray(w["ccs_q"], dtype=w["ccs_q_dtype"]),
+                window_pos=w["window_pos"], name=w["zmw"], ec=w["ec"], np_num_passes=w["np_num_passes"], rq=w["rq"],
+                rg=w["rg"], overflow=w["overflow"])
+      if cur is None or cur[-1]["name"] != w["zmw"]:
+        cur = []
+        zmws.append(cur)
+      cur.append(fd)
+    for_model, skipped = inference.split_skipped_windows(zmws, opts)
+    assert [[w["name"], w["window_pos"]] for w in for_model] == case["for_model"]
+    assert [dataclasses.asdict(x) for x in skipped] == [dict(s) for s in case["skipped"]]
+    n_skipped += len(skipped)
+  assert n_skipped >= 50
