@@ -185,8 +185,16 @@ __device__ __forceinline__ RowStats row_epilogue_pass1(const RowEpi& e, uint32_t
                       : nullptr;
   const bool ln = e.ln_g != nullptr;
   float s1 = 0.f, s2 = 0.f, shift = 0.f;
+  // Compact loop on purpose: fully unrolled (18 blocks x every predicated residual / pos-enc / bias / LayerNorm variant)
+  // this function was thousands of straight-line instructions and its warps stalled on instruction fetch (ncu:
+  // stall_no_inst).  Groups of kRowPF blocks keep the prefetch-buffer indices static.
+  static_assert(kRowPF == 4, "the block loop is unrolled by the prefetch depth");
+#pragma unroll 1
+  for (int cg = 0; cg < kDP / 16; cg += kRowPF) {
 #pragma unroll
-  for (int cb = 0; cb < kDP / 16; ++cb) {
+  for (int cj = 0; cj < kRowPF; ++cj) {
+    const int cb = cg + cj;
+    if (cb >= kDP / 16) break;
     uint32_t acc[16];
 #ifdef DCB_TRACE
     const long long _tl0 = clock64();
@@ -196,10 +204,10 @@ __device__ __forceinline__ RowStats row_epilogue_pass1(const RowEpi& e, uint32_t
     if (e.has_xold) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 t = pf.buf[cb % kRowPF][i];
+        const float4 t = pf.buf[cj][i];
         v[4 * i + 0] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
       }
-      if (cb + kRowPF < kDP / 16) row_prefetch_issue(e, tile, r, cb + kRowPF, pf.buf[cb % kRowPF]);
+      if (cb + kRowPF < kDP / 16) row_prefetch_issue(e, tile, r, cb + kRowPF, pf.buf[cj]);
     } else {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = 0.f;
@@ -217,17 +225,17 @@ __device__ __forceinline__ RowStats row_epilogue_pass1(const RowEpi& e, uint32_t
       if (!e.has_xold) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 t = pf.buf[cb % kRowPF][i];
+          const float4 t = pf.buf[cj][i];
           pev[4 * i + 0] = t.x; pev[4 * i + 1] = t.y; pev[4 * i + 2] = t.z; pev[4 * i + 3] = t.w;
         }
         if (cb + kRowPF < kDP / 16) {
           if (e.pe_img) {
             const float4* pi = reinterpret_cast<const float4*>(e.pe_img) + r;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) pf.buf[cb % kRowPF][i] = __ldg(pi + (size_t)((cb + kRowPF) * 4 + i) * kTileM);
+            for (int i = 0; i < 4; ++i) pf.buf[cj][i] = __ldg(pi + (size_t)((cb + kRowPF) * 4 + i) * kTileM);
           } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) pf.buf[cb % kRowPF][i] = __ldg(pr + kRowPF * 4 + i);
+            for (int i = 0; i < 4; ++i) pf.buf[cj][i] = __ldg(pr + kRowPF * 4 + i);
           }
         }
       } else {
@@ -266,12 +274,46 @@ __device__ __forceinline__ RowStats row_epilogue_pass1(const RowEpi& e, uint32_t
                      pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
     }
   }
+  }
   RowStats st;
   const float m1 = s1 * (1.f / kD);
   const float var = fmaxf(s2 * (1.f / kD) - m1 * m1, 0.f);
   st.mean = shift + m1;
   st.rstd = rsqrtf(var + 1e-6f);
   return st;
+}
+
+// Lean form of the row epilogue for the embedding / condenser GEMM in front of the one-kernel stack: no residual
+// input, no bias, no LayerNorm, no bf16 operand image -- x = acc + positional table (image order), nothing else.
+// A small loop body (the general function carries every predicated variant and stalls on instruction fetch).
+__device__ __forceinline__ void row_epilogue_embed_lean(const RowEpi& e, uint32_t tmem_row_base, int tile, int r) {
+  float4* xrow = reinterpret_cast<float4*>(e.x + (size_t)tile * x_image_elems()) + r;
+  const float4* pi = reinterpret_cast<const float4*>(e.pe_img) + r;
+  float4 pcur[4], pnxt[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pcur[i] = __ldg(pi + (size_t)i * kTileM);
+#pragma unroll 1
+  for (int cb = 0; cb < kDP / 16; ++cb) {
+    uint32_t acc[16];
+    tmem_ld16(tmem_row_base + cb * 16, acc);
+    if (cb + 1 < kDP / 16) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pnxt[i] = __ldg(pi + (size_t)((cb + 1) * 4 + i) * kTileM);
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = cb * 16 + 4 * i;
+      float4 o;
+      o.x = col + 0 < kD ? __uint_as_float(acc[4 * i + 0]) + pcur[i].x : 0.f;
+      o.y = col + 1 < kD ? __uint_as_float(acc[4 * i + 1]) + pcur[i].y : 0.f;
+      o.z = col + 2 < kD ? __uint_as_float(acc[4 * i + 2]) + pcur[i].z : 0.f;
+      o.w = col + 3 < kD ? __uint_as_float(acc[4 * i + 3]) + pcur[i].w : 0.f;
+      xrow[(size_t)(cb * 4 + i) * kTileM] = o;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pcur[i] = pnxt[i];
+  }
 }
 
 // =====================================================================================
@@ -582,23 +624,26 @@ embed_condense_kernel(const float* __restrict__ rows, int R, int L, int Lw, int 
         // exposed memory latency instead of six dependent batches), a warp reads 512 contiguous bytes.
         const bool wvalid = (size_t)tile * kTileM < (size_t)M;
         const float4* base4 = reinterpret_cast<const float4*>(rows + (size_t)(wvalid ? tile : 0) * R * L);
-        constexpr int kMaxItems = 12;                      // ceil(R * 32 / 256) for R <= 96
         const int nitems = (R * 32 + 255) / 256;
-        float4 f[kMaxItems];
-#pragma unroll
-        for (int k = 0; k < kMaxItems; ++k) {
+        auto load_item = [&](int k) -> float4 {
           const int item = bt + k * 256;
           const int ru = item >> 5, g = item & 31;
-          f[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k < nitems && ru < R && wvalid && 4 * g < L) f[k] = __ldg(base4 + ((size_t)ru * L + 4 * g) / 4);
-        }
-#pragma unroll
-        for (int k = 0; k < kMaxItems; ++k) {
+          if (k < nitems && ru < R && wvalid && 4 * g < L) return __ldg(base4 + ((size_t)ru * L + 4 * g) / 4);
+          return make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        // Compact loop with the loads of the next three items in flight.  (A fully unrolled variant with all ~11 loads
+        // issued up front had the shorter id phase, 12.0 k vs 14.2 k cycles per tile, but the larger kernel: 0.147 vs
+        // 0.127 ms -- its instruction footprint slowed every other phase of the kernel.)
+        float4 f0 = load_item(0), f1 = load_item(1), f2 = load_item(2);
+#pragma unroll 1
+        for (int k = 0; k < nitems; ++k) {
+          const float4 cur = f0;
+          f0 = f1; f1 = f2; f2 = load_item(k + 3);
           const int item = bt + k * 256;
           const int ru = item >> 5, g = item & 31;
-          if (k < nitems && ru < R) {
+          if (ru < R) {
             const EmbedRow m = rowmeta[ru];
-            const float vals[4] = {f[k].x, f[k].y, f[k].z, f[k].w};
+            const float vals[4] = {cur.x, cur.y, cur.z, cur.w};
             uint32_t ids[4];
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
@@ -662,34 +707,52 @@ embed_condense_kernel(const float* __restrict__ rows, int R, int L, int Lw, int 
         mbar_wait(&a_empty[b], ((n >> 1) & 1) ^ 1);
         TRACE_ADD(t_aempty);
         uint4* dst = reinterpret_cast<uint4*>(sAslab + b * C::kASlabBytes);
-        for (int idx = bt; idx < kh * 2 * kTileM; idx += 256) {
-          const int kcl = idx / kTileM, r = idx % kTileM;
-          const int kc = sl * C::kSlabK * 2 + kcl;
-          uint4 val;
-          const EmbedCol c0 = s_cols[kc * 8];
-          if (c0.width == 8 && c0.col == 0 && c0.src_row >= 0) {
-            const int id = s_ids[c0.src_row * kTileM + r];
-            val = *reinterpret_cast<const uint4*>(s_tab + c0.table_off + id * 8);
-          } else {
-            uint32_t packed[4];
+        // A thread builds one 16-byte chunk for each of the slab's kh k-steps (items idx = bt + 256 j: chunk kcl = j*2 +
+        // bt/128, row r = bt%128).  The three dependent shared-memory reads (column descriptor -> id -> table row) are
+        // issued for all of its items before any is used, so their latencies overlap instead of adding up.
+        {
+          const int r = bt & (kTileM - 1), kc0 = bt >> 7;
+          EmbedCol c0[C::kSlabK];
+          int id[C::kSlabK];
+          uint4 val[C::kSlabK];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t pr = 0;
+          for (int j = 0; j < C::kSlabK; ++j)
+            if (j < kh) c0[j] = s_cols[(sl * C::kSlabK * 2 + 2 * j + kc0) * 8];
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const EmbedCol c = s_cols[kc * 8 + 2 * j + h];
-                uint32_t bits = 0;
-                if (c.src_row >= 0) {
-                  const int id = s_ids[c.src_row * kTileM + r];
-                  bits = __bfloat16_as_ushort(s_tab[c.table_off + id * c.width + c.col]);
-                }
-                pr |= bits << (16 * h);
-              }
-              packed[j] = pr;
-            }
-            val = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          for (int j = 0; j < C::kSlabK; ++j) {
+            id[j] = 0;
+            if (j < kh && c0[j].src_row >= 0) id[j] = s_ids[c0[j].src_row * kTileM + r];
           }
-          dst[(size_t)kcl * kTileM + r] = val;
+#pragma unroll
+          for (int j = 0; j < C::kSlabK; ++j) {
+            if (j < kh) {
+              const int kc = sl * C::kSlabK * 2 + 2 * j + kc0;
+              if (c0[j].width == 8 && c0[j].col == 0 && c0[j].src_row >= 0) {
+                val[j] = *reinterpret_cast<const uint4*>(s_tab + c0[j].table_off + id[j] * 8);
+              } else {
+                uint32_t packed[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  uint32_t pr = 0;
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    const EmbedCol c = s_cols[kc * 8 + 2 * jj + h];
+                    uint32_t bits = 0;
+                    if (c.src_row >= 0) {
+                      const int idd = s_ids[c.src_row * kTileM + r];
+                      bits = __bfloat16_as_ushort(s_tab[c.table_off + idd * c.width + c.col]);
+                    }
+                    pr |= bits << (16 * h);
+                  }
+                  packed[jj] = pr;
+                }
+                val[j] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < C::kSlabK; ++j)
+            if (j < kh) dst[(size_t)(2 * j + kc0) * kTileM + r] = val[j];
         }
         fence_proxy_async_smem();
         mbar_arrive(&a_full[b]);
@@ -711,13 +774,16 @@ embed_condense_kernel(const float* __restrict__ rows, int R, int L, int Lw, int 
     uint32_t it = 0;
     long long t_accfull = 0, t_epi = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const bool lean = !epi.has_xold && epi.pe_img && !epi.bias && !epi.ln_g && !epi.xb;
       RowPrefetch pf;
-      row_prefetch_start(epi, tile, r, pf);        // positional rows in flight while the GEMM finishes
+      if (!lean) row_prefetch_start(epi, tile, r, pf);   // positional rows in flight while the GEMM finishes
       TRACE_T0();
       mbar_wait(acc_full, it & 1);
       TRACE_ADD(t_accfull);
       tc_fence_after();
-      const RowStats st = row_epilogue_pass1(epi, tmem_row, tile, r, pf);
+      RowStats st{0.f, 1.f};
+      if (lean) row_epilogue_embed_lean(epi, tmem_row, tile, r);
+      else st = row_epilogue_pass1(epi, tmem_row, tile, r, pf);
       tc_fence_before();
       mbar_arrive(acc_empty);
       TRACE_ADD(t_epi);
