@@ -2613,10 +2613,22 @@ __device__ __forceinline__ void head_finish(const HeadParams& p, float (&lg)[kVo
 // =====================================================================================
 __global__ void __launch_bounds__(128)
 head_kernel(HeadParams p) {
-  __shared__ float sW[kD * kVocab];
-  __shared__ float sG[kD], sBt[kD];
-  for (int i = threadIdx.x; i < kD * kVocab; i += blockDim.x) sW[i] = p.wfc[i];
-  for (int i = threadIdx.x; i < kD; i += blockDim.x) { sG[i] = p.ln_g[i]; sBt[i] = p.ln_b[i]; }
+  // logits_j = sum_c ((x_c - mean) * rstd * g_c + b_c) * W_cj + bfc_j
+  //          = rstd * (sum_c y_c * (g_c W_cj) - mean_y * A_j) + B_j + bfc_j,   y = x - shift, A_j = sum_c g_c W_cj,
+  //            B_j = sum_c b_c W_cj
+  // so ONE pass over the row accumulates sum y, sum y^2 and the five sums y * gW_j (the residual image is read once).
+  __shared__ float sGW[kD * kVocab];
+  __shared__ float sA[kVocab], sBj[kVocab];
+  for (int i = threadIdx.x; i < kD * kVocab; i += blockDim.x) sGW[i] = p.ln_g[i / kVocab] * p.wfc[i];
+  if (threadIdx.x < kVocab) {
+    float a = 0.f, bsum = 0.f;
+    for (int c = 0; c < kD; ++c) {
+      a += p.ln_g[c] * p.wfc[c * kVocab + threadIdx.x];
+      bsum += p.ln_b[c] * p.wfc[c * kVocab + threadIdx.x];
+    }
+    sA[threadIdx.x] = a;
+    sBj[threadIdx.x] = bsum;
+  }
   __syncthreads();
   const int tile = blockIdx.x, r = threadIdx.x;
   const int tok = tile * kTileM + r;
@@ -2625,45 +2637,37 @@ head_kernel(HeadParams p) {
   if (pos >= p.L) return;                       // layout padding row
   const size_t oidx = (size_t)wdw * p.L + pos;  // outputs are dense [B, L]
   const float4* xrow = reinterpret_cast<const float4*>(p.x + (size_t)tile * x_image_elems()) + r;
-  // pass 1: mean / variance (biased, eps = 1e-6: encoder_stack.py:131-133); 10 loads in flight per batch
+  // mean / variance are biased, eps = 1e-6 (encoder_stack.py:131-133); 10 loads in flight per batch
   float s1 = 0.f, s2 = 0.f;
+  float t[kVocab];
+#pragma unroll
+  for (int j = 0; j < kVocab; ++j) t[j] = 0.f;
   const float shift = xrow[0].x;
   constexpr int kHB = 10;
   static_assert((kD / 4) % kHB == 0, "head batch");
+#pragma unroll 1
   for (int c0 = 0; c0 < kD / 4; c0 += kHB) {
     float4 v[kHB];
 #pragma unroll
     for (int u = 0; u < kHB; ++u) v[u] = xrow[(size_t)(c0 + u) * kTileM];
 #pragma unroll
     for (int u = 0; u < kHB; ++u) {
-      const float a = v[u].x - shift, b = v[u].y - shift, c = v[u].z - shift, d = v[u].w - shift;
-      s1 += (a + b) + (c + d);
-      s2 += (a * a + b * b) + (c * c + d * d);
-    }
-  }
-  const float m1 = s1 * (1.f / kD);
-  const float mean = shift + m1;
-  const float rstd = rsqrtf(fmaxf(s2 * (1.f / kD) - m1 * m1, 0.f) + 1e-6f);
-  // pass 2: logits = LN(x) Wfc + b (networks.py:342)
-  float lg[kVocab];
-#pragma unroll
-  for (int j = 0; j < kVocab; ++j) lg[j] = 0.f;
-  for (int c0 = 0; c0 < kD / 4; c0 += kHB) {
-    float4 v[kHB];
-#pragma unroll
-    for (int u = 0; u < kHB; ++u) v[u] = xrow[(size_t)(c0 + u) * kTileM];
-#pragma unroll
-    for (int u = 0; u < kHB; ++u) {
-      const float xs[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      const float ys[4] = {v[u].x - shift, v[u].y - shift, v[u].z - shift, v[u].w - shift};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int col = (c0 + u) * 4 + i;
-        const float z = (xs[i] - mean) * rstd * sG[col] + sBt[col];
+        s1 += ys[i];
+        s2 = fmaf(ys[i], ys[i], s2);
 #pragma unroll
-        for (int j = 0; j < kVocab; ++j) lg[j] = fmaf(z, sW[col * kVocab + j], lg[j]);
+        for (int j = 0; j < kVocab; ++j) t[j] = fmaf(ys[i], sGW[col * kVocab + j], t[j]);
       }
     }
   }
+  const float m1 = s1 * (1.f / kD);             // mean of y
+  const float rstd = rsqrtf(fmaxf(s2 * (1.f / kD) - m1 * m1, 0.f) + 1e-6f);
+  float lg[kVocab];
+#pragma unroll
+  for (int j = 0; j < kVocab; ++j) lg[j] = rstd * (t[j] - m1 * sA[j]) + sBj[j];   // + fc1 bias in head_finish (networks.py:342)
   head_finish(p, lg, oidx);
 }
 
