@@ -10,6 +10,7 @@ accumulation, so
   * quality characters within +-1 at those positions, and
   * the device epilogue is bit-exact given the device's own probabilities (integer/byte work).
 """
+import ast
 import os
 
 import numpy as np
@@ -214,7 +215,7 @@ def test_engine_against_reference_code_goldens(engine_mod, golden_dir, name):
   scripts/make_model_golden.py) -- no oracle in between."""
   z = np.load(os.path.join(golden_dir, "ref_model_%s.npz" % name))
   p = params_lib.get_config(str(z["config"]))
-  for k, v in eval(str(z["overrides"])).items():
+  for k, v in ast.literal_eval(str(z["overrides"])).items():
     p[k] = v
   params_lib.modify_params(p, max_length=int(z["max_length"]))
   w = weights_lib.init_weights(p, seed=int(z["seed"]))

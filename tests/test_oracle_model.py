@@ -1,5 +1,6 @@
 """The oracle against the structural invariants the reference pins for the model
 (models/networks_test.py:62-151) and against its own arithmetic modes."""
+import ast
 import os
 
 import numpy as np
@@ -89,12 +90,12 @@ REF_MODEL_CASES = ["rezero_p20", "layernorm_p20", "rezero_p20_bq", "layernorm_p2
 
 def _load_ref_case(golden_dir, name):
   z = np.load(os.path.join(golden_dir, "ref_model_%s.npz" % name))
-  over = eval(str(z["overrides"]))            # a repr()'d dict of plain python values written by our own script
+  over = ast.literal_eval(str(z["overrides"]))   # a repr()'d dict of plain python values written by our own script
   p = params_lib.get_config(str(z["config"]))
   for k, v in over.items():
     p[k] = v
   params_lib.modify_params(p, max_length=int(z["max_length"]))
-  derived = eval(str(z["derived"]))
+  derived = ast.literal_eval(str(z["derived"]))
   for k, v in derived.items():                # model_utils.modify_params ran for real when the golden was made
     assert p[k] == v, (k, p[k], v)
   w = weights_lib.init_weights(p, seed=int(z["seed"]))
