@@ -112,6 +112,13 @@ CASES = [
          over=dict(use_ccs_bq=True, rezero=False, num_hidden_layers=5), src="synthetic", n=3, seed=15),
     dict(name="rezero_p5_win3", config="transformer_learn_values+test",
          over=dict(max_passes=5, attn_win_size=3, num_hidden_layers=2), src="synthetic", n=3, seed=14),
+    # BASELINE configs[1] shape (20 subreads x 120 bp, 6 layers) and configs[4] shape (32 subreads x 200 bp)
+    dict(name="c2_p20_l120", config="transformer_learn_values+test", over={}, src="synthetic", L=120, n=4, seed=16),
+    dict(name="c5_p32_l200", config="transformer_learn_values+test", over=dict(max_passes=32), src="synthetic",
+         L=200, n=3, seed=17),
+    dict(name="c5_p32_l200_ln_bq", config="transformer_learn_values+test",
+         over=dict(max_passes=32, use_ccs_bq=True, rezero=False, num_hidden_layers=5), src="synthetic", L=200, n=2,
+         seed=18),
 ]
 
 
@@ -120,11 +127,14 @@ def main():
   from deepconsensus_b200 import weights as W, synthetic
   from deepconsensus_b200 import params as P
   real = np.load(os.path.join(OUT, "real_windows_human_1m.npz"))["rows"]
+  only = set(sys.argv[1:])
   for case in CASES:
+    if only and case["name"] not in only:
+      continue
     params = model_configs.get_config(case["config"])
     for k, v in case["over"].items():
       params[k] = v
-    max_length = 100 if case["src"] == "real" else 40
+    max_length = case.get("L", 100 if case["src"] == "real" else 40)
     model_utils.modify_params(params, max_length=max_length, is_training=False)
     # our host-side params for the same request (validates deepconsensus_b200.params against the reference)
     mine = P.get_config(case["config"])

@@ -85,7 +85,8 @@ def test_postprocess_matches_quick_inference_semantics():
 # The pin: vectors produced by EXECUTING the reference's own networks.py / encoder_stack.py / attention_layer.py /
 # ffn_layer.py / data_providers.format_rows / model_configs / model_utils.modify_params on a NumPy stand-in for the
 # TF primitives (scripts/make_model_golden.py + scripts/tf_shim.py).  Weights are regenerated from the seed.
-REF_MODEL_CASES = ["rezero_p20", "layernorm_p20", "rezero_p20_bq", "layernorm_p20_bq", "rezero_p5_win3"]
+REF_MODEL_CASES = ["rezero_p20", "layernorm_p20", "rezero_p20_bq", "layernorm_p20_bq", "rezero_p5_win3",
+                   "c2_p20_l120", "c5_p32_l200", "c5_p32_l200_ln_bq"]
 
 
 def _load_ref_case(golden_dir, name):
