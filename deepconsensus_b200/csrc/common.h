@@ -49,6 +49,27 @@ struct EmbedRow {
   int32_t vocab;   // table rows
 };
 
+// ------------------------------------------------------------------ strict-fp32 path (strict_kernels.cu)
+// Per input row: clip / shift / vocabulary as EmbedRow, plus where its embedding lands in the concatenated vector and
+// which float32 table (pre-scaled by sqrt(width), row 0 zeroed) it reads.
+struct StrictEmbedRow {
+  float clip_hi;
+  int32_t shift;
+  int32_t vocab;
+  int32_t width;
+  int32_t col0;        // first column in the [E] embedding vector
+  int32_t table_off;   // element offset in the float32 table blob
+};
+// v = acc (+ bias[n]) -> (ReLU) -> * scale -> (+ residual[m, n]) -> (+ pe[m % pe_L, n])
+struct StrictEpi {
+  const float* bias = nullptr;
+  const float* residual = nullptr;
+  const float* pe = nullptr;
+  int pe_L = 1;
+  int relu = 0;
+  float scale = 1.f;
+};
+
 // ------------------------------------------------------------------ row epilogue
 // Shared tail of every d-wide GEMM: x_new = acc (+ x_old) (+ bias) (+ pos-enc);
 // write x_new (fp32 image) and the next sub-layer's bf16 operand image

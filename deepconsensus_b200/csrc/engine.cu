@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/dcb200.h"
+#include "../../include/dcb200_debug.h"
 #include "kernels.h"
 
 using namespace dcb;
@@ -105,6 +106,21 @@ struct dcb_engine {
   int32_t *d_st_start = nullptr, *d_st_len = nullptr;
   size_t st_cap = 0, st_zcap = 0;
   float* d_dbg = nullptr;  // [stages][chunk_tiles * x_image]
+  // strict-fp32 path (strict_kernels.cu): float32 copies of every variable in the reference's own shapes, and a
+  // row-major workspace allocated on the first strict call
+  struct StrictLayer {
+    float *wq = nullptr, *wk = nullptr, *wv = nullptr, *wo = nullptr, *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+    float *ln_g[2] = {nullptr, nullptr}, *ln_b[2] = {nullptr, nullptr};
+    float alpha[2] = {1.f, 1.f};
+  };
+  struct Strict {
+    StrictEmbedRow* meta = nullptr;
+    float *tables = nullptr, *wc = nullptr, *pe = nullptr;
+    float *fln_g = nullptr, *fln_b = nullptr;
+    std::vector<StrictLayer> layers;
+    float *emb = nullptr, *x = nullptr, *y = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *att = nullptr, *hid = nullptr;
+    int chunk_windows = 0;
+  } strict;
   std::vector<void*> owned;
 };
 
@@ -204,6 +220,8 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   if (cfg->max_passes <= 0 || cfg->max_length <= 0 || cfg->max_length > 256 || cfg->num_hidden_layers <= 0 ||
       cfg->max_batch <= 0)
     return fail(nullptr, DCB_ERR_INVALID, "bad max_passes/max_length(<=256)/num_hidden_layers/max_batch");
+  if (cfg->precision != DCB_PRECISION_BF16 && cfg->precision != DCB_PRECISION_FP32)
+    return fail(nullptr, DCB_ERR_INVALID, "precision must be DCB_PRECISION_BF16 or DCB_PRECISION_FP32");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, DCB_ERR_CUDA, "no CUDA device available (the dcb200 engine has no CPU fallback)");
@@ -217,21 +235,13 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   e->cfg = *cfg;
   e->num_sms = prop.multiProcessorCount;
   e->L = cfg->max_length;
-  // window-aligned tiling: one window per 128-token tile when it fits (lets QKV + attention fuse);
-  // otherwise windows are packed back to back
   e->Lw = e->L;
-  {
-    const char* env = getenv("DCB_ALIGN");
-    const bool align = env ? atoi(env) != 0 : true;
-    if (align && e->L <= kTileM) e->Lw = kTileM;
-  }
-  e->R = 4 * cfg->max_passes + (cfg->use_ccs_bq ? 6 : 5);  // data_providers.py:61-78
-  e->E = cfg->max_passes * (cfg->per_base_hidden_size + cfg->pw_hidden_size + cfg->ip_hidden_size +
-                            cfg->strand_hidden_size) +
-         cfg->per_base_hidden_size + (cfg->use_ccs_bq ? cfg->ccs_bq_hidden_size : 0) +
-         4 * cfg->sn_hidden_size;
-  e->Epad = (e->E + 15) / 16 * 16;
-  e->echunks = e->Epad / 8;
+  bool align = true;
+  int ct = cfg->chunk_tiles;
+#ifdef DCB_DEV_SWITCHES
+  // Developer build only (libdcb200_dev.so, csrc/build.sh): environment switches that select the measured
+  // alternative kernel paths.  The product library ignores the environment.
+  if (const char* env = getenv("DCB_ALIGN")) align = atoi(env) != 0;
   if (const char* env = getenv("DCB_FFN_PAIR")) e->ffn_pair = atoi(env) != 0;
   if (const char* env = getenv("DCB_FUSE_OPROJ")) e->fuse_oproj = atoi(env) != 0;
   if (const char* env = getenv("DCB_QKV2")) e->qkv2 = atoi(env) != 0;
@@ -239,8 +249,18 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   if (const char* env = getenv("DCB_FUSE_QA")) e->fuse_qa = atoi(env) != 0;
   if (const char* env = getenv("DCB_STACK")) e->stack = atoi(env) != 0;
   if (const char* env = getenv("DCB_FUSE_HEAD")) e->fuse_head = atoi(env) != 0;
-  int ct = cfg->chunk_tiles;
   if (const char* env = getenv("DCB_CHUNK_TILES")) ct = atoi(env);
+#endif
+  // window-aligned tiling: one window per 128-token tile when it fits (lets QKV + attention fuse);
+  // otherwise windows are packed back to back
+  if (align && e->L <= kTileM) e->Lw = kTileM;
+  e->R = 4 * cfg->max_passes + (cfg->use_ccs_bq ? 6 : 5);  // data_providers.py:61-78
+  e->E = cfg->max_passes * (cfg->per_base_hidden_size + cfg->pw_hidden_size + cfg->ip_hidden_size +
+                            cfg->strand_hidden_size) +
+         cfg->per_base_hidden_size + (cfg->use_ccs_bq ? cfg->ccs_bq_hidden_size : 0) +
+         4 * cfg->sn_hidden_size;
+  e->Epad = (e->E + 15) / 16 * 16;
+  e->echunks = e->Epad / 8;
   if (ct <= 0) ct = 8 * e->num_sms;   // measured: larger chunks win (kernels are not DRAM-bound)
   const int max_tiles = (int)(((int64_t)cfg->max_batch * e->Lw + kTileM - 1) / kTileM);
   e->chunk_windows = std::max(1, std::min(cfg->max_batch, ct * kTileM / e->Lw));
@@ -584,9 +604,127 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
     if ((rc = upload(e, &e->d_wfc, std::vector<float>(w, w + kD * kVocab)))) return rc;
     if ((rc = upload(e, &e->d_bfc, std::vector<float>(bb, bb + kVocab)))) return rc;
   }
+  // ---- strict-fp32 path: every variable once more as float32, in the reference's own shapes
+  {
+    dcb_engine::Strict& S = e->strict;
+    std::vector<float> fblob;
+    std::vector<int> foff(tabs.size(), 0);
+    for (size_t t = 0; t < tabs.size(); ++t) {
+      if (t == 4 && !c.use_ccs_bq) continue;
+      const Tab& tb = tabs[t];
+      foff[t] = (int)fblob.size();
+      const float scale = sqrtf((float)tb.width);          // networks.py:54
+      for (int v = 0; v < tb.vocab; ++v)
+        for (int j = 0; j < tb.width; ++j) fblob.push_back(v == 0 ? 0.f : tb.data[v * tb.width + j] * scale);   // :58-63
+    }
+    std::vector<StrictEmbedRow> meta(e->R);
+    {
+      const int P = c.max_passes;
+      int col = 0, row = 0;
+      auto add = [&](int tab, int nrows, float clip, int shift) {
+        for (int r = 0; r < nrows; ++r) {
+          meta[row++] = StrictEmbedRow{clip, shift, tabs[tab].vocab, tabs[tab].width, col, foff[tab]};
+          col += tabs[tab].width;
+        }
+      };
+      add(0, P, 0.f, 0); add(1, P, (float)c.pw_max, 0); add(2, P, (float)c.ip_max, 0); add(3, P, 0.f, 0);
+      add(0, 1, 0.f, 0);
+      if (c.use_ccs_bq) add(4, 1, 0.f, 1);
+      add(5, 4, (float)c.sn_max, 0);
+      if (row != e->R || col != e->E) return fail(e, DCB_ERR_INVALID, "internal: strict embedding layout %d/%d", row, col);
+    }
+    if ((rc = upload(e, &S.meta, meta))) return rc;
+    if ((rc = upload(e, &S.tables, fblob))) return rc;
+    const float* wc = tm.get("model/transformer_input_condenser/kernel", {e->E, kD}, &rc); if (rc) return rc;
+    if ((rc = upload(e, &S.wc, std::vector<float>(wc, wc + (size_t)e->E * kD)))) return rc;
+    {
+      std::vector<float> pe((size_t)e->L * kD, 0.f);
+      if (c.add_pos_encoding) {
+        const int nt = kD / 2;
+        const float inc = (float)(log(1e4 / 1.0) / (double)(nt - 1));
+        for (int l = 0; l < e->L; ++l)
+          for (int k = 0; k < nt; ++k) {
+            const float sc = (float)l * expf((float)k * -inc);
+            pe[(size_t)l * kD + k] = sinf(sc);
+            pe[(size_t)l * kD + nt + k] = cosf(sc);
+          }
+      }
+      if ((rc = upload(e, &S.pe, pe))) return rc;
+    }
+    S.layers.assign(c.num_hidden_layers, dcb_engine::StrictLayer());
+    for (int n_ = 0; n_ < c.num_hidden_layers; ++n_) {
+      dcb_engine::StrictLayer& sl = S.layers[n_];
+      char pre[128];
+      snprintf(pre, sizeof pre, "model/encoder_stack/layers/%d", n_);
+      const std::string P0 = std::string(pre) + "/0", P1 = std::string(pre) + "/1";
+      auto up = [&](float** dst, const std::string& name, std::initializer_list<int64_t> shape, size_t count) {
+        const float* src = tm.get(name, shape, &rc);
+        if (rc) return rc;
+        return rc = upload(e, dst, std::vector<float>(src, src + count));
+      };
+      if (c.rezero) {
+        sl.alpha[0] = *tm.get(P0 + "/alpha", std::initializer_list<int64_t>{}, &rc); if (rc) return rc;
+        sl.alpha[1] = *tm.get(P1 + "/alpha", std::initializer_list<int64_t>{}, &rc); if (rc) return rc;
+      } else {
+        for (int sidx = 0; sidx < 2; ++sidx) {
+          const std::string PP = sidx ? P1 : P0;
+          if (up(&sl.ln_g[sidx], PP + "/layer_norm/gamma", {kD}, kD)) return rc;
+          if (up(&sl.ln_b[sidx], PP + "/layer_norm/beta", {kD}, kD)) return rc;
+        }
+      }
+      if (up(&sl.wq, P0 + "/layer/query_dense_layer/kernel", {kD, kHeads, kDH}, (size_t)kD * kD)) return rc;
+      if (up(&sl.wk, P0 + "/layer/key_dense_layer/kernel", {kD, kHeads, kDH}, (size_t)kD * kD)) return rc;
+      if (up(&sl.wv, P0 + "/layer/value_dense_layer/kernel", {kD, kHeads, kDH}, (size_t)kD * kD)) return rc;
+      if (up(&sl.wo, P0 + "/layer/output_dense_layer/kernel", {kHeads, kDH, kD}, (size_t)kD * kD)) return rc;
+      if (up(&sl.w1, P1 + "/layer/filter_dense_layer/kernel", {kD, ff}, (size_t)kD * ff)) return rc;
+      if (up(&sl.b1, P1 + "/layer/filter_dense_layer/bias", {ff}, (size_t)ff)) return rc;
+      if (up(&sl.w2, P1 + "/layer/output_dense_layer/kernel", {ff, kD}, (size_t)ff * kD)) return rc;
+      if (up(&sl.b2, P1 + "/layer/output_dense_layer/bias", {kD}, (size_t)kD)) return rc;
+    }
+  }
   CU(e, cudaDeviceSynchronize());
   e->weights_loaded = true;
   return DCB_OK;
+}
+
+// One chunk of the strict-fp32 forward (strict_kernels.cu): rows [bw, R, L] -> outputs via hp.  Returns launches.
+static int strict_forward_chunk(dcb_engine* e, const float* rows_chunk, int bw, const HeadParams& hp, int* d_status,
+                                cudaStream_t st) {
+  const dcb_config& c = e->cfg;
+  dcb_engine::Strict& S = e->strict;
+  const int L = e->L, M = bw * L, ff = c.filter_size;
+  int launches = 0;
+  launch_strict_embed(rows_chunk, e->R, L, e->E, bw, S.meta, S.tables, S.emb, d_status, st); ++launches;
+  {
+    StrictEpi ep;
+    if (c.add_pos_encoding) { ep.pe = S.pe; ep.pe_L = L; }
+    launch_strict_gemm(S.emb, S.wc, S.x, M, kD, e->E, ep, st); ++launches;            // networks.py:509-516, :319-323
+  }
+  const float qscale = 1.0f / sqrtf((float)kDH);                                       // attention_layer.py:196-197
+  for (int n_ = 0; n_ < c.num_hidden_layers; ++n_) {
+    const dcb_engine::StrictLayer& sl = S.layers[n_];
+    const float* yin = S.x;
+    if (!c.rezero) { launch_strict_layernorm(S.x, S.y, M, sl.ln_g[0], sl.ln_b[0], st); ++launches; yin = S.y; }
+    StrictEpi eq; eq.scale = qscale;
+    launch_strict_gemm(yin, sl.wq, S.q, M, kD, kD, eq, st);
+    launch_strict_gemm(yin, sl.wk, S.k, M, kD, kD, StrictEpi(), st);
+    launch_strict_gemm(yin, sl.wv, S.v, M, kD, kD, StrictEpi(), st);
+    launch_strict_attention(S.q, S.k, S.v, S.att, bw, L, c.attn_win_size, st);
+    StrictEpi eo; eo.residual = S.x; eo.scale = c.rezero ? sl.alpha[0] : 1.f;         // encoder_stack.py:88-92
+    launch_strict_gemm(S.att, sl.wo, S.x, M, kD, kD, eo, st);
+    launches += 5;
+    yin = S.x;
+    if (!c.rezero) { launch_strict_layernorm(S.x, S.y, M, sl.ln_g[1], sl.ln_b[1], st); ++launches; yin = S.y; }
+    StrictEpi e1; e1.bias = sl.b1; e1.relu = 1;                                        // ffn_layer.py:83-86
+    launch_strict_gemm(yin, sl.w1, S.hid, M, ff, kD, e1, st);
+    StrictEpi e2; e2.bias = sl.b2; e2.residual = S.x; e2.scale = c.rezero ? sl.alpha[1] : 1.f;
+    launch_strict_gemm(S.hid, sl.w2, S.x, M, kD, ff, e2, st);
+    launches += 2;
+  }
+  HeadParams h = hp;
+  h.x = S.x; h.M = M; h.L = L; h.Lw = L;
+  launch_strict_head(S.x, M, h, st); ++launches;
+  return launches;
 }
 
 int dcb_set_debug(dcb_engine* e, int32_t enabled) {
@@ -605,8 +743,13 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
                uint8_t* quals_out, float* probs_out, float* logits_out, int64_t* ticket_out) {
   if (!e || !ticket_out) return DCB_ERR_INVALID;
   if (!e->weights_loaded) return fail(e, DCB_ERR_STATE, "dcb_forward before dcb_load_weights");
-  dcb_engine::Slot& sl = e->slots[e->next_ticket & 1];
-  if (sl.busy) return fail(e, DCB_ERR_STATE, "two submissions in flight: dcb_wait(ticket %lld) first", (long long)sl.ticket);
+  // any free slot (preferring the alternating one): a blocking dcb_forward between two submissions must not collide
+  // with the slot of the one still outstanding
+  int si = (int)(e->next_ticket & 1);
+  if (e->slots[si].busy) si ^= 1;
+  dcb_engine::Slot& sl = e->slots[si];
+  if (sl.busy) return fail(e, DCB_ERR_STATE, "two submissions in flight: dcb_wait(ticket %lld) first",
+                           (long long)std::min(e->slots[0].ticket, e->slots[1].ticket));
   if (batch < 0 || batch > e->cfg.max_batch) return fail(e, DCB_ERR_INVALID, "batch %d outside [0, max_batch=%d]", batch, e->cfg.max_batch);
   sl.launches = 0;
   sl.ticket = e->next_ticket;
@@ -620,6 +763,21 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
   if (logits_out && !e->d_logits) { int rc = dev_alloc(e, &e->d_logits, mtok * kVocab); if (rc) return rc; }
   const bool rows_dev = flags & DCB_ROWS_ON_DEVICE;
   const bool out_dev = flags & DCB_OUT_ON_DEVICE;
+  if ((flags & DCB_STRICT_FP32) && (flags & DCB_FAST_BF16)) return fail(e, DCB_ERR_INVALID, "DCB_STRICT_FP32 and DCB_FAST_BF16 are exclusive");
+  const bool strict = (flags & DCB_STRICT_FP32) || (c.precision == DCB_PRECISION_FP32 && !(flags & DCB_FAST_BF16));
+  if (rows_dev && (reinterpret_cast<uintptr_t>(rows) & 15))
+    return fail(e, DCB_ERR_INVALID, "device-resident rows must be 16-byte aligned");
+  if (strict && !e->strict.emb) {
+    // workspace of the strict path, on first use: ~16 k tokens per chunk
+    dcb_engine::Strict& S = e->strict;
+    S.chunk_windows = std::max(1, std::min(c.max_batch, 16384 / L));
+    const size_t Mc = (size_t)S.chunk_windows * L;
+    int rc = 0;
+    if ((rc = dev_alloc(e, &S.emb, Mc * e->E)) || (rc = dev_alloc(e, &S.x, Mc * kD)) || (rc = dev_alloc(e, &S.y, Mc * kD)) ||
+        (rc = dev_alloc(e, &S.q, Mc * kD)) || (rc = dev_alloc(e, &S.k, Mc * kD)) || (rc = dev_alloc(e, &S.v, Mc * kD)) ||
+        (rc = dev_alloc(e, &S.att, Mc * kD)) || (rc = dev_alloc(e, &S.hid, Mc * c.filter_size)))
+      return rc;
+  }
   cudaStream_t st = e->stream;
   if (!rows_dev) {
     // The slot's previous forward (two submissions ago) was waited for before the slot was handed out again, so its
@@ -650,7 +808,28 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
     cudaEventRecord(sl.prof_events[sl.prof_used].second, st);
     ++sl.prof_used;
   };
-  for (int w0 = 0; w0 < batch; w0 += e->chunk_windows) {
+  auto make_head_at = [&](int w0) {
+    HeadParams hp{};
+    hp.x = e->d_x; hp.ln_g = e->d_fln_g; hp.ln_b = e->d_fln_b; hp.wfc = e->d_wfc; hp.bfc = e->d_bfc;
+    const size_t t0 = (size_t)w0 * L;
+    hp.bases = (out_dev ? bases_out : e->d_bases) + t0;
+    hp.quals = (out_dev ? quals_out : e->d_quals) + t0;
+    hp.probs = probs_out ? ((out_dev ? probs_out : e->d_probs) + t0 * kVocab) : nullptr;
+    hp.logits = logits_out ? ((out_dev ? logits_out : e->d_logits) + t0 * kVocab) : nullptr;
+    hp.calib_enabled = c.calibration_enabled;
+    hp.calib_thr = (float)c.calibration_threshold; hp.calib_w = (float)c.calibration_w; hp.calib_b = (float)c.calibration_b;
+    hp.calib_thr64 = c.calibration_threshold; hp.calib_w64 = c.calibration_w; hp.calib_b64 = c.calibration_b;
+    hp.max_q = (float)c.max_base_quality;
+    return hp;
+  };
+  if (strict) {
+    for (int w0 = 0; w0 < batch; w0 += e->strict.chunk_windows) {
+      const int bw = std::min(e->strict.chunk_windows, batch - w0);
+      launches += strict_forward_chunk(e, rows_base + (size_t)w0 * R * L, bw, make_head_at(w0), sl.d_status, st);
+    }
+    e->stack_last = false;
+  }
+  for (int w0 = 0; !strict && w0 < batch; w0 += e->chunk_windows) {
     const int bw = std::min(e->chunk_windows, batch - w0);
     const int Lw = e->Lw;
     const int M = bw * Lw;          // tokens in the (possibly window-aligned) layout
@@ -662,18 +841,8 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
       ++stage;
     };
     auto make_head = [&]() {
-      HeadParams hp{};
-      hp.x = e->d_x; hp.ln_g = e->d_fln_g; hp.ln_b = e->d_fln_b; hp.wfc = e->d_wfc; hp.bfc = e->d_bfc;
-      const size_t t0 = (size_t)w0 * L;
-      hp.bases = (out_dev ? bases_out : e->d_bases) + t0;
-      hp.quals = (out_dev ? quals_out : e->d_quals) + t0;
-      hp.probs = probs_out ? ((out_dev ? probs_out : e->d_probs) + t0 * kVocab) : nullptr;
-      hp.logits = logits_out ? ((out_dev ? logits_out : e->d_logits) + t0 * kVocab) : nullptr;
+      HeadParams hp = make_head_at(w0);
       hp.M = M; hp.L = L; hp.Lw = Lw;
-      hp.calib_enabled = c.calibration_enabled;
-      hp.calib_thr = (float)c.calibration_threshold; hp.calib_w = (float)c.calibration_w; hp.calib_b = (float)c.calibration_b;
-      hp.calib_thr64 = c.calibration_threshold; hp.calib_w64 = c.calibration_w; hp.calib_b64 = c.calibration_b;
-      hp.max_q = (float)c.max_base_quality;
       return hp;
     };
     const bool use_stack = e->stack && e->fuse_qa && e->ffn_pair && e->fuse_oproj && e->fuse_embed && !e->debug && Lw == kTileM &&
@@ -806,8 +975,11 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
 
 int dcb_wait(dcb_engine* e, int64_t ticket) {
   if (!e) return DCB_ERR_INVALID;
-  dcb_engine::Slot& sl = e->slots[ticket & 1];
-  if (ticket < 0 || !sl.busy || sl.ticket != ticket) return fail(e, DCB_ERR_STATE, "dcb_wait: ticket %lld is not in flight", (long long)ticket);
+  int si = -1;
+  for (int i = 0; i < 2; ++i)
+    if (e->slots[i].busy && e->slots[i].ticket == ticket) si = i;
+  if (ticket < 0 || si < 0) return fail(e, DCB_ERR_STATE, "dcb_wait: ticket %lld is not in flight", (long long)ticket);
+  dcb_engine::Slot& sl = e->slots[si];
   sl.busy = false;
   if (!sl.used) { e->last_ms = 0.f; e->last_launches = 0; return DCB_OK; }   // empty batch
   CU(e, cudaSetDevice(e->cfg.device));

@@ -18,6 +18,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include "head_finish.cuh"
 #include "sm100.cuh"
 
 namespace dcb {
@@ -2561,51 +2562,6 @@ qkv_attn_pair_kernel(const __nv_bfloat16* __restrict__ a_img, const uint8_t* __r
   }
 }
 
-// logits (+ fc1 bias) -> softmax -> argmax -> Phred -> calibration -> cap / round -> ASCII, for one token
-// (networks.py:238, quick_inference.py:377-414).  Shared by head_kernel and the fused tail of stack_pair_kernel.
-__device__ __forceinline__ void head_finish(const HeadParams& p, float (&lg)[kVocab], size_t oidx) {
-  float mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < kVocab; ++j) { lg[j] += p.bfc[j]; mx = fmaxf(mx, lg[j]); }
-  // softmax (networks.py:238), float32
-  float ex[kVocab], sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < kVocab; ++j) { ex[j] = expf(lg[j] - mx); sum += ex[j]; }
-  float pr[kVocab], pmax = -1.f;
-  int arg = 0;
-#pragma unroll
-  for (int j = 0; j < kVocab; ++j) {
-    pr[j] = ex[j] / sum;
-    if (pr[j] > pmax) { pmax = pr[j]; arg = j; }  // first maximum wins (np.argmax)
-  }
-  // quick_inference.py:378-389
-  const float err = 1.f - pmax;
-  float qf = -10.f * log10f(err);  // err == 0 -> +inf
-  int qi;
-  if (p.calib_enabled && p.calib_thr != 0.f) {
-    // np.where branch of calibrate_quality_scores promotes to float64 (calibration_lib.py:93-99)
-    const double qd = (double)qf;
-    const bool above = qd > p.calib_thr64;
-    const double qc = qd * (above ? p.calib_w64 : 1.0) + (above ? p.calib_b64 : 0.0);
-    qi = (int)rint(fmin(qc, (double)p.max_q));
-  } else {
-    if (p.calib_enabled) qf = qf * p.calib_w + p.calib_b;    // float32 path (threshold == 0)
-    qi = (int)rintf(fminf(qf, p.max_q));                     // np.round: half to even
-  }
-  qi = qi < 0 ? 0 : qi;
-  const char vocab[kVocab] = {' ', 'A', 'T', 'C', 'G'};
-  p.bases[oidx] = (uint8_t)vocab[arg];
-  p.quals[oidx] = (uint8_t)(qi + 33);
-  if (p.probs) {
-#pragma unroll
-    for (int j = 0; j < kVocab; ++j) p.probs[oidx * kVocab + j] = pr[j];
-  }
-  if (p.logits) {
-#pragma unroll
-    for (int j = 0; j < kVocab; ++j) p.logits[oidx * kVocab + j] = lg[j];
-  }
-}
-
 #include "stack_kernel.cuh"
 
 // =====================================================================================
@@ -2674,6 +2630,16 @@ head_kernel(HeadParams p) {
 // =====================================================================================
 // launchers
 // =====================================================================================
+// Environment switches exist only in the developer build (-DDCB_DEV_SWITCHES, libdcb200_dev.so).
+static const char* dev_env(const char* name) {
+#ifdef DCB_DEV_SWITCHES
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -2797,7 +2763,7 @@ void launch_stack(float* x, int ntiles, int L, int win, const StackParams& p, co
     int nc = 0;
     if (cudaOccupancyMaxActiveClusters(&nc, stack_pair_kernel, &cfg) != cudaSuccess || nc <= 0) nc = num_sms() / 2;
     max_pairs = nc;
-    if (getenv("DCB_VERBOSE")) fprintf(stderr, "[dcb200] stack kernel: %d co-resident CTA pairs\n", nc);
+    if (dev_env("DCB_VERBOSE")) fprintf(stderr, "[dcb200] stack kernel: %d co-resident CTA pairs\n", nc);
   }
   int pairs = (ntiles + 1) / 2;
   if (pairs > max_pairs) pairs = max_pairs;
@@ -2835,7 +2801,7 @@ static void launch_ffn_cs(const __nv_bfloat16* a_img, const uint8_t* w_img, cons
     int nc = 0;
     if (cudaOccupancyMaxActiveClusters(&nc, ffn_kernel<CS>, &cfg) != cudaSuccess || nc <= 0) nc = num_sms() / CS;
     max_clusters = nc;
-    if (getenv("DCB_VERBOSE")) fprintf(stderr, "[dcb200] ffn cluster size %d: %d co-resident clusters\n", CS, nc);
+    if (dev_env("DCB_VERBOSE")) fprintf(stderr, "[dcb200] ffn cluster size %d: %d co-resident clusters\n", CS, nc);
   }
   int clusters = (ntiles + CS - 1) / CS;
   if (clusters > max_clusters) clusters = max_clusters;
@@ -2856,14 +2822,14 @@ void launch_ffn_pair(const __nv_bfloat16* a_img, const uint8_t* w2img, const flo
     int nc = 0;
     if (cudaOccupancyMaxActiveClusters(&nc, ffn_pair_kernel<false>, &cfg) != cudaSuccess || nc <= 0) nc = num_sms() / 2;
     max_pairs = nc;
-    if (const char* env = getenv("DCB_FFN_MAX_PAIRS")) { const int v = atoi(env); if (v > 0 && v < max_pairs) max_pairs = v; }
-    if (getenv("DCB_VERBOSE")) fprintf(stderr, "[dcb200] ffn pair kernel: %d co-resident CTA pairs\n", nc);
+    if (const char* env = dev_env("DCB_FFN_MAX_PAIRS")) { const int v = atoi(env); if (v > 0 && v < max_pairs) max_pairs = v; }
+    if (dev_env("DCB_VERBOSE")) fprintf(stderr, "[dcb200] ffn pair kernel: %d co-resident CTA pairs\n", nc);
   }
   int pairs = (ntiles + 1) / 2;
   if (pairs > max_pairs) pairs = max_pairs;
   cfg.gridDim = dim3(pairs * 2);
   static int stagger = -1;
-  if (stagger < 0) { const char* env = getenv("DCB_FFN_STAGGER"); stagger = env ? atoi(env) : 0; }
+  if (stagger < 0) { const char* env = dev_env("DCB_FFN_STAGGER"); stagger = env ? atoi(env) : 0; }
   if (wo2img)
     cudaLaunchKernelEx(&cfg, ffn_pair_kernel<true>, a_img, w2img, b1, ff, ntiles, epi, stagger, wo2img, mid_ln_g, mid_ln_b);
   else
@@ -2873,7 +2839,7 @@ void launch_ffn_pair(const __nv_bfloat16* a_img, const uint8_t* w2img, const flo
 void launch_ffn(const __nv_bfloat16* a_img, const uint8_t* w_img, const float* b1, int ff, int ntiles,
                 const RowEpi& epi, cudaStream_t st) {
   if (!g_ffn_cluster) {
-    const char* env = getenv("DCB_FFN_CLUSTER");
+    const char* env = dev_env("DCB_FFN_CLUSTER");
     g_ffn_cluster = env ? atoi(env) : 1;   // measured: multicast does not pay here (smem-bound, not L2-bound)
     if (g_ffn_cluster != 1 && g_ffn_cluster != 2 && g_ffn_cluster != 4) g_ffn_cluster = 1;
   }

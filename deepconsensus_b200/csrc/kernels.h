@@ -52,4 +52,15 @@ void launch_head(const HeadParams& p, int ntiles, cudaStream_t st);
 void launch_stitch(const uint8_t* bases, const uint8_t* quals, int L, const int32_t* zmw_start, int n_zmw,
                    uint8_t* seq_out, uint8_t* qual_out, int32_t* len_out, cudaStream_t st);
 
+
+// ---- strict-fp32 path (strict_kernels.cu): row-major float32 activations, windows packed back to back
+void launch_strict_embed(const float* rows, int R, int L, int E, int nwindows, const StrictEmbedRow* meta,
+                         const float* tables, float* emb, int* status, cudaStream_t st);
+void launch_strict_gemm(const float* A, const float* B, float* C, int M, int N, int K, const StrictEpi& ep,
+                        cudaStream_t st);
+void launch_strict_layernorm(const float* x, float* y, int M, const float* g, const float* b, cudaStream_t st);
+void launch_strict_attention(const float* q, const float* k, const float* v, float* o, int nwindows, int L, int win,
+                             cudaStream_t st);
+void launch_strict_head(const float* x, int M, const HeadParams& hp, cudaStream_t st);
+
 }  // namespace dcb

@@ -30,6 +30,10 @@ _lib = None
 
 DCB_ROWS_ON_DEVICE = 1
 DCB_OUT_ON_DEVICE = 2
+DCB_STRICT_FP32 = 4
+DCB_FAST_BF16 = 8
+DCB_PRECISION_BF16 = 0
+DCB_PRECISION_FP32 = 1
 
 
 class DcbError(RuntimeError):
@@ -56,7 +60,8 @@ class DcbConfig(ctypes.Structure):
       ("calibration_threshold", ctypes.c_double), ("calibration_w", ctypes.c_double),
       ("calibration_b", ctypes.c_double),
       ("max_batch", ctypes.c_int32), ("chunk_tiles", ctypes.c_int32),
-      ("reserved", ctypes.c_int32 * 6),
+      ("precision", ctypes.c_int32),
+      ("reserved", ctypes.c_int32 * 5),
   ]
 
 
@@ -68,10 +73,12 @@ class DcbTensor(ctypes.Structure):
 # Every symbol include/dcb200.h declares; tests check the built library exports all of them.
 ABI_SYMBOLS = (
     "dcb_create", "dcb_load_weights", "dcb_forward", "dcb_submit", "dcb_wait", "dcb_stitch", "dcb_last_forward_ms",
-    "dcb_last_forward_launches", "dcb_set_profile", "dcb_get_profile", "dcb_get_profile_kernels", "dcb_set_debug", "dcb_debug_residual", "dcb_debug_trace", "dcb_alloc_host",
+    "dcb_last_forward_launches", "dcb_set_profile", "dcb_get_profile", "dcb_get_profile_kernels", "dcb_alloc_host",
     "dcb_free_host", "dcb_alloc_device", "dcb_free_device", "dcb_memcpy_h2d", "dcb_memcpy_d2h",
     "dcb_synchronize", "dcb_last_error", "dcb_version", "dcb_destroy",
 )
+# include/dcb200_debug.h: developer / test hooks, not part of the drop-in boundary
+DEBUG_SYMBOLS = ("dcb_set_debug", "dcb_debug_residual", "dcb_debug_trace")
 
 
 def library_path() -> str:
@@ -81,13 +88,29 @@ def library_path() -> str:
 def load_library() -> ctypes.CDLL:
   """Loads libdcb200.so (built in-tree by `__graft_entry__.build()` / csrc/build.sh)."""
   global _lib
-  if _lib is not None:
-    return _lib
-  if not os.path.exists(_LIB_PATH):
+  if _lib is None:
+    _lib = _load(_LIB_PATH)
+  return _lib
+
+
+_dev_lib = None
+
+
+def load_dev_library() -> ctypes.CDLL:
+  """libdcb200_dev.so: the same sources built with -DDCB_DEV_SWITCHES, where DCB_* environment variables select the
+  measured alternative kernel paths (tests and scripts only; pass as B200Model(..., library=...))."""
+  global _dev_lib
+  if _dev_lib is None:
+    _dev_lib = _load(os.path.join(os.path.dirname(_LIB_PATH), "libdcb200_dev.so"))
+  return _dev_lib
+
+
+def _load(path: str) -> ctypes.CDLL:
+  if not os.path.exists(path):
     raise FileNotFoundError(
         "%s not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
-        "g.build()'); the dcb200 engine has no CPU fallback" % _LIB_PATH)
-  lib = ctypes.CDLL(_LIB_PATH)
+        "g.build()'); the dcb200 engine has no CPU fallback" % path)
+  lib = ctypes.CDLL(path)
   vp, i32, u32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint32
   lib.dcb_create.argtypes = [ctypes.POINTER(DcbConfig), ctypes.POINTER(vp)]
   lib.dcb_load_weights.argtypes = [vp, ctypes.POINTER(DcbTensor), i32]
@@ -116,15 +139,16 @@ def load_library() -> ctypes.CDLL:
   lib.dcb_version.restype = ctypes.c_char_p
   lib.dcb_destroy.argtypes = [vp]
   lib.dcb_destroy.restype = None
-  _lib = lib
   return lib
 
 
 def make_config(params: params_lib.Params, max_batch: int, device: int = 0,
                 max_base_quality: int = 93,
                 calibration: Optional[calibration_lib.QualityCalibrationValues] = None,
-                chunk_tiles: int = 0) -> DcbConfig:
+                chunk_tiles: int = 0, precision: str = "bf16") -> DcbConfig:
   """params (params.json surface) + InferenceOptions fields -> dcb_config."""
+  if precision not in ("bf16", "fp32"):
+    raise ValueError("precision must be 'bf16' (tensor cores) or 'fp32' (strict, the reference's arithmetic)")
   c = DcbConfig()
   c.struct_size = ctypes.sizeof(DcbConfig)
   c.device = device
@@ -147,6 +171,7 @@ def make_config(params: params_lib.Params, max_batch: int, device: int = 0,
     c.calibration_w, c.calibration_b = float(calibration.w), float(calibration.b)
   c.max_batch = int(max_batch)
   c.chunk_tiles = int(chunk_tiles)
+  c.precision = DCB_PRECISION_FP32 if precision == "fp32" else DCB_PRECISION_BF16
   for need in ("use_bases", "use_pw", "use_ip", "use_strand", "use_ccs", "use_sn"):
     if not params.get(need, True):
       raise DcbError(-1, "params.%s=False is not supported by the dcb200 engine" % need)
@@ -169,14 +194,17 @@ class B200Model:
   def __init__(self, params: params_lib.Params, weights: weights_lib.Weights, max_batch: int = 1024,
                device: int = 0, max_base_quality: int = 93,
                calibration: Optional[calibration_lib.QualityCalibrationValues] = None,
-               chunk_tiles: int = 0):
-    self._lib = load_library()
+               chunk_tiles: int = 0, precision: str = "bf16", library: Optional[ctypes.CDLL] = None):
+    """precision: "bf16" = tensor-core path (default); "fp32" = strict path, the reference's float32 arithmetic
+    (identical bases wherever the float32 top-2 logit margin exceeds 1e-3; ~25x slower).  Either can be overridden
+    per call with forward(..., strict=True/False)."""
+    self._lib = library if library is not None else load_library()
     self._handle = ctypes.c_void_p()
     self.params = params
     self.max_batch = max_batch
     self.max_length = int(params.max_length)
     self.total_rows = params_lib.get_total_rows(params.max_passes, params.use_ccs_bq)
-    cfg = make_config(params, max_batch, device, max_base_quality, calibration, chunk_tiles)
+    cfg = make_config(params, max_batch, device, max_base_quality, calibration, chunk_tiles, precision)
     rc = self._lib.dcb_create(ctypes.byref(cfg), ctypes.byref(self._handle))
     if rc:
       msg = self._lib.dcb_last_error(None).decode()
@@ -231,8 +259,12 @@ class B200Model:
                        (self.total_rows, self.max_length, rows.shape))
     return np.ascontiguousarray(rows, dtype=np.float32)
 
+  @staticmethod
+  def _precision_flag(strict: Optional[bool]) -> int:
+    return 0 if strict is None else (DCB_STRICT_FP32 if strict else DCB_FAST_BF16)
+
   def forward(self, rows: np.ndarray, want_probs: bool = False, want_logits: bool = False,
-              strict_input: bool = True) -> Dict[str, np.ndarray]:
+              strict_input: bool = True, strict: Optional[bool] = None) -> Dict[str, np.ndarray]:
     """rows float32 [B, R, L(,1)] -> dict(bases u8 [B,L], quals u8 [B,L], [probs], [logits]).
 
     Batches larger than `max_batch` are split, like `batch_examples` does with
@@ -249,8 +281,8 @@ class B200Model:
     for b0 in range(0, B, self.max_batch):
       b1 = min(B, b0 + self.max_batch)
       ptr = lambda k: out[k][b0:b1].ctypes.data_as(ctypes.c_void_p) if k in out else None
-      rc = self._lib.dcb_forward(self._handle, rows[b0:b1].ctypes.data_as(ctypes.c_void_p), b1 - b0, 0,
-                                 ptr("bases"), ptr("quals"), ptr("probs"), ptr("logits"))
+      rc = self._lib.dcb_forward(self._handle, rows[b0:b1].ctypes.data_as(ctypes.c_void_p), b1 - b0,
+                                 self._precision_flag(strict), ptr("bases"), ptr("quals"), ptr("probs"), ptr("logits"))
       self._check(rc, tolerate=() if strict_input else (-5,))
       ms += self.last_forward_ms()
       launches += self.last_forward_launches()
@@ -292,13 +324,15 @@ class B200Model:
     return st[key]
 
   def submit(self, rows: Optional[np.ndarray] = None, batch: Optional[int] = None, slot: Optional[int] = None,
-             want_probs: bool = False, want_logits: bool = False) -> Dict[str, Any]:
+             want_probs: bool = False, want_logits: bool = False, strict: Optional[bool] = None) -> Dict[str, Any]:
     """Enqueue one batch (<= max_batch windows) and return a handle for wait().  Either pass `rows` (copied into the
     slot's pinned staging) or fill staging_rows(slot)[:batch] yourself and pass `batch`.  At most two handles may be
     outstanding and they must be waited for in submission order."""
     busy = self.__dict__.setdefault("_slot_busy", {0: False, 1: False})
     if slot is None:
       slot = 1 - getattr(self, "_last_slot", 1)
+      if busy[slot] and not busy[1 - slot]:
+        slot = 1 - slot
     if busy[slot]:   # its pinned staging may still be read by the copy engine: refuse before touching it
       raise DcbError(-4, "two submissions in flight: wait() for the oldest first")
     self._last_slot = slot
@@ -315,7 +349,8 @@ class B200Model:
     probs = self._staging_opt(slot, "probs") if want_probs else None
     logits = self._staging_opt(slot, "logits") if want_logits else None
     ticket = ctypes.c_int64(-1)
-    self._check(self._lib.dcb_submit(self._handle, vp(st["rows"]), batch, 0, vp(st["bases"]), vp(st["quals"]),
+    self._check(self._lib.dcb_submit(self._handle, vp(st["rows"]), batch, self._precision_flag(strict),
+                                     vp(st["bases"]), vp(st["quals"]),
                                      vp(probs) if want_probs else None, vp(logits) if want_logits else None,
                                      ctypes.byref(ticket)))
     busy[slot] = True
@@ -336,17 +371,32 @@ class B200Model:
     self.last_ms, self.last_launches = self.last_forward_ms(), self.last_forward_launches()
     return out
 
+  def drain(self, *handles) -> None:
+    """Retire outstanding submissions whose results are no longer wanted (error paths): waits for each handle and
+    swallows its status, so the engine's and this object's pipeline slots are free again."""
+    for h in handles:
+      if h is None:
+        continue
+      try:
+        self.wait(h, strict_input=False)
+      except DcbError:
+        pass
+
   def forward_batches(self, batches, want_probs: bool = False, want_logits: bool = False,
-                      strict_input: bool = True):
+                      strict_input: bool = True, strict: Optional[bool] = None):
     """Pipelined forward over an iterable of row batches; yields one output dict per batch, in order."""
     pending = None
-    for rows in batches:
-      h = self.submit(rows, want_probs=want_probs, want_logits=want_logits)
+    try:
+      for rows in batches:
+        h = self.submit(rows, want_probs=want_probs, want_logits=want_logits, strict=strict)
+        prev, pending = pending, h
+        if prev is not None:
+          yield self.wait(prev, strict_input)
       if pending is not None:
-        yield self.wait(pending, strict_input)
-      pending = h
-    if pending is not None:
-      yield self.wait(pending, strict_input)
+        h, pending = pending, None
+        yield self.wait(h, strict_input)
+    finally:
+      self.drain(pending)
 
   # -- stitch: per-read window concatenation + gap compaction on the device -------------------------
   def stitch(self, bases, quals, zmw_start: np.ndarray, n_windows: Optional[int] = None,

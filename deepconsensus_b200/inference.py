@@ -97,16 +97,26 @@ def run_model_on_examples(feature_dicts: List[Dict[str, Any]], model: engine_lib
           sequence=bases[i].tobytes().decode("ascii"),
           quality_string=quals[i].tobytes().decode("ascii")))
 
-  # Two batches in flight: while the device scores batch i, batch i+1 is stacked and copied (dcb_submit / dcb_wait).
-  pending = None
-  for data in batch_examples(feature_dicts, model_params, options):
-    handle = model.submit(data["rows"])
-    if pending is not None:
-      collect(pending[0], model.wait(pending[1]))
-    pending = (data, handle)
-  if pending is not None:
-    collect(pending[0], model.wait(pending[1]))
+  _pipelined(model, batch_examples(feature_dicts, model_params, options), collect)
   return predictions
+
+
+def _pipelined(model: engine_lib.B200Model, batches: Iterable[Dict[str, Any]], collect) -> None:
+  """Two batches in flight: while the device scores batch i, batch i+1 is stacked and copied (dcb_submit / dcb_wait).
+  If a wait raises (e.g. DCB_ERR_INPUT_RANGE), the younger submission is retired too, so the model stays usable."""
+  pending = None
+  try:
+    for data in batches:
+      handle = model.submit(data["rows"])
+      prev, pending = pending, (data, handle)
+      if prev is not None:
+        collect(prev[0], model.wait(prev[1]))
+    if pending is not None:
+      last, pending = pending, None
+      collect(last[0], model.wait(last[1]))
+  finally:
+    if pending is not None:
+      model.drain(pending[1])
 
 
 def process_skipped_window(feature_dict: Dict[str, Any], options: InferenceOptions) -> stitch_utils.DCModelOutput:
@@ -149,17 +159,22 @@ def split_skipped_windows(feature_dicts_for_zmws: Iterable[Iterable[Dict[str, An
 
 def run_model_and_stitch(feature_dicts: List[Dict[str, Any]], model: engine_lib.B200Model,
                          model_params: params_lib.Params, options: InferenceOptions,
-                         outcome_counter: stitch_utils.OutcomeCounter) -> List[Optional[str]]:
-  """Windows -> FASTQ records without per-window Python objects: `run_model_on_examples` followed, per read, by
-  `stitch_utils.stitch_to_fastq` (quick_inference.py:341-415 and :721-760), with the byte work on the device.
+                         outcome_counter: stitch_utils.OutcomeCounter,
+                         skipped_outputs: Optional[List[stitch_utils.DCModelOutput]] = None
+                         ) -> List[Optional[str]]:
+  """Windows -> FASTQ records without per-window Python objects: `run_model_on_examples`, the merge with the windows
+  that bypassed the model, the sort, and per read `stitch_utils.stitch_to_fastq` (quick_inference.py:341-415, :686 and
+  :721-760), with the byte work on the device.
 
-  `feature_dicts` must be grouped by read (`name`) and sorted by `window_pos` inside a read, as `run()` sorts the
-  model outputs before stitching (quick_inference.py:721-728).  Returns one FASTQ record (or None when a filter
-  drops the read) per read, in input order; `outcome_counter` is updated like the reference's.
+  `feature_dicts`: the windows to score (the `for_model` list of `split_skipped_windows`).  `skipped_outputs`: the
+  DCModelOutputs `split_skipped_windows` produced for overflow / high-quality windows (`process_skipped_window`); they
+  are interleaved with the model's outputs exactly as the reference does -- concatenate, sort by (molecule_name,
+  window_pos), group by name (quick_inference.py:686,721-736).  Returns one FASTQ record (or None when a filter drops
+  the read) per read, in sorted-name order; `outcome_counter` is updated like the reference's.
   """
   from deepconsensus_b200 import stitch_gpu
+  L = int(model_params.max_length)
   names, positions, bases, quals = [], [], [], []
-  pending = None
 
   def collect(data, out):
     bases.append(out["bases"])
@@ -167,18 +182,30 @@ def run_model_and_stitch(feature_dicts: List[Dict[str, Any]], model: engine_lib.
     names.extend(_as_str(x) for x in data["name"])
     positions.extend(int(x) for x in data["window_pos"])
 
-  for data in batch_examples(feature_dicts, model_params, options):
-    handle = model.submit(data["rows"])
-    if pending is not None:
-      collect(pending[0], model.wait(pending[1]))
-    pending = (data, handle)
-  if pending is not None:
-    collect(pending[0], model.wait(pending[1]))
+  _pipelined(model, batch_examples(feature_dicts, model_params, options), collect)
+  if skipped_outputs:
+    sb = np.empty((len(skipped_outputs), L), np.uint8)
+    sq = np.empty((len(skipped_outputs), L), np.uint8)
+    for i, o in enumerate(skipped_outputs):
+      seq, qual = o.sequence.encode("latin-1"), o.quality_string.encode("latin-1")
+      if len(seq) != L or len(qual) != L:
+        raise ValueError("skipped window %s@%s is not %d characters long" % (o.molecule_name, o.window_pos, L))
+      sb[i] = np.frombuffer(seq, np.uint8)
+      sq[i] = np.frombuffer(qual, np.uint8)
+      names.append(_as_str(o.molecule_name))
+      positions.append(int(o.window_pos))
+    bases.append(sb)
+    quals.append(sq)
   if not names:
     return []
-  return stitch_gpu.stitch_batch_to_fastq(model, np.concatenate(bases), np.concatenate(quals), names, positions,
-                                          model_params.max_length, options.min_quality, options.min_length,
-                                          outcome_counter)
+  all_b, all_q = np.concatenate(bases), np.concatenate(quals)
+  order = sorted(range(len(names)), key=lambda i: (names[i], positions[i]))     # quick_inference.py:721-728
+  if order != list(range(len(names))):
+    all_b, all_q = all_b[order], all_q[order]
+    names = [names[i] for i in order]
+    positions = [positions[i] for i in order]
+  return stitch_gpu.stitch_batch_to_fastq(model, all_b, all_q, names, positions, L, options.min_quality,
+                                          options.min_length, outcome_counter)
 
 
 def _as_str(x) -> str:

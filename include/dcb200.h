@@ -65,8 +65,20 @@ typedef struct dcb_config {
   /* engine sizing */
   int32_t max_batch;          /* largest B a single dcb_forward call will see */
   int32_t chunk_tiles;        /* 128-token tiles processed per pass through the layer stack; 0 = auto */
-  int32_t reserved[6];
+  int32_t precision;          /* DCB_PRECISION_BF16 (default) or DCB_PRECISION_FP32: which arithmetic dcb_forward uses
+                                 when the call does not say (see DCB_STRICT_FP32) */
+  int32_t reserved[5];
 } dcb_config;
+
+/* Arithmetic of the forward pass.
+ *   DCB_PRECISION_BF16  tensor-core path: bf16 operands, float32 accumulation / residual / LayerNorm / softmax.
+ *                       Logits differ from the reference's float32 graph by the operand rounding (0.02-0.1 on
+ *                       random-weight models), so the argmax can flip at near-ties.
+ *   DCB_PRECISION_FP32  the reference's own arithmetic (float32 operands and accumulation, networks.py:506-507):
+ *                       differs from the reference by summation order only (~1e-5 on logits); identical bases wherever
+ *                       the float32 top-2 logit margin exceeds 1e-3.  CUDA-core kernels, ~25x slower. */
+#define DCB_PRECISION_BF16 0
+#define DCB_PRECISION_FP32 1
 
 /* A named host tensor in the reference checkpoint's layout, e.g.
  * "model/encoder_stack/layers/0/0/layer/query_dense_layer/kernel" float32 [280,2,140]. */
@@ -78,8 +90,10 @@ typedef struct dcb_tensor {
 } dcb_tensor;
 
 /* flags for dcb_forward */
-#define DCB_ROWS_ON_DEVICE 1u   /* `rows` is a device pointer (already resident in HBM) */
+#define DCB_ROWS_ON_DEVICE 1u   /* `rows` is a device pointer (already resident in HBM); must be 16-byte aligned */
 #define DCB_OUT_ON_DEVICE 2u    /* output pointers are device pointers */
+#define DCB_STRICT_FP32 4u      /* this call runs in float32 (DCB_PRECISION_FP32) whatever dcb_config.precision says */
+#define DCB_FAST_BF16 8u        /* this call runs the bf16 tensor-core path whatever dcb_config.precision says */
 
 /* Create an engine on cfg->device.  Replaces model construction in initialize_model
  * (quick_inference.py:515-526). */
@@ -136,16 +150,6 @@ int dcb_get_profile(dcb_engine* e, float* ffn_ms_total, int32_t* ffn_launches, i
  * (condenser / unfused out-proj), [2] QKV GEMM, [3] attention, [4] FFN (+ fused out-proj), [5] head;
  * *fused_oproj = 1 when the attention out-projection runs inside the FFN kernel. */
 int dcb_get_profile_kernels(dcb_engine* e, float* ms6, int32_t* n6, int32_t* fused_oproj);
-
-/* Debug/test hook: copy the fp32 residual stream after stage `stage` of the LAST chunk of the
- * last forward into out [tokens, 280] (row-major).  stage 0 = condenser+pos-enc,
- * 1+2n = attention sub-layer n, 2+2n = FFN sub-layer n.  Requires dcb_set_debug(e, 1). */
-int dcb_set_debug(dcb_engine* e, int32_t enabled);
-int dcb_debug_residual(dcb_engine* e, int32_t stage, float* out, int64_t out_elems);
-
-/* Developer hook: cycle counters of the last ffn_kernel launch (only meaningful in a -DDCB_TRACE
- * build; 16 uint64 per CTA). */
-int dcb_debug_trace(uint64_t* out, int32_t n);
 
 /* Pinned host memory helpers (for callers that want async H2D/D2H). */
 int dcb_alloc_host(size_t bytes, void** out);

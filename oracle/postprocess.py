@@ -16,14 +16,24 @@ SEQ_VOCAB = " ATCG"   # dc_constants.py:39-41
 
 
 def quality_from_probs(probs: np.ndarray, max_base_quality: int = 93,
-                       calibration: Optional[Tuple[float, float, float]] = None
-                       ) -> Tuple[np.ndarray, np.ndarray]:
-  """probs [B,L,5] float32 -> (y_preds int64 [B,L], quality int32 [B,L])."""
+                       calibration: Optional[Tuple[float, float, float]] = None,
+                       log10: str = "libm") -> Tuple[np.ndarray, np.ndarray]:
+  """probs [B,L,5] float32 -> (y_preds int64 [B,L], quality int32 [B,L]).
+
+  log10="libm": `np.log10` on the float32 array, as the reference writes it -- the platform's float32 log10 (glibc /
+  SVML: <= 1 ulp, not always correctly rounded, so the value is platform-dependent in its last bit).
+  log10="exact": the correctly rounded float32 log10 (float64 log10 rounded once) -- the platform-independent
+  definition the device epilogue implements (csrc/head_finish.cuh); differs from "libm" only where the platform's
+  float32 log10 is off by an ulp AND that ulp crosses a rounding boundary of the final integer.
+  """
   probs = np.asarray(probs, dtype=np.float32)
   y_preds = np.argmax(probs, -1)                         # :377
   error_prob = 1 - np.max(probs, axis=-1)                # :378 (float32)
   with np.errstate(divide="ignore"):
-    q = -10 * np.log10(error_prob)                       # :379 (float32; inf when p == 1)
+    if log10 == "exact":
+      q = np.float32(-10) * np.log10(error_prob.astype(np.float64)).astype(np.float32)
+    else:
+      q = -10 * np.log10(error_prob)                     # :379 (float32; inf when p == 1)
   if calibration is not None:                            # :380-383
     thr, w, b = calibration
     if thr == 0:

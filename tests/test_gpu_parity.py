@@ -1,14 +1,25 @@
 """Parity of the CUDA engine (through the C-ABI / ctypes binding) against the oracle.  -m gpu.
 
-Tolerances (written here, per BASELINE.json north_star: "within fp32 logit tolerance (identical
-argmax bases)"): the engine computes its tensor-core contractions with bf16 operands and fp32
-accumulation, so
-  * |logit - oracle_fp32|  <= LOGIT_TOL_FP32 (absolute) everywhere,
-  * |logit - oracle_bf16|  <= LOGIT_TOL_EMU  where the oracle rounds at the same points,
-  * bases identical at every position whose fp32-oracle top-2 logit margin exceeds MARGIN
-    (positions inside the margin are near-ties that random-weight models produce in bulk),
-  * quality characters within +-1 at those positions, and
-  * the device epilogue is bit-exact given the device's own probabilities (integer/byte work).
+BASELINE.json north_star: outputs "must match the reference TF-CPU path on the same input windows within fp32 logit
+tolerance (identical argmax bases)".  Two arithmetic modes are checked, with the tolerances written here:
+
+STRICT (dcb_config.precision = DCB_PRECISION_FP32 / DCB_STRICT_FP32): float32 operands and accumulation, the
+reference's own arithmetic; differs from the oracle / the reference-code goldens by summation order only.
+  * |logit - oracle_fp32| <= STRICT_LOGIT_TOL (2e-4 absolute; measured ~2e-5),
+  * bases identical on EVERY position whose fp32 top-2 logit margin exceeds STRICT_MARGIN = 1e-3,
+  * quality characters within +-1 everywhere (a 1e-5 probability change can cross a rounding boundary of the integer
+    Phred score), exact on >= STRICT_QV_EXACT of the positions.
+
+DEFAULT (bf16 tensor-core operands, fp32 accumulation): the operand rounding moves logits by
+0.02-0.1 on these random-weight models (gates = ~1.2x the largest value measured over all cases):
+  * max |logit - oracle_fp32| <= LOGIT_TOL_FP32, RMS <= LOGIT_RMS_FP32, |logit - oracle_bf16| <= LOGIT_TOL_EMU,
+  * bases identical on >= BASES_MIN of ALL positions and on every position with fp32 margin > MARGIN,
+  * quality characters exact on >= QV_EXACT_MIN of all positions, within +-1 outside the margin.
+
+BOTH: the device epilogue (argmax / 1-p / -10 log10 / calibration / cap / round / ASCII) is bit-exact integer/byte work
+given the device's own probabilities -- np.array_equal against an independent NumPy evaluation of the same definition
+(float32 throughout, correctly rounded float32 log10; oracle.postprocess log10="exact"), and equal to the reference's
+literal `np.log10` form up to the platform libm's last-ulp differences (none on this image).
 """
 import ast
 import os
@@ -16,14 +27,20 @@ import os
 import numpy as np
 import pytest
 
-from deepconsensus_b200 import calibration, params as params_lib, synthetic, weights as weights_lib
+from deepconsensus_b200 import calibration, parity, params as params_lib, synthetic, weights as weights_lib
 from oracle import model as omodel, postprocess as opost
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_TOL_FP32 = 0.25
-LOGIT_TOL_EMU = 0.20
-MARGIN = 0.5
+STRICT_LOGIT_TOL = 2e-4
+STRICT_MARGIN = 1e-3
+STRICT_QV_EXACT = 0.995
+LOGIT_TOL_FP32 = 0.12
+LOGIT_RMS_FP32 = 0.02
+LOGIT_TOL_EMU = 0.12
+MARGIN = 0.25
+BASES_MIN = 0.99
+QV_EXACT_MIN = 0.96
 CAL = "0,1.197654,-0.99781"
 
 
@@ -34,33 +51,63 @@ def engine_mod():
   return engine
 
 
+def _cal_tuple(cal):
+  return (cal.threshold, cal.w, cal.b) if cal.enabled else None
+
+
+def _epilogue_exact(out, cal):
+  """The device epilogue on the device's own probabilities: bit-exact."""
+  yy, qq = opost.quality_from_probs(out["probs"], 93, _cal_tuple(cal), log10="exact")
+  sb, sq = opost.to_ascii(yy, qq)
+  assert np.array_equal(sb, out["bases"])
+  assert np.array_equal(sq, out["quals"])
+  y2, q2 = opost.quality_from_probs(out["probs"], 93, _cal_tuple(cal))           # the reference's literal np.log10 form
+  assert (opost.to_ascii(y2, q2)[1] != out["quals"]).mean() <= 1e-4
+
+
+def _ref_dict(logits, probs, cal):
+  y, q = opost.quality_from_probs(probs, 93, _cal_tuple(cal))
+  rb, rq = opost.to_ascii(y, q)
+  return dict(bases=rb, quals=rq, logits=logits)
+
+
+def _assert_strict(out, ref, what=""):
+  st = parity.compare(out, ref, margin=STRICT_MARGIN)
+  assert st["max_logit_err"] <= STRICT_LOGIT_TOL, (what, st)
+  assert st["base_mismatches_outside_margin"] == 0, (what, st)
+  assert st["max_dq"] <= 1 and st["qv_exact_pct"] >= 100 * STRICT_QV_EXACT, (what, st)
+  return st
+
+
+def _assert_default(out, ref, what=""):
+  st = parity.compare(out, ref, margin=MARGIN)
+  assert st["max_logit_err"] <= LOGIT_TOL_FP32 and st["rms_logit_err"] <= LOGIT_RMS_FP32, (what, st)
+  assert st["base_mismatches_outside_margin"] == 0 and st["bases_identical_pct"] >= 100 * BASES_MIN, (what, st)
+  assert st["qv_exact_pct"] >= 100 * QV_EXACT_MIN and st["max_dq_outside_margin"] <= 1, (what, st)
+  return st
+
+
 def _check(engine_mod, p, w, rows, cal_str=CAL, chunk_tiles=0, max_batch=None):
   cal = calibration.parse_calibration_string(cal_str)
   model = engine_mod.B200Model(p, w, max_batch=max_batch or rows.shape[0], calibration=cal, chunk_tiles=chunk_tiles)
-  out = model.forward(rows, want_probs=True, want_logits=True, strict_input=False)
+  out = model.forward(rows, want_probs=True, want_logits=True)           # strict_input: any id out of range raises
   launches = model.last_launches
+  strict = model.forward(rows, want_probs=True, want_logits=True, strict=True)
+  strict_launches = model.last_launches
   model.close()
-  assert launches > 0
-  cal_t = (cal.threshold, cal.w, cal.b) if cal.enabled else None
+  assert launches > 0 and strict_launches > launches
   ref = omodel.forward(rows, p, w)
   emu = omodel.forward(rows, p, w, emulate="bf16")
-  assert np.isfinite(out["logits"]).all()
-  assert np.abs(out["logits"] - ref["logits"]).max() <= LOGIT_TOL_FP32
+  refd = _ref_dict(ref["logits"], ref["probs"], cal)
+  for o in (out, strict):
+    assert np.isfinite(o["logits"]).all() and np.abs(o["probs"].sum(-1) - 1).max() < 1e-5
+    _epilogue_exact(o, cal)
+  _assert_strict(strict, refd)
+  assert np.abs(strict["probs"] - ref["probs"]).max() < 2e-5
+  _assert_default(out, refd)
   assert np.abs(out["logits"] - emu["logits"]).max() <= LOGIT_TOL_EMU
-  assert np.abs(out["probs"].sum(-1) - 1).max() < 1e-5
-  y, q = opost.quality_from_probs(ref["probs"], 93, cal_t)
-  rb, rq = opost.to_ascii(y, q)
-  srt = np.sort(ref["logits"], axis=-1)
-  safe = (srt[..., -1] - srt[..., -2]) > MARGIN
-  assert safe.mean() > 0.5
-  assert (out["bases"][safe] == rb[safe]).all()
-  assert np.abs(out["quals"].astype(int) - rq.astype(int))[safe].max() <= 1
-  assert (out["bases"] == rb).mean() > 0.98
-  # device epilogue is exact integer/byte work on the device's own probabilities
-  yy, qq = opost.quality_from_probs(out["probs"], 93, cal_t)
-  sb, sq = opost.to_ascii(yy, qq)
-  assert np.array_equal(sb, out["bases"])
-  assert (sq == out["quals"]).mean() > 0.999 and np.abs(sq.astype(int) - out["quals"].astype(int)).max() <= 1
+  # the default path against the strict path (both on the device): same gates
+  _assert_default(out, strict)
   return out
 
 
@@ -97,9 +144,9 @@ def test_ragged_batches_chunks_and_determinism(engine_mod):
   whole = _check(engine_mod, p, w, rows)
   model = engine_mod.B200Model(p, w, max_batch=16, chunk_tiles=3,     # 3 engine calls, several chunks each
                                calibration=calibration.parse_calibration_string(CAL))
-  split = model.forward(rows, want_logits=True, strict_input=False)
-  again = model.forward(rows, want_logits=True, strict_input=False)
-  one = model.forward(rows[:1], want_logits=True, strict_input=False)
+  split = model.forward(rows, want_logits=True)
+  again = model.forward(rows, want_logits=True)
+  one = model.forward(rows[:1], want_logits=True)
   model.close()
   assert np.array_equal(split["logits"], again["logits"])             # deterministic
   assert np.array_equal(split["bases"], whole["bases"]) and np.array_equal(split["quals"], whole["quals"])
@@ -174,13 +221,96 @@ def test_run_model_on_examples_and_stitch(engine_mod, golden_dir):
   assert fq is not None and fq.startswith("@" + first + "\n") and cnt.success == 1
 
 
+def test_run_model_and_stitch_merges_skipped_windows(engine_mod, golden_dir):
+  """The reference concatenates predictions_from_model + predictions_for_skipped_windows, sorts by (name, window_pos)
+  and stitches per read (quick_inference.py:657-686,721-736); skip_windows_above=45 is the default and overflow
+  windows always bypass the model.  run_model_and_stitch(..., skipped_outputs=...) must give the same FASTQ records as
+  that flow built from per-window objects, read for read -- including reads that consist only of skipped windows."""
+  import itertools
+  from deepconsensus_b200 import inference, stitch_utils
+  z = np.load(os.path.join(golden_dir, "real_windows_human_1m.npz"))
+  rows, names, pos = z["rows"], z["names"], z["window_pos"]
+  p = params_lib.synthetic_params(20, 100, num_hidden_layers=2)
+  w = weights_lib.init_weights(p, seed=15)
+  cal = calibration.parse_calibration_string(CAL)
+  opts = inference.InferenceOptions(max_length=100, example_height=85, max_passes=20, min_quality=0, min_length=0,
+                                    batch_size=16, use_ccs_bq=False, cpus=0, skip_windows_above=45,
+                                    use_saved_model=False, max_base_quality=93, dc_calibration_values=cal,
+                                    ccs_calibration_values=calibration.parse_calibration_string("skip"))
+  model, p = inference.initialize_model("", p, opts, weights=w)
+  rng = np.random.default_rng(3)
+  by_zmw = {}
+  for i in range(len(rows)):
+    kind = rng.integers(0, 4)                      # 0: overflow, 1: high-quality CCS (skipped), 2-3: scored
+    bq = np.full(100, 60 if kind == 1 else 20, np.int64)
+    fd = dict(subreads=rows[i][..., None], **{"subreads/num_passes": 3}, window_pos=int(pos[i]), name=str(names[i]),
+              ccs_base_quality_scores=bq, ec=1.0, np_num_passes=3, rq=0.99, rg="rg", overflow=bool(kind == 0))
+    by_zmw.setdefault(str(names[i]), []).append(fd)
+  first = sorted(by_zmw)[0]
+  for fd in by_zmw[first]:                         # one read made of skipped windows only
+    fd["overflow"] = True
+  for_model, skipped = inference.split_skipped_windows(by_zmw.values(), opts)
+  assert skipped and for_model and len(skipped) + len(for_model) == len(rows)
+  # the reference flow on per-window objects
+  preds = inference.run_model_on_examples(for_model, model, p, opts) + skipped
+  preds = sorted(preds, key=lambda dc: (dc.molecule_name, dc.window_pos))
+  want, want_cnt = [], stitch_utils.OutcomeCounter()
+  for name, grp in itertools.groupby(preds, lambda dc: dc.molecule_name):
+    want.append(stitch_utils.stitch_to_fastq(name, list(grp), 100, 0, 0, want_cnt))
+  got_cnt = stitch_utils.OutcomeCounter()
+  got = inference.run_model_and_stitch(for_model, model, p, opts, got_cnt, skipped_outputs=skipped)
+  assert got == want and got_cnt.__dict__ == want_cnt.__dict__
+  assert sum(r is not None for r in got) >= 1
+  # dropping the skipped windows (the round-1 behaviour) is NOT equivalent
+  lost_cnt = stitch_utils.OutcomeCounter()
+  lost = inference.run_model_and_stitch(for_model, model, p, opts, lost_cnt)
+  assert lost != want
+  model.close()
+
+
+def test_pipeline_survives_errors_and_mixed_use(engine_mod):
+  """(1) a wait() that raises (out-of-range id) must not leave the younger submission in flight: the next call works;
+  (2) a blocking forward() between two submit()s must not collide with the slot of the outstanding handle."""
+  from deepconsensus_b200 import inference
+  p = params_lib.synthetic_params(20, 100, num_hidden_layers=1)
+  w = weights_lib.init_weights(p, seed=16)
+  model = engine_mod.B200Model(p, w, max_batch=8)
+  good = synthetic.make_rows(p, 8, seed=17)
+  bad = good.copy()
+  bad[0, 0, 0] = 9.0
+  want = model.forward(good)
+  with pytest.raises(engine_mod.DcbError):
+    list(model.forward_batches([bad, good, good]))
+  again = list(model.forward_batches([good, good[:3]]))
+  assert np.array_equal(again[0]["bases"], want["bases"]) and np.array_equal(again[1]["quals"], want["quals"][:3])
+  fds = [dict(subreads=r[..., None] if r.ndim == 2 else r, **{"subreads/num_passes": 3}, window_pos=0, name="m/%d/ccs" % i,
+              ccs_base_quality_scores=np.zeros(100), ec=1.0, np_num_passes=3, rq=0.99, rg="rg")
+         for i, r in enumerate(np.concatenate([bad, good, good]))]
+  opts = inference.InferenceOptions(max_length=100, example_height=85, max_passes=20, min_quality=0, min_length=0,
+                                    batch_size=8, use_ccs_bq=False, cpus=0, skip_windows_above=0, use_saved_model=False,
+                                    max_base_quality=93, dc_calibration_values=calibration.parse_calibration_string("skip"),
+                                    ccs_calibration_values=calibration.parse_calibration_string("skip"))
+  with pytest.raises(engine_mod.DcbError):
+    inference.run_model_on_examples(fds, model, p, opts)
+  assert len(inference.run_model_on_examples(fds[8:], model, p, opts)) == 16
+  h0 = model.submit(good)
+  mid = model.forward(good[:2])                     # consumes a ticket while h0 is outstanding
+  h1 = model.submit(good[:5])
+  o0, o1 = model.wait(h0), model.wait(h1)
+  assert np.array_equal(o0["bases"], want["bases"]) and np.array_equal(o1["bases"], want["bases"][:5])
+  assert np.array_equal(mid["quals"], want["quals"][:2])
+  model.close()
+
+
 def test_unfused_fallback_paths_agree_with_fused(engine_mod):
-  """DCB_STACK / DCB_FUSE_HEAD / DCB_FUSE_OPROJ / DCB_FUSE_EMBED / DCB_FUSE_QA / DCB_ALIGN / DCB_FFN_PAIR select measured alternatives of the same math;
-  they are read when an engine is created, so flip them around model construction."""
+  """DCB_STACK / DCB_FUSE_HEAD / DCB_FUSE_OPROJ / DCB_FUSE_EMBED / DCB_FUSE_QA / DCB_ALIGN / DCB_FFN_PAIR select measured
+  alternatives of the same math.  They exist only in the developer build (libdcb200_dev.so, -DDCB_DEV_SWITCHES) and
+  are read when an engine is created; the product library ignores the environment (checked first)."""
   p = params_lib.synthetic_params(20, 120, num_hidden_layers=2)
   w = weights_lib.init_weights(p, seed=21)
   rows = synthetic.make_rows(p, 5, seed=22)
   ref = omodel.forward(rows, p, w)["logits"]
+  dev = engine_mod.load_dev_library()
   outs = {}
   for name, env in (("fused", {}),                                     # default: whole stack in one kernel
                     ("per_layer", {"DCB_STACK": "0"}),                  # QKV+attention and out-proj+FFN kernels per layer
@@ -192,9 +322,15 @@ def test_unfused_fallback_paths_agree_with_fused(engine_mod):
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
     try:
-      model = engine_mod.B200Model(p, w, max_batch=8)
-      outs[name] = model.forward(rows, want_logits=True, strict_input=False)["logits"]
+      model = engine_mod.B200Model(p, w, max_batch=8, library=dev)
+      outs[name] = model.forward(rows, want_logits=True)["logits"]
+      launches = model.last_launches
       model.close()
+      if name == "per_layer":
+        prod = engine_mod.B200Model(p, w, max_batch=8)              # product library: the switch is ignored
+        prod.forward(rows)
+        assert prod.last_launches == 3 and launches > 3
+        prod.close()
     finally:
       for k, v in old.items():
         if v is None:
@@ -209,10 +345,12 @@ def test_unfused_fallback_paths_agree_with_fused(engine_mod):
   assert np.abs(outs["qkv2"] - outs["unfused"]).max() < 0.05
 
 
-@pytest.mark.parametrize("name", ["rezero_p20", "layernorm_p20", "rezero_p20_bq", "layernorm_p20_bq", "rezero_p5_win3"])
+@pytest.mark.parametrize("name", ["rezero_p20", "layernorm_p20", "rezero_p20_bq", "layernorm_p20_bq", "rezero_p5_win3",
+                                  "c2_p20_l120", "c5_p32_l200", "c5_p32_l200_ln_bq"])
 def test_engine_against_reference_code_goldens(engine_mod, golden_dir, name):
-  """CUDA path vs outputs of the reference's OWN model code (tests/golden/ref_model_*.npz, generated by
-  scripts/make_model_golden.py) -- no oracle in between."""
+  """CUDA paths vs outputs of the reference's OWN model code (tests/golden/ref_model_*.npz, generated by
+  scripts/make_model_golden.py) -- no oracle in between.  Includes the BASELINE configs[1] (P=20, L=120) and
+  configs[4] (P=32, L=200) shapes."""
   z = np.load(os.path.join(golden_dir, "ref_model_%s.npz" % name))
   p = params_lib.get_config(str(z["config"]))
   for k, v in ast.literal_eval(str(z["overrides"])).items():
@@ -220,17 +358,86 @@ def test_engine_against_reference_code_goldens(engine_mod, golden_dir, name):
   params_lib.modify_params(p, max_length=int(z["max_length"]))
   w = weights_lib.init_weights(p, seed=int(z["seed"]))
   rows = z["rows"]
+  cal = calibration.parse_calibration_string("skip")
   model = engine_mod.B200Model(p, w, max_batch=rows.shape[0])
-  out = model.forward(rows, want_probs=True, want_logits=True, strict_input=False)
+  out = model.forward(rows, want_probs=True, want_logits=True)
+  strict = model.forward(rows, want_probs=True, want_logits=True, strict=True)
   model.close()
-  assert np.abs(out["logits"] - z["logits"]).max() <= LOGIT_TOL_FP32
-  srt = np.sort(z["logits"], axis=-1)
-  safe = (srt[..., -1] - srt[..., -2]) > MARGIN
-  y, q = opost.quality_from_probs(z["probs"], 93, None)
-  rb, rq = opost.to_ascii(y, q)
-  assert (out["bases"][safe] == rb[safe]).all()
-  assert (out["bases"] == rb).mean() > 0.98
-  assert np.abs(out["probs"] - z["probs"]).max() < 0.05
+  refd = _ref_dict(z["logits"], z["probs"], cal)
+  _assert_strict(strict, refd, name)
+  assert np.abs(strict["probs"] - z["probs"]).max() < 2e-5
+  _assert_default(out, refd, name)
+  assert np.abs(out["probs"] - z["probs"]).max() < 0.03
+
+
+def test_strict_precision_engine_and_per_call_override(engine_mod):
+  """dcb_config.precision = DCB_PRECISION_FP32 makes strict the default of the engine; DCB_FAST_BF16 / DCB_STRICT_FP32
+  override per call; both flags at once are refused; ragged batches, chunking (batch > strict chunk) and determinism."""
+  p = params_lib.synthetic_params(20, 120, num_hidden_layers=2)
+  w = weights_lib.init_weights(p, seed=71)
+  rows = synthetic.make_rows(p, 150, seed=72)                # 150 x 120 tokens > the 16 k-token strict chunk
+  cal = calibration.parse_calibration_string(CAL)
+  ms = engine_mod.B200Model(p, w, max_batch=150, calibration=cal, precision="fp32")
+  mf = engine_mod.B200Model(p, w, max_batch=150, calibration=cal)
+  a = ms.forward(rows, want_logits=True, want_probs=True)
+  b = mf.forward(rows, want_logits=True, want_probs=True, strict=True)
+  assert np.array_equal(a["logits"], b["logits"]) and np.array_equal(a["quals"], b["quals"])
+  again = ms.forward(rows, want_logits=True)
+  assert np.array_equal(a["logits"], again["logits"])
+  sub = ms.forward(rows[140:147], want_logits=True)
+  assert np.array_equal(sub["logits"], a["logits"][140:147])          # windows are independent units
+  fast_on_strict = ms.forward(rows, want_logits=True, strict=False)
+  fast = mf.forward(rows, want_logits=True)
+  assert np.array_equal(fast_on_strict["logits"], fast["logits"])
+  piped = list(ms.forward_batches([rows[:150], rows[:33]], want_logits=True))
+  assert np.array_equal(piped[0]["logits"], a["logits"]) and np.array_equal(piped[1]["logits"], a["logits"][:33])
+  with pytest.raises(engine_mod.DcbError):
+    ms.forward_raw(rows.ctypes.data, 1, engine_mod.DCB_STRICT_FP32 | engine_mod.DCB_FAST_BF16,
+                   a["bases"].ctypes.data, a["quals"].ctypes.data)
+  ref = omodel.forward(rows[:16], p, w)
+  _assert_strict({k: v[:16] for k, v in a.items()}, _ref_dict(ref["logits"], ref["probs"], cal))
+  _epilogue_exact(a, cal)
+  bad = rows[:2].copy()
+  bad[1, 0, 3] = 9.0
+  with pytest.raises(engine_mod.DcbError) as ei:
+    ms.forward(bad)
+  assert ei.value.code == -5
+  ms.close()
+  mf.close()
+
+
+@pytest.mark.parametrize("cfg", ["c3_b4096", "c5_b8192"])
+def test_full_size_default_vs_strict_on_device(engine_mod, cfg):
+  """BASELINE configs[2] (checkpoint config: L=100, CCS-BQ, 5 pre-LN layers; batch 4096) and configs[4] (P=32, L=200,
+  batch 8192) at FULL size.  The oracle cannot score thousands of windows in test time, so: (1) the default path is
+  compared with the strict-fp32 path ON THE DEVICE over 512 windows spread over the whole batch (first / middle / last
+  CTA rounds and chunks), (2) the strict path is pinned to the oracle on 8 of those windows, (3) sub-batch
+  reproducibility and the exact epilogue hold over the full batch."""
+  if cfg == "c3_b4096":
+    p = params_lib.synthetic_params(20, 100, use_ccs_bq=True, num_hidden_layers=5, rezero=False)
+    B, seed = 4096, 301
+  else:
+    p = params_lib.synthetic_params(32, 200)
+    B, seed = 8192, 302
+  w = weights_lib.init_weights(p, seed=seed)
+  rows = synthetic.make_rows(p, B, seed=seed + 1)
+  cal = calibration.parse_calibration_string(CAL)
+  model = engine_mod.B200Model(p, w, max_batch=B, calibration=cal)
+  full = model.forward(rows, want_probs=True, want_logits=True)
+  _epilogue_exact(full, cal)
+  assert np.isfinite(full["logits"]).all()
+  idx = np.unique(np.concatenate([np.arange(0, 64), np.arange(B // 2 - 32, B // 2 + 32), np.arange(B - 64, B),
+                                  np.random.default_rng(5).choice(B, 320, replace=False)]))
+  sub = model.forward(rows[idx], want_probs=True, want_logits=True)
+  assert np.array_equal(sub["logits"], full["logits"][idx])              # windows are independent units
+  strict = model.forward(rows[idx], want_probs=True, want_logits=True, strict=True)
+  model.close()
+  st = _assert_default(sub, strict, cfg)
+  print(cfg, "default vs strict on %d windows:" % len(idx), parity.summary(st))
+  pick = idx[:: max(1, len(idx) // 8)][:8]
+  ref = omodel.forward(rows[pick], p, w)
+  sel = np.searchsorted(idx, pick)
+  _assert_strict({k: v[sel] for k, v in strict.items()}, _ref_dict(ref["logits"], ref["probs"], cal), cfg)
 
 
 def test_pipelined_submit_wait_matches_blocking_forward(engine_mod):
@@ -277,30 +484,35 @@ def test_full_size_properties_c2_batch_1024(engine_mod):
   rows = synthetic.make_rows(p, B, seed=102)
   cal = calibration.parse_calibration_string(CAL)
   model = engine_mod.B200Model(p, w, max_batch=B, calibration=cal)
-  full = model.forward(rows, want_probs=True, strict_input=False)
-  again = model.forward(rows, want_probs=True, strict_input=False)
+  full = model.forward(rows, want_probs=True)
+  again = model.forward(rows, want_probs=True)
   assert np.array_equal(full["probs"], again["probs"]) and np.array_equal(full["quals"], again["quals"])
   rng = np.random.default_rng(7)
   perm = rng.permutation(B)
-  permuted = model.forward(rows[perm], want_probs=True, strict_input=False)
+  permuted = model.forward(rows[perm], want_probs=True)
   assert np.array_equal(permuted["probs"], full["probs"][perm])
   assert np.array_equal(permuted["bases"], full["bases"][perm]) and np.array_equal(permuted["quals"], full["quals"][perm])
   for lo, hi in ((0, 1), (5, 12), (300, 811), (1023, 1024)):
-    sub = model.forward(rows[lo:hi], want_probs=True, strict_input=False)
+    sub = model.forward(rows[lo:hi], want_probs=True)
     assert np.array_equal(sub["probs"], full["probs"][lo:hi]), (lo, hi)
     assert np.array_equal(sub["bases"], full["bases"][lo:hi]) and np.array_equal(sub["quals"], full["quals"][lo:hi])
   assert np.isfinite(full["probs"]).all() and np.abs(full["probs"].sum(-1) - 1).max() < 1e-5
-  y, q = opost.quality_from_probs(full["probs"], 93, (cal.threshold, cal.w, cal.b))
-  sb, sq = opost.to_ascii(y, q)
-  assert np.array_equal(sb, full["bases"])
-  assert (sq == full["quals"]).mean() > 0.999 and np.abs(sq.astype(int) - full["quals"].astype(int)).max() <= 1
+  _epilogue_exact(full, cal)
+  # every one of the 1024 windows: default path against the strict-fp32 path, both on the device
+  fl = model.forward(rows, want_probs=True, want_logits=True)
+  assert np.array_equal(fl["probs"], full["probs"])
+  strict = model.forward(rows, want_probs=True, want_logits=True, strict=True)
+  st = _assert_default(fl, strict, "c2 b1024")
+  print("C2 B=1024 default vs strict:", parity.summary(st))
   ref = omodel.forward(rows[500:516], p, w)
+  refd = _ref_dict(ref["logits"], ref["probs"], cal)
+  _assert_strict({k: v[500:516] for k, v in strict.items()}, refd, "c2 b1024 strict")
+  _assert_default({k: v[500:516] for k, v in fl.items()}, refd, "c2 b1024 default")
   model.close()
   m2 = engine_mod.B200Model(p, w, max_batch=16, calibration=cal)
-  o16 = m2.forward(rows[500:516], want_probs=True, want_logits=True, strict_input=False)
+  o16 = m2.forward(rows[500:516], want_probs=True, want_logits=True)
   m2.close()
   assert np.array_equal(o16["probs"], full["probs"][500:516])
-  assert np.abs(o16["logits"] - ref["logits"]).max() <= LOGIT_TOL_FP32
 
 
 @pytest.mark.parametrize("layers,ff,rezero,win,L,B", [
@@ -315,7 +527,7 @@ def test_stack_kernel_corner_shapes(engine_mod, layers, ff, rezero, win, L, B):
   w = weights_lib.init_weights(p, seed=50 + layers)
   rows = synthetic.make_rows(p, B, seed=60 + layers)
   model = engine_mod.B200Model(p, w, max_batch=B)
-  out = model.forward(rows, want_logits=True, strict_input=False)
+  out = model.forward(rows, want_logits=True)
   launches = model.last_launches
   model.close()
   assert launches == (3 if layers <= 8 else 2 + 2 * layers)
@@ -386,7 +598,7 @@ def test_device_stitch_chain_from_forward_outputs(engine_mod):
   B, L = 37, 100
   model = engine_mod.B200Model(p, w, max_batch=B)
   rows = synthetic.make_rows(p, B, seed=78)
-  host = model.forward(rows, strict_input=False)
+  host = model.forward(rows)
   counts = [1, 5, 2, 9, 3, 7, 10]
   assert sum(counts) == B
   names, pos = [], []
