@@ -218,17 +218,34 @@ def load_weights_npz(path: str) -> weights_lib.Weights:
     return {k: z[k] for k in z.files}
 
 
+def load_weights(checkpoint_path: str) -> weights_lib.Weights:
+  """What `--checkpoint` may point at (quick_inference.py:515-529): a TF2 checkpoint prefix (".../checkpoint-50"), its
+  `.index` file, a directory holding a `checkpoint` state file -- read without TensorFlow by `tf_checkpoint` -- or an
+  .npz export of the same variables."""
+  if checkpoint_path.endswith(".npz"):
+    return load_weights_npz(checkpoint_path)
+  from deepconsensus_b200 import tf_checkpoint
+  return tf_checkpoint.load_variables(tf_checkpoint.resolve_prefix(checkpoint_path))
+
+
+def read_params_from_json(checkpoint_path: str) -> params_lib.Params:
+  """params.json next to the checkpoint (model_utils.read_params_from_json, model_utils.py:434-465)."""
+  return params_lib.read_params_from_json(checkpoint_path)
+
+
 def initialize_model(checkpoint_path: str, params: params_lib.Params, options: InferenceOptions,
-                     weights: Optional[weights_lib.Weights] = None, device: int = 0
+                     weights: Optional[weights_lib.Weights] = None, device: int = 0, precision: str = "bf16"
                      ) -> Tuple[engine_lib.B200Model, params_lib.Params]:
   """Builds the engine for `params` and loads variables (quick_inference.py:485-532).
 
-  `checkpoint_path` may point at an .npz export of the checkpoint's variables; `weights` overrides it.
+  `checkpoint_path`: a TF2 checkpoint (prefix / directory / .index) or an .npz export; `weights` overrides it.
+  Like the reference's `assert_existing_objects_matched()`, a variable the model needs but the checkpoint lacks (or
+  holds with another shape) raises; extra keys (optimizer slots) are ignored as with `expect_partial()`.
   """
   params_lib.modify_params(params, max_length=options.max_length, is_training=False)
   if weights is None:
-    weights = load_weights_npz(checkpoint_path)
+    weights = load_weights(checkpoint_path)
   model = engine_lib.B200Model(params, weights, max_batch=options.batch_size, device=device,
                                max_base_quality=options.max_base_quality,
-                               calibration=options.dc_calibration_values)
+                               calibration=options.dc_calibration_values, precision=precision)
   return model, params

@@ -240,12 +240,18 @@ def test_run_model_and_stitch_merges_skipped_windows(engine_mod, golden_dir):
   model, p = inference.initialize_model("", p, opts, weights=w)
   rng = np.random.default_rng(3)
   by_zmw = {}
+  keep_real = set(sorted(set(str(n) for n in names))[-2:])
   for i in range(len(rows)):
     kind = rng.integers(0, 4)                      # 0: overflow, 1: high-quality CCS (skipped), 2-3: scored
     bq = np.full(100, 60 if kind == 1 else 20, np.int64)
-    fd = dict(subreads=rows[i][..., None], **{"subreads/num_passes": 3}, window_pos=int(pos[i]), name=str(names[i]),
+    # window_pos re-indexed contiguously per read (get_full_sequence advances by max_length per window,
+    # stitch_utils.py:60-78); two reads keep their real CCS coordinates and therefore stitch to "missing window"
+    name = str(names[i])
+    k = len(by_zmw.get(name, []))
+    wp = int(pos[i]) if name in keep_real else k * 100
+    fd = dict(subreads=rows[i][..., None], **{"subreads/num_passes": 3}, window_pos=wp, name=name,
               ccs_base_quality_scores=bq, ec=1.0, np_num_passes=3, rq=0.99, rg="rg", overflow=bool(kind == 0))
-    by_zmw.setdefault(str(names[i]), []).append(fd)
+    by_zmw.setdefault(name, []).append(fd)
   first = sorted(by_zmw)[0]
   for fd in by_zmw[first]:                         # one read made of skipped windows only
     fd["overflow"] = True
@@ -260,7 +266,7 @@ def test_run_model_and_stitch_merges_skipped_windows(engine_mod, golden_dir):
   got_cnt = stitch_utils.OutcomeCounter()
   got = inference.run_model_and_stitch(for_model, model, p, opts, got_cnt, skipped_outputs=skipped)
   assert got == want and got_cnt.__dict__ == want_cnt.__dict__
-  assert sum(r is not None for r in got) >= 1
+  assert sum(r is not None for r in got) >= 3 and got_cnt.empty_sequence >= 1
   # dropping the skipped windows (the round-1 behaviour) is NOT equivalent
   lost_cnt = stitch_utils.OutcomeCounter()
   lost = inference.run_model_and_stitch(for_model, model, p, opts, lost_cnt)
