@@ -49,6 +49,33 @@ struct EmbedRow {
   int32_t vocab;   // table rows
 };
 
+// ------------------------------------------------------------------ packed input rows (include/dcb200.h)
+// Per window: u8 [P][L] base|strand<<3, u8 [P][L] pw, u8 [P][L] ip, u8 [L] ccs, (u8 [L] ccs_bq + 1), pad to 16 B,
+// f32 [4] SN.  Reference row r of the float32 layout (data_providers.py:81-113) maps to:
+struct PackedLayout {
+  int P, L, bq;
+  int R;          // reference rows: 4P + 5 + bq
+  int sn_off;     // byte offset of the four SN floats
+  int stride;     // bytes per window (multiple of 16)
+};
+__host__ __device__ inline PackedLayout make_packed_layout(int P, int L, int bq) {
+  PackedLayout pl;
+  pl.P = P; pl.L = L; pl.bq = bq; pl.R = 4 * P + 5 + bq;
+  pl.sn_off = ((3 * P + 1 + bq) * L + 15) & ~15;
+  pl.stride = pl.sn_off + 16;
+  return pl;
+}
+// The float32 value row r of the reference layout holds at position l (ccs_bq: the stored byte is value + 1).
+__host__ __device__ inline float packed_value(const PackedLayout& pl, const uint8_t* w, int r, int l) {
+  const int P = pl.P, L = pl.L;
+  if (r < P) return (float)(w[r * L + l] & 7);
+  if (r < 3 * P) return (float)w[r * L + l];
+  if (r < 4 * P) return (float)((w[(r - 3 * P) * L + l] >> 3) & 3);
+  if (r == 4 * P) return (float)w[3 * P * L + l];
+  if (pl.bq && r == 4 * P + 1) return (float)w[(3 * P + 1) * L + l] - 1.f;
+  return reinterpret_cast<const float*>(w + pl.sn_off)[r - (pl.R - 4)];
+}
+
 // ------------------------------------------------------------------ strict-fp32 path (strict_kernels.cu)
 // Per input row: clip / shift / vocabulary as EmbedRow, plus where its embedding lands in the concatenated vector and
 // which float32 table (pre-scaled by sqrt(width), row 0 zeroed) it reads.

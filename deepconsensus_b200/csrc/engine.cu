@@ -44,6 +44,7 @@ struct dcb_engine {
   dcb_config cfg{};
   std::string err;
   int R = 0, L = 0, Lw = 0, E = 0, Epad = 0, echunks = 0;   // Lw: tokens per window in the layout (>= L)
+  PackedLayout pl{};
   int chunk_tiles = 0, chunk_windows = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;        // compute (+ result D2H)
@@ -52,6 +53,7 @@ struct dcb_engine {
   // other buffer is reused in stream order.
   struct Slot {
     float* d_rows = nullptr;
+    uint8_t* d_packed = nullptr;        // packed rows of a dcb_submit_packed call (allocated on first use)
     int* d_status = nullptr;
     int* h_status = nullptr;            // pinned
     cudaEvent_t rows_ready = nullptr, ev0 = nullptr, ev1 = nullptr, done = nullptr;
@@ -255,6 +257,7 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   // otherwise windows are packed back to back
   if (align && e->L <= kTileM) e->Lw = kTileM;
   e->R = 4 * cfg->max_passes + (cfg->use_ccs_bq ? 6 : 5);  // data_providers.py:61-78
+  e->pl = make_packed_layout(cfg->max_passes, cfg->max_length, cfg->use_ccs_bq ? 1 : 0);
   e->E = cfg->max_passes * (cfg->per_base_hidden_size + cfg->pw_hidden_size + cfg->ip_hidden_size +
                             cfg->strand_hidden_size) +
          cfg->per_base_hidden_size + (cfg->use_ccs_bq ? cfg->ccs_bq_hidden_size : 0) +
@@ -739,8 +742,8 @@ int dcb_set_debug(dcb_engine* e, int32_t enabled) {
   return DCB_OK;
 }
 
-int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, uint8_t* bases_out,
-               uint8_t* quals_out, float* probs_out, float* logits_out, int64_t* ticket_out) {
+static int submit_impl(dcb_engine* e, const float* rows, const uint8_t* packed, int32_t batch, uint32_t flags,
+                       uint8_t* bases_out, uint8_t* quals_out, float* probs_out, float* logits_out, int64_t* ticket_out) {
   if (!e || !ticket_out) return DCB_ERR_INVALID;
   if (!e->weights_loaded) return fail(e, DCB_ERR_STATE, "dcb_forward before dcb_load_weights");
   // any free slot (preferring the alternating one): a blocking dcb_forward between two submissions must not collide
@@ -754,9 +757,10 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
   sl.launches = 0;
   sl.ticket = e->next_ticket;
   if (batch == 0) { sl.busy = true; sl.used = false; *ticket_out = e->next_ticket++; return DCB_OK; }
-  if (!rows || !bases_out || !quals_out) return fail(e, DCB_ERR_INVALID, "null rows / output buffer");
+  if ((!rows && !packed) || !bases_out || !quals_out) return fail(e, DCB_ERR_INVALID, "null rows / output buffer");
   CU(e, cudaSetDevice(e->cfg.device));
   const dcb_config& c = e->cfg;
+  if (packed && (c.pw_max > 255 || c.ip_max > 255)) return fail(e, DCB_ERR_INVALID, "packed rows need PW_MAX, IP_MAX <= 255");
   const int L = e->L, R = e->R;
   const size_t mtok = (size_t)c.max_batch * L;
   if (probs_out && !e->d_probs) { int rc = dev_alloc(e, &e->d_probs, mtok * kVocab); if (rc) return rc; }
@@ -765,7 +769,7 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
   const bool out_dev = flags & DCB_OUT_ON_DEVICE;
   if ((flags & DCB_STRICT_FP32) && (flags & DCB_FAST_BF16)) return fail(e, DCB_ERR_INVALID, "DCB_STRICT_FP32 and DCB_FAST_BF16 are exclusive");
   const bool strict = (flags & DCB_STRICT_FP32) || (c.precision == DCB_PRECISION_FP32 && !(flags & DCB_FAST_BF16));
-  if (rows_dev && (reinterpret_cast<uintptr_t>(rows) & 15))
+  if (rows_dev && ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(packed)) & 15))
     return fail(e, DCB_ERR_INVALID, "device-resident rows must be 16-byte aligned");
   if (strict && !e->strict.emb) {
     // workspace of the strict path, on first use: ~16 k tokens per chunk
@@ -779,17 +783,27 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
       return rc;
   }
   cudaStream_t st = e->stream;
+  if (packed && !rows_dev && !sl.d_packed) {
+    int rc = dev_alloc(e, &sl.d_packed, (size_t)c.max_batch * e->pl.stride);
+    if (rc) return rc;
+  }
   if (!rows_dev) {
     // The slot's previous forward (two submissions ago) was waited for before the slot was handed out again, so its
     // rows buffer is free; the copy overlaps whatever the compute stream is still running for the other slot.
-    CU(e, cudaMemcpyAsync(sl.d_rows, rows, (size_t)batch * R * L * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
+    if (packed) CU(e, cudaMemcpyAsync(sl.d_packed, packed, (size_t)batch * e->pl.stride, cudaMemcpyHostToDevice, e->copy_stream));
+    else CU(e, cudaMemcpyAsync(sl.d_rows, rows, (size_t)batch * R * L * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
     CU(e, cudaEventRecord(sl.rows_ready, e->copy_stream));
     CU(e, cudaStreamWaitEvent(st, sl.rows_ready, 0));
   }
-  const float* rows_base = rows_dev ? rows : sl.d_rows;
+  const uint8_t* packed_base = packed ? (rows_dev ? packed : sl.d_packed) : nullptr;
+  // the embedding kernel reads packed rows directly on the window-aligned fast path; every other path gets the float32
+  // rows they stand for
+  const bool packed_direct = packed_base && !strict && e->fuse_embed && embed_condense_reads_packed(L, e->Lw);
+  if (packed_base && !packed_direct) launch_unpack_rows(packed_base, e->pl, batch, sl.d_rows, st);
+  const float* rows_base = packed ? sl.d_rows : (rows_dev ? rows : sl.d_rows);
   CU(e, cudaMemsetAsync(sl.d_status, 0, sizeof(int), st));
   CU(e, cudaEventRecord(sl.ev0, st));
-  int launches = 0;
+  int launches = (packed_base && !packed_direct) ? 1 : 0;
   const size_t ximg = x_image_elems();
   bool prof_err = false;
   auto pbegin = [&](int kind) {
@@ -859,8 +873,10 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
       bool fused_embed = false;
       if (e->fuse_embed) {
         pbegin(1);
-        fused_embed = launch_embed_condense(rows_chunk, R, L, Lw, M, T, e->echunks, e->d_cols, e->d_rowmeta, e->d_tables,
+        fused_embed = launch_embed_condense(rows_chunk, packed_direct ? packed_base + (size_t)w0 * e->pl.stride : nullptr, e->pl,
+                                            R, L, Lw, M, T, e->echunks, e->d_cols, e->d_rowmeta, e->d_tables,
                                             e->table_elems, e->d_wc, epi, sl.d_status, st);
+        if (!fused_embed && packed_direct) return fail(e, DCB_ERR_INVALID, "internal: packed rows on a path that cannot read them");
         pend();
         if (fused_embed) ++launches;
       }
@@ -970,6 +986,72 @@ int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, 
   sl.busy = true;
   sl.used = true;
   *ticket_out = e->next_ticket++;
+  return DCB_OK;
+}
+
+int dcb_submit(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags, uint8_t* bases_out,
+               uint8_t* quals_out, float* probs_out, float* logits_out, int64_t* ticket_out) {
+  return submit_impl(e, rows, nullptr, batch, flags, bases_out, quals_out, probs_out, logits_out, ticket_out);
+}
+
+int dcb_submit_packed(dcb_engine* e, const uint8_t* packed, int32_t batch, uint32_t flags, uint8_t* bases_out,
+                      uint8_t* quals_out, float* probs_out, float* logits_out, int64_t* ticket_out) {
+  return submit_impl(e, nullptr, packed, batch, flags, bases_out, quals_out, probs_out, logits_out, ticket_out);
+}
+
+int dcb_forward_packed(dcb_engine* e, const uint8_t* packed, int32_t batch, uint32_t flags, uint8_t* bases_out,
+                       uint8_t* quals_out, float* probs_out, float* logits_out) {
+  int64_t ticket = -1;
+  int rc = dcb_submit_packed(e, packed, batch, flags, bases_out, quals_out, probs_out, logits_out, &ticket);
+  if (rc) return rc;
+  return dcb_wait(e, ticket);
+}
+
+size_t dcb_packed_window_bytes(const dcb_config* cfg) {
+  if (!cfg || cfg->max_passes <= 0 || cfg->max_length <= 0) return 0;
+  return (size_t)make_packed_layout(cfg->max_passes, cfg->max_length, cfg->use_ccs_bq ? 1 : 0).stride;
+}
+
+// float32 rows [B, R, L] -> packed rows (include/dcb200.h).  Host code (no GPU, no engine): the producer side of the path.
+int dcb_pack_rows(const dcb_config* cfg, const float* rows, int32_t batch, uint8_t* out) {
+  if (!cfg || !rows || !out || batch < 0 || cfg->max_passes <= 0 || cfg->max_length <= 0)
+    return fail(nullptr, DCB_ERR_INVALID, "dcb_pack_rows: bad argument");
+  const dcb_config& c = *cfg;
+  dcb_engine* e = nullptr;   // messages go to the engine-less error slot (dcb_last_error(NULL))
+  if (c.pw_max > 255 || c.ip_max > 255) return fail(e, DCB_ERR_INVALID, "packed rows need PW_MAX, IP_MAX <= 255");
+  const PackedLayout pl = make_packed_layout(c.max_passes, c.max_length, c.use_ccs_bq ? 1 : 0);
+  const int P = pl.P, L = pl.L, R = pl.R;
+  bool bad = false;
+  auto trunc_clip = [](float v, int hi, bool* flag) {   // clip to [0, hi] as format_rows, then truncate as tf.cast
+    if (!(v >= 0.f)) { if (v < 0.f || v != v) { if (flag) *flag = true; } return 0; }
+    if (v > (float)hi) { if (flag) *flag = true; return hi; }
+    return (int)v;
+  };
+  for (int b = 0; b < batch; ++b) {
+    const float* w = rows + (size_t)b * R * L;
+    uint8_t* o = out + (size_t)b * pl.stride;
+    memset(o, 0, pl.stride);
+    for (int p_ = 0; p_ < P; ++p_)
+      for (int l = 0; l < L; ++l) {
+        const int base = trunc_clip(w[(size_t)p_ * L + l], kVocab - 1, &bad);               // outside 0..4: TF raises
+        const int strand = trunc_clip(w[(size_t)(3 * P + p_) * L + l], c.strand_max, &bad);
+        o[p_ * L + l] = (uint8_t)(base | (strand << 3));
+        o[(P + p_) * L + l] = (uint8_t)trunc_clip(w[(size_t)(P + p_) * L + l], 255, nullptr);       // clip, not an error
+        o[(2 * P + p_) * L + l] = (uint8_t)trunc_clip(w[(size_t)(2 * P + p_) * L + l], 255, nullptr);
+      }
+    for (int l = 0; l < L; ++l) o[3 * P * L + l] = (uint8_t)trunc_clip(w[(size_t)4 * P * L + l], kVocab - 1, &bad);
+    if (pl.bq)
+      for (int l = 0; l < L; ++l)
+        o[(3 * P + 1) * L + l] = (uint8_t)trunc_clip(w[(size_t)(4 * P + 1) * L + l] + 1.f, c.ccs_bq_max - 1, &bad);
+    float* sn = reinterpret_cast<float*>(o + pl.sn_off);
+    for (int i = 0; i < 4; ++i) {
+      const float* row = w + (size_t)(R - 4 + i) * L;
+      sn[i] = row[0];
+      for (int l = 1; l < L; ++l)
+        if (row[l] != row[0]) bad = true;
+    }
+  }
+  if (bad) return fail(e, DCB_ERR_INPUT_RANGE, "dcb_pack_rows: value outside its vocabulary (clamped) or SN row not constant");
   return DCB_OK;
 }
 

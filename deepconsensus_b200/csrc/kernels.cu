@@ -495,7 +495,8 @@ struct EmbCfg {
 };
 
 __global__ void __launch_bounds__(EmbCfg::kThreads, 1)
-embed_condense_kernel(const float* __restrict__ rows, int R, int L, int Lw, int M, int ntiles, int echunks,
+embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict__ packed, PackedLayout pl, int R, int L,
+                      int Lw, int M, int ntiles, int echunks,
                       const EmbedCol* __restrict__ cols, const EmbedRow* __restrict__ rowmeta,
                       const __nv_bfloat16* __restrict__ tables, int table_elems,
                       const __nv_bfloat16* __restrict__ wc_img, RowEpi epi, int* __restrict__ status) {
@@ -599,8 +600,9 @@ embed_condense_kernel(const float* __restrict__ rows, int R, int L, int Lw, int 
         int w_hi = (nxt * kTileM + kTileM - 1) / Lw;
         const int nwin = (M + Lw - 1) / Lw;
         if (w_hi > nwin - 1) w_hi = nwin - 1;
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(rows + (size_t)w_lo * R * L);
-        const size_t bytes = (size_t)(w_hi - w_lo + 1) * R * L * sizeof(float);
+        const uint8_t* base = packed ? packed + (size_t)w_lo * pl.stride
+                                     : reinterpret_cast<const uint8_t*>(rows + (size_t)w_lo * R * L);
+        const size_t bytes = packed ? (size_t)(w_hi - w_lo + 1) * pl.stride : (size_t)(w_hi - w_lo + 1) * R * L * sizeof(float);
         for (size_t off = (size_t)pt * 128; off < bytes; off += 64 * 128)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
       }
@@ -619,7 +621,71 @@ embed_condense_kernel(const float* __restrict__ rows, int R, int L, int Lw, int 
       // every slab of the previous tile has been built (program order), but its last reads of s_ids
       // happen in other builder threads: synchronise the builders before overwriting the ids
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (Lw == kTileM && (L & 3) == 0) {
+      if (packed) {
+        // Packed rows (include/dcb200.h; launcher guarantees Lw == kTileM and L % 4 == 0): the window is
+        // [3P+1+bq][L] bytes + four SN floats.  Item = (plane row pr, 4 consecutive positions) = one 32-bit load; a
+        // warp reads 128 contiguous bytes.  Ids are what tf.cast(format_rows(value)) would give for the float32 rows
+        // the packed form stands for (data_providers.py:151-162, networks.py:457-507).
+        const bool wvalid = (size_t)tile * kTileM < (size_t)M;
+        const uint8_t* wbase = packed + (size_t)(wvalid ? tile : 0) * pl.stride;
+        const uint32_t* base32 = reinterpret_cast<const uint32_t*>(wbase);
+        const int P = pl.P, PR = 3 * P + 1 + pl.bq, L4 = L >> 2;
+        const int nitems = (PR * 32 + 255) / 256;
+        auto load_item = [&](int k) -> uint32_t {
+          const int item = bt + k * 256;
+          const int pr = item >> 5, g = item & 31;
+          if (k < nitems && pr < PR && wvalid && g < L4) return __ldg(base32 + (size_t)pr * L4 + g);
+          return 0u;
+        };
+        uint32_t f0 = load_item(0), f1 = load_item(1), f2 = load_item(2);
+#pragma unroll 1
+        for (int k = 0; k < nitems; ++k) {
+          const uint32_t cur = f0;
+          f0 = f1; f1 = f2; f2 = load_item(k + 3);
+          const int item = bt + k * 256;
+          const int pr = item >> 5, g = item & 31;
+          if (pr < PR) {
+            // reference row this plane feeds (a base|strand byte feeds two)
+            const int ru = pr < 3 * P ? pr : (pr == 3 * P ? 4 * P : 4 * P + 1);
+            const EmbedRow m = rowmeta[ru];
+            const int hi = m.clip_hi > 0.f ? (int)m.clip_hi : 255;
+            uint32_t ids[4], ids2[4];
+            bool bad = false;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              int b = (int)((cur >> (8 * q4)) & 0xffu);
+              int id = pr < P ? (b & 7) : min(b, hi);
+              if (id >= m.vocab) { bad = true; id = m.vocab - 1; }
+              ids[q4] = (uint32_t)id;
+              int sid = (b >> 3) & 3;
+              if (pr < P) {
+                const int sv = rowmeta[3 * P + pr].vocab;
+                if ((b >> 5) != 0 || sid >= sv) { bad = true; sid = sid >= sv ? sv - 1 : sid; }
+              }
+              ids2[q4] = (uint32_t)sid;
+            }
+            if (bad) atomicOr(status, 1);
+            *reinterpret_cast<uint2*>(&s_ids[ru * kTileM + 4 * g]) = make_uint2(ids[0] | (ids[1] << 16), ids[2] | (ids[3] << 16));
+            if (pr < P)
+              *reinterpret_cast<uint2*>(&s_ids[(3 * P + pr) * kTileM + 4 * g]) = make_uint2(ids2[0] | (ids2[1] << 16), ids2[2] | (ids2[3] << 16));
+          }
+        }
+        if (bt < 128) {
+          // the four SN rows: one value per window, repeated along L (pre_lib.py:741-742)
+          const int ri = bt >> 5, g = bt & 31, ru = R - 4 + ri;
+          uint32_t id = 0;
+          if (wvalid && g < L4) {
+            const EmbedRow m = rowmeta[ru];
+            float v = __ldg(reinterpret_cast<const float*>(wbase + pl.sn_off) + ri);
+            if (m.clip_hi > 0.f) v = fminf(fmaxf(v, 0.f), m.clip_hi);
+            v += (float)m.shift;
+            int iv = (int)v;
+            if (iv < 0 || iv >= m.vocab) { atomicOr(status, 1); iv = iv < 0 ? 0 : m.vocab - 1; }
+            id = (uint32_t)iv;
+          }
+          *reinterpret_cast<uint2*>(&s_ids[ru * kTileM + 4 * g]) = make_uint2(id | (id << 16), id | (id << 16));
+        }
+      } else if (Lw == kTileM && (L & 3) == 0) {
         // window-aligned layout (tile == window): the tile's input is one contiguous [R][L] block.  Item = (row ru,
         // 4 consecutive positions): all of a thread's ~11 float4 loads are issued before the first is used (one
         // exposed memory latency instead of six dependent batches), a warp reads 512 contiguous bytes.
@@ -2714,15 +2780,36 @@ void launch_gemm_qkv(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int
                                                                      qkv_img, kQKVN / 8, none);
 }
 
-bool launch_embed_condense(const float* rows, int R, int L, int Lw, int M, int ntiles, int echunks, const EmbedCol* cols,
+bool embed_condense_reads_packed(int L, int Lw) { return Lw == kTileM && (L & 3) == 0; }
+
+bool launch_embed_condense(const float* rows, const uint8_t* packed, const PackedLayout& pl, int R, int L, int Lw, int M,
+                           int ntiles, int echunks, const EmbedCol* cols,
                            const EmbedRow* rowmeta, const __nv_bfloat16* tables, int table_elems,
                            const __nv_bfloat16* wc_img, const RowEpi& epi, int* status, cudaStream_t st) {
   const size_t smem = embed_condense_smem_bytes(R, echunks, table_elems);
   if (smem > 227 * 1024) return false;
+  if (packed && !embed_condense_reads_packed(L, Lw)) return false;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  embed_condense_kernel<<<grid, EmbCfg::kThreads, smem, st>>>(rows, R, L, Lw, M, ntiles, echunks, cols, rowmeta, tables,
-                                                              table_elems, wc_img, epi, status);
+  embed_condense_kernel<<<grid, EmbCfg::kThreads, smem, st>>>(rows, packed, pl, R, L, Lw, M, ntiles, echunks, cols, rowmeta,
+                                                              tables, table_elems, wc_img, epi, status);
   return true;
+}
+
+// packed rows -> the float32 [B, R, L] rows they stand for (paths that do not read the packed form directly: strict
+// fp32, L > 128 / L % 4 != 0, the developer build's unfused kernels)
+__global__ void __launch_bounds__(256)
+unpack_rows_kernel(const uint8_t* __restrict__ packed, PackedLayout pl, int nwindows, float* __restrict__ rows) {
+  const int b = blockIdx.x;
+  const uint8_t* w = packed + (size_t)b * pl.stride;
+  float* out = rows + (size_t)b * pl.R * pl.L;
+  for (int i = threadIdx.x; i < pl.R * pl.L; i += blockDim.x) {
+    const int r = i / pl.L, l = i - r * pl.L;
+    out[i] = packed_value(pl, w, r, l);
+  }
+}
+
+void launch_unpack_rows(const uint8_t* packed, const PackedLayout& pl, int nwindows, float* rows, cudaStream_t st) {
+  if (nwindows > 0) unpack_rows_kernel<<<nwindows, 256, 0, st>>>(packed, pl, nwindows, rows);
 }
 
 void launch_qkv2(const __nv_bfloat16* a_img, const uint8_t* b_img, int ntiles, __nv_bfloat16* qkv_img,

@@ -20,9 +20,13 @@ void launch_gemm_qkv(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int
                      __nv_bfloat16* qkv_img, cudaStream_t st);
 // fused embedding + condenser (+pos-enc, residual image, next operand); false if it does not fit smem
 size_t embed_condense_smem_bytes(int R, int echunks, int table_elems);
-bool launch_embed_condense(const float* rows, int R, int L, int Lw, int M, int ntiles, int echunks, const EmbedCol* cols,
+// `packed` != null: read the packed rows (include/dcb200.h) instead of `rows`; only when embed_condense_reads_packed().
+bool embed_condense_reads_packed(int L, int Lw);
+bool launch_embed_condense(const float* rows, const uint8_t* packed, const PackedLayout& pl, int R, int L, int Lw, int M,
+                           int ntiles, int echunks, const EmbedCol* cols,
                            const EmbedRow* rowmeta, const __nv_bfloat16* tables, int table_elems,
                            const __nv_bfloat16* wc_img, const RowEpi& epi, int* status, cudaStream_t st);
+void launch_unpack_rows(const uint8_t* packed, const PackedLayout& pl, int nwindows, float* rows, cudaStream_t st);
 // two-tiles-per-weight-pass QKV projection; b_img: 9 groups x [36][96][8]
 void launch_qkv2(const __nv_bfloat16* a_img, const uint8_t* b_img, int ntiles, __nv_bfloat16* qkv_img,
                  cudaStream_t st);

@@ -73,6 +73,7 @@ class DcbTensor(ctypes.Structure):
 # Every symbol include/dcb200.h declares; tests check the built library exports all of them.
 ABI_SYMBOLS = (
     "dcb_create", "dcb_load_weights", "dcb_forward", "dcb_submit", "dcb_wait", "dcb_stitch", "dcb_last_forward_ms",
+    "dcb_packed_window_bytes", "dcb_pack_rows", "dcb_forward_packed", "dcb_submit_packed",
     "dcb_last_forward_launches", "dcb_set_profile", "dcb_get_profile", "dcb_get_profile_kernels", "dcb_alloc_host",
     "dcb_free_host", "dcb_alloc_device", "dcb_free_device", "dcb_memcpy_h2d", "dcb_memcpy_d2h",
     "dcb_synchronize", "dcb_last_error", "dcb_version", "dcb_destroy",
@@ -117,6 +118,11 @@ def _load(path: str) -> ctypes.CDLL:
   lib.dcb_forward.argtypes = [vp, vp, i32, u32, vp, vp, vp, vp]
   lib.dcb_submit.argtypes = [vp, vp, i32, u32, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int64)]
   lib.dcb_wait.argtypes = [vp, ctypes.c_int64]
+  lib.dcb_packed_window_bytes.argtypes = [ctypes.POINTER(DcbConfig)]
+  lib.dcb_packed_window_bytes.restype = ctypes.c_size_t
+  lib.dcb_pack_rows.argtypes = [ctypes.POINTER(DcbConfig), vp, i32, vp]
+  lib.dcb_forward_packed.argtypes = [vp, vp, i32, u32, vp, vp, vp, vp]
+  lib.dcb_submit_packed.argtypes = [vp, vp, i32, u32, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int64)]
   lib.dcb_stitch.argtypes = [vp, vp, vp, i32, i32, ctypes.POINTER(i32), i32, u32, vp, vp, vp]
   lib.dcb_last_forward_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
   lib.dcb_last_forward_launches.argtypes = [vp, ctypes.POINTER(i32)]
@@ -288,6 +294,48 @@ class B200Model:
       launches += self.last_forward_launches()
     self.last_ms, self.last_launches = ms, launches
     return out
+
+  # -- packed input rows (include/dcb200.h "packed input rows") -------------------------
+  @property
+  def packed_window_bytes(self) -> int:
+    return packed_window_bytes(self.params)
+
+  def pack_rows(self, rows: np.ndarray, out: Optional[np.ndarray] = None, strict_input: bool = True) -> np.ndarray:
+    return pack_rows(self.params, rows, out, strict_input)
+
+  def forward_packed(self, packed: np.ndarray, want_probs: bool = False, want_logits: bool = False,
+                     strict_input: bool = True, strict: Optional[bool] = None) -> Dict[str, np.ndarray]:
+    """forward() on packed rows uint8 [B, packed_window_bytes]: bit-identical to forward() on the float32 rows they
+    were packed from."""
+    packed = np.ascontiguousarray(packed, dtype=np.uint8)
+    if packed.ndim != 2 or packed.shape[1] != self.packed_window_bytes:
+      raise ValueError("packed rows must be uint8 [B, %d]" % self.packed_window_bytes)
+    B, L = packed.shape[0], self.max_length
+    out = dict(bases=np.empty((B, L), np.uint8), quals=np.empty((B, L), np.uint8))
+    if want_probs:
+      out["probs"] = np.empty((B, L, 5), np.float32)
+    if want_logits:
+      out["logits"] = np.empty((B, L, 5), np.float32)
+    ms, launches = 0.0, 0
+    for b0 in range(0, B, self.max_batch):
+      b1 = min(B, b0 + self.max_batch)
+      ptr = lambda k: out[k][b0:b1].ctypes.data_as(ctypes.c_void_p) if k in out else None
+      rc = self._lib.dcb_forward_packed(self._handle, packed[b0:b1].ctypes.data_as(ctypes.c_void_p), b1 - b0,
+                                        self._precision_flag(strict), ptr("bases"), ptr("quals"), ptr("probs"),
+                                        ptr("logits"))
+      self._check(rc, tolerate=() if strict_input else (-5,))
+      ms += self.last_forward_ms()
+      launches += self.last_forward_launches()
+    self.last_ms, self.last_launches = ms, launches
+    return out
+
+  def submit_packed_raw(self, packed_ptr: int, batch: int, flags: int, bases_ptr: int, quals_ptr: int) -> int:
+    """dcb_submit_packed on caller-managed pointers; returns the ticket for wait_raw()."""
+    ticket = ctypes.c_int64(-1)
+    self._check(self._lib.dcb_submit_packed(self._handle, ctypes.c_void_p(packed_ptr), batch, flags,
+                                            ctypes.c_void_p(bases_ptr), ctypes.c_void_p(quals_ptr), None, None,
+                                            ctypes.byref(ticket)))
+    return int(ticket.value)
 
   # -- the hot path, pipelined over a stream of batches ----------------------------------------
   # dcb_submit / dcb_wait: the host->device copy of batch i+1 overlaps the kernels of batch i.  Page-locked staging
@@ -515,6 +563,58 @@ class B200Model:
 
   def synchronize(self) -> None:
     self._check(self._lib.dcb_synchronize(self._handle))
+
+
+def packed_window_bytes(params: params_lib.Params) -> int:
+  """Bytes per window of the packed row format (include/dcb200.h "packed input rows")."""
+  cfg = make_config(params, max_batch=1)
+  return int(load_library().dcb_packed_window_bytes(ctypes.byref(cfg)))
+
+
+def pack_rows(params: params_lib.Params, rows: np.ndarray, out: Optional[np.ndarray] = None,
+              strict_input: bool = True) -> np.ndarray:
+  """float32 rows [B, R, L(,1)] -> packed uint8 [B, packed_window_bytes] (dcb_pack_rows; host code, needs no GPU).
+  Raises DcbError(-5) when a base / strand / ccs / ccs_bq value lies outside its vocabulary (TensorFlow's gather would
+  raise) or an SN row is not constant, unless `strict_input` is False (values are clamped either way)."""
+  rows = np.asarray(rows)
+  if rows.ndim == 4:
+    rows = rows[..., 0]
+  R = params_lib.get_total_rows(params.max_passes, params.use_ccs_bq)
+  if rows.ndim != 3 or rows.shape[1] != R or rows.shape[2] != int(params.max_length):
+    raise ValueError("rows must be [B, %d, %d(, 1)], got %s" % (R, int(params.max_length), rows.shape))
+  rows = np.ascontiguousarray(rows, dtype=np.float32)
+  lib, cfg = load_library(), make_config(params, max_batch=1)
+  stride = int(lib.dcb_packed_window_bytes(ctypes.byref(cfg)))
+  B = rows.shape[0]
+  if out is None:
+    out = np.empty((B, stride), np.uint8)
+  if out.shape != (B, stride) or out.dtype != np.uint8 or not out.flags.c_contiguous:
+    raise ValueError("pack_rows(out=...): need C-contiguous uint8 [%d, %d]" % (B, stride))
+  rc = lib.dcb_pack_rows(ctypes.byref(cfg), rows.ctypes.data_as(ctypes.c_void_p), B, out.ctypes.data_as(ctypes.c_void_p))
+  if rc and not (rc == -5 and not strict_input):
+    raise DcbError(rc, lib.dcb_last_error(None).decode())
+  return out
+
+
+def unpack_rows(params: params_lib.Params, packed: np.ndarray) -> np.ndarray:
+  """The float32 rows [B, R, L] a packed batch stands for (NumPy mirror of csrc/common.h packed_value; tests and
+  debugging -- the engine never needs it)."""
+  P, L, bq = int(params.max_passes), int(params.max_length), int(bool(params.use_ccs_bq))
+  R = 4 * P + 5 + bq
+  packed = np.asarray(packed, np.uint8)
+  B = packed.shape[0]
+  sn_off = ((3 * P + 1 + bq) * L + 15) & ~15
+  planes = packed[:, :(3 * P + 1 + bq) * L].reshape(B, 3 * P + 1 + bq, L)
+  rows = np.zeros((B, R, L), np.float32)
+  rows[:, :P] = planes[:, :P] & 7
+  rows[:, P:3 * P] = planes[:, P:3 * P]
+  rows[:, 3 * P:4 * P] = (planes[:, :P] >> 3) & 3
+  rows[:, 4 * P] = planes[:, 3 * P]
+  if bq:
+    rows[:, 4 * P + 1] = planes[:, 3 * P + 1].astype(np.float32) - 1
+  sn = np.ascontiguousarray(packed[:, sn_off:sn_off + 16]).view(np.float32)
+  rows[:, R - 4:] = sn[:, :, None]
+  return rows
 
 
 def alloc_pinned(nbytes: int) -> Tuple[int, np.ndarray]:

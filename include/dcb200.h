@@ -112,6 +112,34 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n);
 int dcb_forward(dcb_engine* e, const float* rows, int32_t batch, uint32_t flags,
                 uint8_t* bases_out, uint8_t* quals_out, float* probs_out, float* logits_out);
 
+/* ---- packed input rows (the feature-construction side of the path) --------------------------
+ * The float32 [B, R, L] rows of quick_inference.py:363 hold small integers: bases / ccs in 0..4, pw / ip from uint8
+ * BAM tags (pre_lib.py:221-226,704-744), strand in 0..2, ccs_bq in -1..93, plus four float SN values per window that
+ * extract_features repeats along L (pre_lib.py:741-742).  The packed form keeps exactly that information in
+ * dcb_packed_window_bytes() bytes per window (7,344 B instead of 40,800 B for 20 x 120) -- per window, in this order:
+ *     u8 [P][L]   bits 0-2 = base id of subread p (row p), bits 3-4 = its strand id (row 3P + p)
+ *     u8 [P][L]   pw (rows P..2P-1),   clipped to [0, 255] and truncated, as format_rows + tf.cast would
+ *     u8 [P][L]   ip (rows 2P..3P-1),  same
+ *     u8 [L]      ccs base id (row 4P)
+ *     u8 [L]      ccs_bq + 1 (row 4P+1; only when use_ccs_bq) -- the embedding id itself (networks.py:495)
+ *     padding to a multiple of 16 bytes
+ *     f32 [4]     the window's SN values (rows R-4..R-1, taken at position 0; not clipped)
+ * The engine turns packed bytes into table ids inside its embedding kernel (PW_MAX / IP_MAX / SN_MAX clipping included);
+ * results are bit-identical to dcb_forward on the float32 rows the packed form was made from.
+ *
+ * dcb_pack_rows: host helper (needs no GPU and no engine -- it belongs to the producer of the rows; only max_passes,
+ * max_length, use_ccs_bq and the *_max fields of `cfg` are read), float32 rows [B, R, L] -> packed.  Returns DCB_ERR_INPUT_RANGE (and still writes
+ * clamped output) if a base / strand / ccs / ccs_bq value is outside its vocabulary -- the values TensorFlow's gather
+ * would raise on -- or an SN row is not constant along L; DCB_ERR_INVALID if the configuration cannot be packed
+ * (PW_MAX or IP_MAX above 255). */
+size_t dcb_packed_window_bytes(const dcb_config* cfg);
+int dcb_pack_rows(const dcb_config* cfg, const float* rows, int32_t batch, uint8_t* packed_out);
+/* dcb_forward / dcb_submit on packed rows (host pointer, or device pointer with DCB_ROWS_ON_DEVICE: 16-byte aligned). */
+int dcb_forward_packed(dcb_engine* e, const uint8_t* packed, int32_t batch, uint32_t flags,
+                       uint8_t* bases_out, uint8_t* quals_out, float* probs_out, float* logits_out);
+int dcb_submit_packed(dcb_engine* e, const uint8_t* packed, int32_t batch, uint32_t flags,
+                      uint8_t* bases_out, uint8_t* quals_out, float* probs_out, float* logits_out, int64_t* ticket);
+
 /* Pipelined form of dcb_forward for a stream of batches (the `for batch in batches: model.predict(batch)` loop of
  * quick_inference.py:352-368): dcb_submit enqueues the host->device copy of `rows` on a copy stream, the kernels and
  * the device->host copy of the results, and returns a ticket without waiting; dcb_wait(ticket) blocks until that
