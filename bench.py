@@ -258,6 +258,15 @@ def main():
     arr.view(np.float32)[:] = h.reshape(-1)
     pin_addr.append(a)
     pin.append(arr)
+  # packed form of the same batches (include/dcb200.h "packed input rows": what a producer of rows hands over)
+  stride = model.packed_window_bytes
+  packed_bytes = B * stride
+  ppin_addr, ppin = [], []
+  for h in host_rows:
+    a, arr = engine_lib.alloc_pinned(packed_bytes)
+    model.pack_rows(h, out=arr.reshape(B, stride))
+    ppin_addr.append(a)
+    ppin.append(arr)
   out_addr, out_pin = engine_lib.alloc_pinned(2 * B * L)
   out_addr2, out_pin2 = engine_lib.alloc_pinned(2 * B * L)
   outs = (out_addr, out_addr2)
@@ -282,12 +291,16 @@ def main():
     run_resident_pipelined.dev_ms += model.last_forward_ms()
   run_resident_pipelined.dev_ms = 0.0
 
-  def run_e2e_pipelined(steps):
+  def run_e2e_pipelined(steps, packed=True):
     # the call sequence of inference.run_model_on_examples: submit batch i, then collect batch i-1; every step's rows
-    # go host->device and every step's bases/quals come back to the host inside the timed region
+    # go host->device (packed rows: dcb_submit_packed; float32 rows: dcb_submit) and every step's bases/quals come back
+    # to the host inside the timed region
     pending = None
     for i in range(steps):
-      t = model.submit_raw(pin_addr[i % NBUF], B, 0, outs[i % 2], outs[i % 2] + B * L)
+      if packed:
+        t = model.submit_packed_raw(ppin_addr[i % NBUF], B, 0, outs[i % 2], outs[i % 2] + B * L)
+      else:
+        t = model.submit_raw(pin_addr[i % NBUF], B, 0, outs[i % 2], outs[i % 2] + B * L)
       if pending is not None:
         model.wait_raw(pending)
       pending = t
@@ -343,6 +356,9 @@ def main():
   res_trials = [trial(run_resident_pipelined) for _ in range(TRIALS)]          # per-kernel events OFF
   run_e2e_pipelined(3)
   e2e_trials = [trial(run_e2e_pipelined) for _ in range(TRIALS)]
+  run_e2e_pipelined(3, packed=False)
+  f32_trials = [trial(lambda n: run_e2e_pipelined(n, packed=False)) for _ in range(3)]
+  dt_e2e_f32 = sorted(t[0] for t in f32_trials)[1]
   for i in range(3):
     step_e2e(i)
   dt_e2e_blocking, _ = timed(step_e2e, args.steps)
@@ -466,11 +482,16 @@ def main():
                           e2e_trials=[round(total_windows / t[0], 1) for t in e2e_trials],
                           l2="inputs rotate over %d resident batches (%.0f MB > L2)" % (NBUF, NBUF * row_bytes / 1e6),
                           gflop_per_window=F / 1e9),
-              e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=row_bytes * world,
+              e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=packed_bytes * world,
                        d2h_bytes_per_step=2 * B * L * world, ms_per_step=dt_e2e / args.steps * 1e3,
-                       call="dcb_submit/dcb_wait, 2 batches in flight (as inference.run_model_on_examples)",
+                       call="dcb_submit_packed/dcb_wait from pinned host memory, 2 batches in flight (as "
+                            "inference.run_model_on_examples); input = packed rows, %d B/window "
+                            "(include/dcb200.h), results = base + quality characters back on the host" % stride,
+                       float32_rows=dict(value=total_windows / dt_e2e_f32, h2d_bytes_per_step=row_bytes * world,
+                                         call="dcb_submit/dcb_wait on the reference's float32 [B,R,L] rows (%d B/window)"
+                                              % (row_bytes // B)),
                        blocking_value=total_windows / dt_e2e_blocking,
-                       blocking_call="dcb_forward, one batch at a time"),
+                       blocking_call="dcb_forward on float32 rows, one batch at a time"),
               gpu_launches=launches, roofline=roof, parity=par, clocks=sampler.summary(), numa_node=numa, stitch=stitch_info)
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     os.sched_setaffinity(0, full_affinity)   # the CPU arm may use every host core again
@@ -483,7 +504,7 @@ def main():
     print(json.dumps(line))
   for d in dev_rows + [dev_bases, dev_quals]:
     model.free_device(d)
-  for a in pin_addr + [out_addr, out_addr2]:
+  for a in pin_addr + ppin_addr + [out_addr, out_addr2]:
     engine_lib.free_pinned(a)
   model.close()
   if world > 1:

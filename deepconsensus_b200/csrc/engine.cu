@@ -107,6 +107,10 @@ struct dcb_engine {
   uint8_t *d_st_in = nullptr, *d_st_out = nullptr;   // [2][cap] each: bases|quals, seq|qual
   int32_t *d_st_start = nullptr, *d_st_len = nullptr;
   size_t st_cap = 0, st_zcap = 0;
+  // post-model stage scratch (dcb_stitch_fastq / dcb_skip_mask / dcb_fill_skipped), grown on demand
+  double* d_p10 = nullptr;           // 10^(-q/10), q = 0..255 (host libm pow, as NumPy)
+  struct Scratch { void* p = nullptr; size_t cap = 0; } sc_pos, sc_names, sc_nameoff, sc_outcome, sc_avg, sc_recoff, sc_fastq,
+      sc_bq, sc_mask, sc_ids, sc_dst, sc_tmpb, sc_tmpq;
   float* d_dbg = nullptr;  // [stages][chunk_tiles * x_image]
   // strict-fp32 path (strict_kernels.cu): float32 copies of every variable in the reference's own shapes, and a
   // row-major workspace allocated on the first strict call
@@ -283,6 +287,11 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
     CUC(cudaMallocHost(reinterpret_cast<void**>(&sl.h_status), sizeof(int)));
   }
   CUC(kernels_init());
+  {
+    std::vector<double> p10(256);
+    for (int q = 0; q < 256; ++q) p10[q] = pow(10.0, (double)q / -10.0);    // utils.py:103: 10 ** (q / -10.0)
+    TRY(upload(e, &e->d_p10, p10));
+  }
   const size_t T = e->chunk_tiles;
   for (auto& sl : e->slots) {
     TRY(dev_alloc(e, &sl.d_rows, (size_t)cfg->max_batch * e->R * e->L));
@@ -311,6 +320,9 @@ void dcb_destroy(dcb_engine* e) {
   if (e->d_st_out) cudaFree(e->d_st_out);
   if (e->d_st_start) cudaFree(e->d_st_start);
   if (e->d_st_len) cudaFree(e->d_st_len);
+  for (dcb_engine::Scratch* sc : {&e->sc_pos, &e->sc_names, &e->sc_nameoff, &e->sc_outcome, &e->sc_avg, &e->sc_recoff,
+                                  &e->sc_fastq, &e->sc_bq, &e->sc_mask, &e->sc_ids, &e->sc_dst, &e->sc_tmpb, &e->sc_tmpq})
+    if (sc->p) cudaFree(sc->p);
   for (auto& sl : e->slots)
     for (auto& pr : sl.prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
@@ -1204,6 +1216,161 @@ int dcb_stitch(dcb_engine* e, const uint8_t* bases, const uint8_t* quals, int32_
   }
   CU(e, cudaStreamSynchronize(st));
   CU(e, cudaGetLastError());
+  return DCB_OK;
+}
+
+namespace {
+// grow-on-demand device scratch; contents are not preserved
+int ensure(dcb_engine* e, dcb_engine::Scratch& sc, size_t bytes) {
+  if (bytes <= sc.cap) return DCB_OK;
+  CU(e, cudaStreamSynchronize(e->stream));
+  if (sc.p) cudaFree(sc.p);
+  sc.p = nullptr; sc.cap = 0;
+  CU(e, cudaMalloc(&sc.p, bytes));
+  sc.cap = bytes;
+  return DCB_OK;
+}
+}  // namespace
+
+int dcb_stitch_fastq(dcb_engine* e, const uint8_t* bases, const uint8_t* quals, int32_t n_windows, int32_t L,
+                     const int32_t* zmw_start, int32_t n_zmw, const int32_t* window_pos, const uint8_t* names,
+                     const int32_t* name_off, double min_quality, int32_t min_length, uint32_t flags, uint8_t* fastq_out,
+                     int64_t fastq_cap, int64_t* rec_off, int32_t* outcome, double* avg_q) {
+  if (!e) return DCB_ERR_INVALID;
+  if (n_windows < 0 || L <= 0 || n_zmw < 0 || fastq_cap < 0) return fail(e, DCB_ERR_INVALID, "dcb_stitch_fastq: negative size");
+  if (!rec_off) return fail(e, DCB_ERR_INVALID, "dcb_stitch_fastq: null pointer");
+  if (n_zmw == 0) { rec_off[0] = 0; return DCB_OK; }
+  if (!bases || !quals || !zmw_start || !window_pos || !names || !name_off || !fastq_out || !outcome || !avg_q)
+    return fail(e, DCB_ERR_INVALID, "dcb_stitch_fastq: null pointer");
+  if (name_off[0] != 0) return fail(e, DCB_ERR_INVALID, "dcb_stitch_fastq: name_off[0] must be 0");
+  for (int z = 0; z < n_zmw; ++z)
+    if (name_off[z + 1] < name_off[z]) return fail(e, DCB_ERR_INVALID, "dcb_stitch_fastq: name_off must be non-decreasing");
+  const size_t nbytes = (size_t)n_windows * L;
+  // stage 1: concatenation + gap compaction (dcb_stitch), results stay on the device
+  CU(e, cudaSetDevice(e->cfg.device));
+  cudaStream_t st = e->stream;
+  int rc;
+  // reuse dcb_stitch with device-side outputs into our own scratch
+  if ((rc = ensure(e, e->sc_tmpb, nbytes ? nbytes : 1)) || (rc = ensure(e, e->sc_tmpq, nbytes ? nbytes : 1)) ||
+      (rc = ensure(e, e->sc_dst, ((size_t)n_zmw + 1) * sizeof(int32_t))))
+    return rc;
+  uint8_t* d_seq = static_cast<uint8_t*>(e->sc_tmpb.p);
+  uint8_t* d_qual = static_cast<uint8_t*>(e->sc_tmpq.p);
+  int32_t* d_len = static_cast<int32_t*>(e->sc_dst.p);
+  if (n_windows > 0) {
+    rc = dcb_stitch(e, bases, quals, n_windows, L, zmw_start, n_zmw, (flags & DCB_ROWS_ON_DEVICE) | DCB_OUT_ON_DEVICE, d_seq, d_qual, d_len);
+    if (rc) return rc;
+  } else {
+    CU(e, cudaMemsetAsync(d_len, 0, ((size_t)n_zmw + 1) * sizeof(int32_t), st));
+  }
+  const size_t names_bytes = (size_t)name_off[n_zmw];
+  const size_t cap = (size_t)fastq_cap;
+  if ((rc = ensure(e, e->sc_pos, (nbytes ? (size_t)n_windows : 1) * sizeof(int32_t))) ||
+      (rc = ensure(e, e->sc_names, names_bytes ? names_bytes : 1)) ||
+      (rc = ensure(e, e->sc_nameoff, ((size_t)n_zmw + 1) * sizeof(int32_t))) ||
+      (rc = ensure(e, e->sc_outcome, (size_t)n_zmw * sizeof(int32_t))) || (rc = ensure(e, e->sc_avg, (size_t)n_zmw * sizeof(double))) ||
+      (rc = ensure(e, e->sc_recoff, ((size_t)n_zmw + 1) * sizeof(int64_t))) || (rc = ensure(e, e->sc_fastq, cap ? cap : 1)))
+    return rc;
+  // dcb_stitch left zmw_start in its own scratch (d_st_start)
+  if (n_windows == 0) {
+    if ((size_t)n_zmw + 1 > e->st_zcap) {
+      if (e->d_st_start) cudaFree(e->d_st_start);
+      if (e->d_st_len) cudaFree(e->d_st_len);
+      e->d_st_start = e->d_st_len = nullptr; e->st_zcap = 0;
+      CU(e, cudaMalloc(reinterpret_cast<void**>(&e->d_st_start), ((size_t)n_zmw + 1) * sizeof(int32_t)));
+      CU(e, cudaMalloc(reinterpret_cast<void**>(&e->d_st_len), ((size_t)n_zmw + 1) * sizeof(int32_t)));
+      e->st_zcap = (size_t)n_zmw + 1;
+    }
+    CU(e, cudaMemcpyAsync(e->d_st_start, zmw_start, ((size_t)n_zmw + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
+  if (n_windows > 0) CU(e, cudaMemcpyAsync(e->sc_pos.p, window_pos, (size_t)n_windows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (names_bytes) CU(e, cudaMemcpyAsync(e->sc_names.p, names, names_bytes, cudaMemcpyHostToDevice, st));
+  CU(e, cudaMemcpyAsync(e->sc_nameoff.p, name_off, ((size_t)n_zmw + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  int32_t* d_out = static_cast<int32_t*>(e->sc_outcome.p);
+  double* d_avg = static_cast<double*>(e->sc_avg.p);
+  int64_t* d_rec = static_cast<int64_t*>(e->sc_recoff.p);
+  launch_read_outcome(d_qual, d_len, e->d_st_start, static_cast<const int32_t*>(e->sc_pos.p), L, n_zmw, e->d_p10, min_quality,
+                      min_length, d_out, d_avg, st);
+  launch_fastq(d_seq, d_qual, d_len, e->d_st_start, L, n_zmw, d_out, static_cast<const uint8_t*>(e->sc_names.p),
+               static_cast<const int32_t*>(e->sc_nameoff.p), d_rec, static_cast<uint8_t*>(e->sc_fastq.p), fastq_cap, st);
+  CU(e, cudaMemcpyAsync(rec_off, d_rec, ((size_t)n_zmw + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CU(e, cudaMemcpyAsync(outcome, d_out, (size_t)n_zmw * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU(e, cudaMemcpyAsync(avg_q, d_avg, (size_t)n_zmw * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(e, cudaStreamSynchronize(st));
+  if (rec_off[n_zmw] > fastq_cap) return fail(e, DCB_ERR_INVALID, "dcb_stitch_fastq: fastq_out too small: need %lld bytes", (long long)rec_off[n_zmw]);
+  if (rec_off[n_zmw] > 0) CU(e, cudaMemcpy(fastq_out, e->sc_fastq.p, (size_t)rec_off[n_zmw], cudaMemcpyDeviceToHost));
+  CU(e, cudaGetLastError());
+  return DCB_OK;
+}
+
+int dcb_skip_mask(dcb_engine* e, const int16_t* ccs_bq, int32_t n_windows, int32_t L, double skip_windows_above,
+                  uint8_t* mask_out, double* avg_out) {
+  if (!e) return DCB_ERR_INVALID;
+  if (n_windows < 0 || L <= 0) return fail(e, DCB_ERR_INVALID, "dcb_skip_mask: negative size");
+  if (n_windows == 0) return DCB_OK;
+  if (!ccs_bq || !mask_out) return fail(e, DCB_ERR_INVALID, "dcb_skip_mask: null pointer");
+  CU(e, cudaSetDevice(e->cfg.device));
+  cudaStream_t st = e->stream;
+  const size_t n = (size_t)n_windows * L;
+  int rc;
+  if ((rc = ensure(e, e->sc_bq, n * sizeof(int16_t))) || (rc = ensure(e, e->sc_mask, (size_t)n_windows)) ||
+      (rc = ensure(e, e->sc_avg, (size_t)n_windows * sizeof(double))))
+    return rc;
+  CU(e, cudaMemcpyAsync(e->sc_bq.p, ccs_bq, n * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+  launch_skip_mask(static_cast<const int16_t*>(e->sc_bq.p), n_windows, L, e->d_p10, skip_windows_above,
+                   static_cast<uint8_t*>(e->sc_mask.p), static_cast<double*>(e->sc_avg.p), st);
+  CU(e, cudaMemcpyAsync(mask_out, e->sc_mask.p, (size_t)n_windows, cudaMemcpyDeviceToHost, st));
+  if (avg_out) CU(e, cudaMemcpyAsync(avg_out, e->sc_avg.p, (size_t)n_windows * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(e, cudaStreamSynchronize(st));
+  CU(e, cudaGetLastError());
+  return DCB_OK;
+}
+
+int dcb_fill_skipped(dcb_engine* e, const uint8_t* ccs_ids, const int16_t* ccs_bq, const int32_t* dst_window, int32_t k,
+                     int32_t L, int32_t calibration_enabled, double calibration_threshold, double calibration_w,
+                     double calibration_b, uint32_t flags, uint8_t* bases, uint8_t* quals) {
+  if (!e) return DCB_ERR_INVALID;
+  if (k < 0 || L <= 0) return fail(e, DCB_ERR_INVALID, "dcb_fill_skipped: negative size");
+  if (k == 0) return DCB_OK;
+  if (!ccs_ids || !ccs_bq || !dst_window || !bases || !quals) return fail(e, DCB_ERR_INVALID, "dcb_fill_skipped: null pointer");
+  for (int j = 0; j < k; ++j)
+    if (dst_window[j] < 0) return fail(e, DCB_ERR_INVALID, "dcb_fill_skipped: negative destination window");
+  CU(e, cudaSetDevice(e->cfg.device));
+  cudaStream_t st = e->stream;
+  const size_t n = (size_t)k * L;
+  const bool out_dev = flags & DCB_OUT_ON_DEVICE;
+  int rc;
+  if ((rc = ensure(e, e->sc_ids, n)) || (rc = ensure(e, e->sc_bq, n * sizeof(int16_t))) ||
+      (rc = ensure(e, e->sc_dst, ((size_t)k + 1) * sizeof(int32_t))) || (rc = ensure(e, e->sc_mask, sizeof(int))))
+    return rc;
+  if (!out_dev && ((rc = ensure(e, e->sc_tmpb, n)) || (rc = ensure(e, e->sc_tmpq, n)))) return rc;
+  std::vector<int32_t> dst(dst_window, dst_window + k);
+  if (!out_dev) for (int j = 0; j < k; ++j) dst[j] = j;      // dense temporary, scattered on the host below
+  CU(e, cudaMemcpyAsync(e->sc_ids.p, ccs_ids, n, cudaMemcpyHostToDevice, st));
+  CU(e, cudaMemcpyAsync(e->sc_bq.p, ccs_bq, n * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+  CU(e, cudaMemcpyAsync(e->sc_dst.p, dst.data(), (size_t)k * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CU(e, cudaMemsetAsync(e->sc_mask.p, 0, sizeof(int), st));
+  uint8_t* db = out_dev ? bases : static_cast<uint8_t*>(e->sc_tmpb.p);
+  uint8_t* dq = out_dev ? quals : static_cast<uint8_t*>(e->sc_tmpq.p);
+  launch_fill_skipped(static_cast<const uint8_t*>(e->sc_ids.p), static_cast<const int16_t*>(e->sc_bq.p),
+                      static_cast<const int32_t*>(e->sc_dst.p), k, L, calibration_enabled, calibration_threshold,
+                      calibration_w, calibration_b, e->cfg.max_base_quality, db, dq, static_cast<int*>(e->sc_mask.p), st);
+  int status = 0;
+  CU(e, cudaMemcpyAsync(&status, e->sc_mask.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (!out_dev) {
+    std::vector<uint8_t> hb(n), hq(n);
+    CU(e, cudaMemcpyAsync(hb.data(), db, n, cudaMemcpyDeviceToHost, st));
+    CU(e, cudaMemcpyAsync(hq.data(), dq, n, cudaMemcpyDeviceToHost, st));
+    CU(e, cudaStreamSynchronize(st));
+    for (int j = 0; j < k; ++j) {
+      memcpy(bases + (size_t)dst_window[j] * L, hb.data() + (size_t)j * L, L);
+      memcpy(quals + (size_t)dst_window[j] * L, hq.data() + (size_t)j * L, L);
+    }
+  } else {
+    CU(e, cudaStreamSynchronize(st));
+  }
+  CU(e, cudaGetLastError());
+  if (status & 1) return fail(e, DCB_ERR_INPUT_RANGE, "dcb_fill_skipped: CCS base id outside 0..4 (clamped)");
   return DCB_OK;
 }
 

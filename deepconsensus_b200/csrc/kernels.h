@@ -57,6 +57,19 @@ void launch_stitch(const uint8_t* bases, const uint8_t* quals, int L, const int3
                    uint8_t* seq_out, uint8_t* qual_out, int32_t* len_out, cudaStream_t st);
 
 
+// ---- post-model stage on the device (post_kernels.cu); outcome codes: DCB_READ_* of include/dcb200.h
+void launch_read_outcome(const uint8_t* qual, const int32_t* len, const int32_t* zmw_start, const int32_t* window_pos,
+                         int L, int n_zmw, const double* p10, double min_quality, int min_length, int32_t* outcome,
+                         double* avg_q, cudaStream_t st);
+void launch_fastq(const uint8_t* seq, const uint8_t* qual, const int32_t* len, const int32_t* zmw_start, int L, int n_zmw,
+                  const int32_t* outcome, const uint8_t* names, const int32_t* name_off, int64_t* rec_off, uint8_t* fastq,
+                  int64_t cap, cudaStream_t st);
+void launch_skip_mask(const int16_t* ccs_bq, int n_windows, int L, const double* p10, double thr, uint8_t* mask,
+                      double* avg_out, cudaStream_t st);
+void launch_fill_skipped(const uint8_t* ccs_ids, const int16_t* ccs_bq, const int32_t* dst, int k, int L, int calib_enabled,
+                         double thr, double cw, double cb, int max_q, uint8_t* bases, uint8_t* quals, int* status,
+                         cudaStream_t st);
+
 // ---- strict-fp32 path (strict_kernels.cu): row-major float32 activations, windows packed back to back
 void launch_strict_embed(const float* rows, int R, int L, int E, int nwindows, const StrictEmbedRow* meta,
                          const float* tables, float* emb, int* status, cudaStream_t st);

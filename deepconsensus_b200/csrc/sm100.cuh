@@ -20,6 +20,33 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Race-evidence build (-DDCB_JITTER, scripts/gpu_jitter.py): a pseudo-random delay in front of every mbarrier wait /
+// arrive, bulk-copy issue and tcgen05.commit perturbs the relative timing of producer, UMMA-issuer, relay and worker
+// warps by up to ~2 us per synchronisation point.  If any hand-over relied on timing instead of on the barrier chain,
+// outputs would differ from the plain build's; the script requires them to be bit-identical over hundreds of runs.
+#ifdef DCB_JITTER
+__device__ __forceinline__ uint32_t dcb_jitter_hash() {
+  uint32_t t;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(t));
+  uint32_t h = (t ^ (threadIdx.x * 2654435761u) ^ (blockIdx.x * 40503u)) * 2246822519u;
+  h ^= h >> 13;
+  h *= 3266489917u;
+  return h ^ (h >> 16);
+}
+__device__ __forceinline__ void dcb_jitter() {          // per thread (callers are single threads or divergent-safe)
+  const uint32_t h = dcb_jitter_hash();
+  if ((h & 3u) == 0u) __nanosleep((h >> 8) & 2047u);
+}
+__device__ __forceinline__ void dcb_jitter_warp() {     // warp-uniform (in front of elect.sync / .aligned forms)
+  const uint32_t h = __shfl_sync(0xffffffffu, dcb_jitter_hash(), 0);
+  if ((h & 3u) == 0u) __nanosleep((h >> 8) & 2047u);
+  __syncwarp();
+}
+#else
+__device__ __forceinline__ void dcb_jitter() {}
+__device__ __forceinline__ void dcb_jitter_warp() {}
+#endif
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -28,11 +55,13 @@ __device__ __forceinline__ void mbar_fence_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  dcb_jitter();
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(
                    smem_u32(bar))
                : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  dcb_jitter();
   asm volatile(
       "{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
           smem_u32(bar)),
@@ -51,12 +80,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  dcb_jitter();
   while (!mbar_try_wait(bar, parity)) {
   }
 }
 
 // Wait with cluster-scope acquire (for barriers that peers of the cluster arrive on).
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  dcb_jitter();
   uint32_t ok = 0;
   while (!ok) {
     asm volatile(
@@ -74,6 +105,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 // size % 16 == 0, both addresses 16-byte aligned.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
                                          uint64_t* bar) {
+  dcb_jitter();
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
           "r"(smem_u32(smem_dst)),
@@ -163,6 +195,7 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
 // Arrive on an mbarrier when all previously issued MMAs of this thread have completed.
 // (Implies tcgen05.fence::before_thread_sync.)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  dcb_jitter();
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
@@ -180,6 +213,7 @@ __device__ __forceinline__ void umma_bf16_ss_warp(uint32_t d_tmem, uint64_t a_de
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
+  dcb_jitter_warp();
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
       "elect.sync _|q, 0xffffffff;\n\t"
@@ -235,6 +269,7 @@ __device__ __forceinline__ void umma_bf16_ss_pair_warp(uint32_t d_tmem, uint64_t
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_pair_warp(uint64_t* bar, uint16_t cta_mask) {
+  dcb_jitter_warp();
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
       "elect.sync _|q, 0xffffffff;\n\t"
@@ -245,6 +280,7 @@ __device__ __forceinline__ void umma_commit_pair_warp(uint64_t* bar, uint16_t ct
 }
 // Completion of all prior pair-MMAs -> arrive on the barrier at this offset in the CTAs of cta_mask.
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  dcb_jitter();
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
       "[%0], %1;" ::"r"(smem_u32(bar)),
@@ -253,6 +289,7 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
 }
 // Arrive on the mbarrier at the same shared-memory offset in CTA `target_cta` of the cluster.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t target_cta) {
+  dcb_jitter();
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(target_cta));
   // default semantics (.release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id) does: a

@@ -34,6 +34,9 @@ DCB_STRICT_FP32 = 4
 DCB_FAST_BF16 = 8
 DCB_PRECISION_BF16 = 0
 DCB_PRECISION_FP32 = 1
+# per-read outcome codes of dcb_stitch_fastq (the OutcomeCounter field the reference would bump)
+DCB_READ_OK, DCB_READ_EMPTY, DCB_READ_ONLY_GAPS, DCB_READ_LOW_QUALITY, DCB_READ_TOO_SHORT = 0, 1, 2, 3, 4
+DCB_READ_BORDERLINE = 0x80
 
 
 class DcbError(RuntimeError):
@@ -74,6 +77,7 @@ class DcbTensor(ctypes.Structure):
 ABI_SYMBOLS = (
     "dcb_create", "dcb_load_weights", "dcb_forward", "dcb_submit", "dcb_wait", "dcb_stitch", "dcb_last_forward_ms",
     "dcb_packed_window_bytes", "dcb_pack_rows", "dcb_forward_packed", "dcb_submit_packed",
+    "dcb_stitch_fastq", "dcb_skip_mask", "dcb_fill_skipped",
     "dcb_last_forward_launches", "dcb_set_profile", "dcb_get_profile", "dcb_get_profile_kernels", "dcb_alloc_host",
     "dcb_free_host", "dcb_alloc_device", "dcb_free_device", "dcb_memcpy_h2d", "dcb_memcpy_d2h",
     "dcb_synchronize", "dcb_last_error", "dcb_version", "dcb_destroy",
@@ -124,6 +128,10 @@ def _load(path: str) -> ctypes.CDLL:
   lib.dcb_forward_packed.argtypes = [vp, vp, i32, u32, vp, vp, vp, vp]
   lib.dcb_submit_packed.argtypes = [vp, vp, i32, u32, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int64)]
   lib.dcb_stitch.argtypes = [vp, vp, vp, i32, i32, ctypes.POINTER(i32), i32, u32, vp, vp, vp]
+  f64 = ctypes.c_double
+  lib.dcb_stitch_fastq.argtypes = [vp, vp, vp, i32, i32, vp, i32, vp, vp, vp, f64, i32, u32, vp, ctypes.c_int64, vp, vp, vp]
+  lib.dcb_skip_mask.argtypes = [vp, vp, i32, i32, f64, vp, vp]
+  lib.dcb_fill_skipped.argtypes = [vp, vp, vp, vp, i32, i32, i32, f64, f64, f64, u32, vp, vp]
   lib.dcb_last_forward_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
   lib.dcb_last_forward_launches.argtypes = [vp, ctypes.POINTER(i32)]
   lib.dcb_set_debug.argtypes = [vp, i32]
@@ -474,6 +482,82 @@ class B200Model:
                                      seq.ctypes.data_as(ctypes.c_void_p), qual.ctypes.data_as(ctypes.c_void_p),
                                      lens.ctypes.data_as(ctypes.c_void_p)))
     return seq, qual, lens
+
+  def stitch_fastq(self, bases, quals, zmw_start: np.ndarray, window_pos, names, min_quality: float, min_length: int,
+                   n_windows: Optional[int] = None, on_device: bool = False, length: Optional[int] = None):
+    """dcb_stitch_fastq: stitch_utils.stitch_to_fastq for a batch of reads on the device.  Returns (fastq bytes,
+    rec_off int64 [n_zmw + 1], outcome int32 [n_zmw], avg_q float64 [n_zmw]); read z's record is
+    fastq[rec_off[z]:rec_off[z + 1]] (empty unless outcome[z] & 0x7f == DCB_READ_OK)."""
+    zs = np.ascontiguousarray(zmw_start, dtype=np.int32)
+    nz = int(zs.shape[0]) - 1
+    L = int(length) if length is not None else self.max_length
+    if on_device:
+      if n_windows is None:
+        raise ValueError("stitch_fastq(on_device=True) needs n_windows")
+      b_ptr, q_ptr, flags = ctypes.c_void_p(int(bases)), ctypes.c_void_p(int(quals)), DCB_ROWS_ON_DEVICE
+    else:
+      bases = np.ascontiguousarray(bases, dtype=np.uint8)
+      quals = np.ascontiguousarray(quals, dtype=np.uint8)
+      n_windows = int(bases.shape[0])
+      b_ptr, q_ptr, flags = bases.ctypes.data_as(ctypes.c_void_p), quals.ctypes.data_as(ctypes.c_void_p), 0
+    pos = np.ascontiguousarray(window_pos, dtype=np.int32)
+    if pos.shape[0] != n_windows:
+      raise ValueError("window_pos must have one entry per window")
+    enc = [n.encode("latin-1") if isinstance(n, str) else bytes(n) for n in names]
+    if len(enc) != nz:
+      raise ValueError("names must have one entry per read")
+    name_off = np.zeros(nz + 1, np.int32)
+    if nz:
+      name_off[1:] = np.cumsum([len(x) for x in enc])
+    blob = np.frombuffer(b"".join(enc) or b"\0", np.uint8)
+    cap = int(name_off[-1]) + 2 * n_windows * L + 6 * nz + 16
+    fastq = np.empty(cap, np.uint8)
+    rec_off = np.zeros(nz + 1, np.int64)
+    outcome = np.zeros(max(nz, 0), np.int32)
+    avg_q = np.zeros(max(nz, 0), np.float64)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    self._check(self._lib.dcb_stitch_fastq(self._handle, b_ptr, q_ptr, n_windows, L, vp(zs), nz, vp(pos), vp(blob),
+                                           vp(name_off), float(min_quality), int(min_length), flags, vp(fastq), cap,
+                                           vp(rec_off), vp(outcome), vp(avg_q)))
+    return fastq[:int(rec_off[-1])].tobytes(), rec_off, outcome, avg_q
+
+  def skip_mask(self, ccs_base_quality_scores: np.ndarray, skip_windows_above: float) -> Tuple[np.ndarray, np.ndarray]:
+    """dcb_skip_mask: per window avg_phred(ccs_base_quality_scores) > skip_windows_above on the device
+    (quick_inference.py:663-672).  Returns (mask uint8 [n] with 2 = within 1e-7 of the threshold, avg float64 [n])."""
+    bq = np.ascontiguousarray(ccs_base_quality_scores, dtype=np.int16)
+    if bq.ndim != 2:
+      raise ValueError("ccs_base_quality_scores must be [n_windows, L]")
+    n, L = bq.shape
+    mask, avg = np.zeros(n, np.uint8), np.zeros(n, np.float64)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    self._check(self._lib.dcb_skip_mask(self._handle, vp(bq), n, L, float(skip_windows_above), vp(mask), vp(avg)))
+    return mask, avg
+
+  def fill_skipped(self, ccs_ids: np.ndarray, ccs_base_quality_scores: np.ndarray, dst_window: np.ndarray,
+                   bases, quals, calibration: Optional[calibration_lib.QualityCalibrationValues] = None,
+                   on_device: bool = False) -> None:
+    """dcb_fill_skipped: process_skipped_window (quick_inference.py:567-594) for k windows on the device; window j
+    lands in row dst_window[j] of `bases` / `quals` (uint8 [*, L] arrays, or device addresses with on_device)."""
+    ids = np.ascontiguousarray(ccs_ids, dtype=np.uint8)
+    bq = np.ascontiguousarray(ccs_base_quality_scores, dtype=np.int16)
+    dst = np.ascontiguousarray(dst_window, dtype=np.int32)
+    k, L = ids.shape
+    if bq.shape != (k, L) or dst.shape != (k,):
+      raise ValueError("fill_skipped: ccs_ids / ccs_base_quality_scores [k, L] and dst_window [k] expected")
+    cal = calibration
+    en = int(bool(cal is not None and cal.enabled))
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    if on_device:
+      b_ptr, q_ptr, flags = ctypes.c_void_p(int(bases)), ctypes.c_void_p(int(quals)), DCB_OUT_ON_DEVICE
+    else:
+      if not (bases.flags.c_contiguous and quals.flags.c_contiguous and bases.dtype == np.uint8 and quals.dtype == np.uint8):
+        raise ValueError("fill_skipped: bases / quals must be C-contiguous uint8 arrays")
+      if k and int(dst.max()) >= bases.shape[0]:
+        raise ValueError("fill_skipped: destination window outside the output arrays")
+      b_ptr, q_ptr, flags = vp(bases), vp(quals), 0
+    self._check(self._lib.dcb_fill_skipped(self._handle, vp(ids), vp(bq), vp(dst), k, L, en,
+                                           float(cal.threshold) if en else 0.0, float(cal.w) if en else 1.0,
+                                           float(cal.b) if en else 0.0, flags, b_ptr, q_ptr))
 
   def stitch_raw(self, bases_ptr: int, quals_ptr: int, n_windows: int, zmw_start: np.ndarray, flags: int,
                  seq_ptr: int, qual_ptr: int, len_ptr: int, length: Optional[int] = None) -> None:

@@ -208,6 +208,58 @@ def run_model_and_stitch(feature_dicts: List[Dict[str, Any]], model: engine_lib.
                                           options.min_length, outcome_counter)
 
 
+def inference_on_zmw_windows(feature_dicts_for_zmws: Iterable[Iterable[Dict[str, Any]]], model: engine_lib.B200Model,
+                             model_params: params_lib.Params, options: InferenceOptions,
+                             outcome_counter: stitch_utils.OutcomeCounter) -> List[Optional[str]]:
+  """The model-facing part of `inference_on_n_zmws` + the stitching of `run()` for a batch of ZMWs
+  (quick_inference.py:657-686,721-760) with every per-window / per-read byte and arithmetic step on the device:
+
+    skip decision   avg_phred(ccs_base_quality_scores) > skip_windows_above     dcb_skip_mask
+    model           run_model_on_examples on the windows that are not skipped    dcb_submit / dcb_wait
+    skipped windows process_skipped_window: adopt CCS bases / calibrated quals    dcb_fill_skipped
+    stitch          sort by (name, window_pos), stitch_to_fastq per read          dcb_stitch_fastq
+
+  Returns one FASTQ record (or None) per read in sorted-name order -- identical to the reference flow built from
+  `split_skipped_windows`, `run_model_on_examples`, `sorted(...)` and `stitch_utils.stitch_to_fastq`.
+  """
+  from deepconsensus_b200 import stitch_gpu
+  L = int(model_params.max_length)
+  windows = [w for one_zmw in feature_dicts_for_zmws for w in one_zmw]
+  n = len(windows)
+  if n == 0:
+    return []
+  names = [_as_str(w["name"]) for w in windows]
+  positions = [int(w["window_pos"]) for w in windows]
+  bq = np.stack([np.asarray(w["ccs_base_quality_scores"]) for w in windows]).astype(np.int16)
+  skip = np.array([bool(w.get("overflow", False)) for w in windows])
+  if options.skip_windows_above:
+    mask, _ = model.skip_mask(bq, options.skip_windows_above)
+    for i in np.nonzero(mask == 2)[0]:                       # within 1e-7 of the threshold: the reference's expression
+      mask[i] = utils.avg_phred(windows[i]["ccs_base_quality_scores"]) > options.skip_windows_above
+    skip |= mask.astype(bool)
+  order = sorted(range(n), key=lambda i: (names[i], positions[i]))          # quick_inference.py:721-728
+  dest = np.empty(n, np.int32)
+  dest[order] = np.arange(n, dtype=np.int32)
+  all_b, all_q = np.empty((n, L), np.uint8), np.empty((n, L), np.uint8)
+  scored = np.nonzero(~skip)[0]
+  cursor = [0]
+
+  def collect(data, out):
+    k = out["bases"].shape[0]
+    rows = dest[scored[cursor[0]:cursor[0] + k]]
+    all_b[rows], all_q[rows] = out["bases"], out["quals"]
+    cursor[0] += k
+
+  _pipelined(model, batch_examples([windows[i] for i in scored], model_params, options), collect)
+  skipped = np.nonzero(skip)[0]
+  if len(skipped):
+    ccs_row = params_lib.get_indices(options.max_passes, options.use_ccs_bq)[4][0]
+    ccs_ids = np.stack([np.asarray(windows[i]["subreads"])[ccs_row, :, 0] for i in skipped]).astype(np.uint8)
+    model.fill_skipped(ccs_ids, bq[skipped], dest[skipped], all_b, all_q, calibration=options.ccs_calibration_values)
+  return stitch_gpu.stitch_batch_to_fastq(model, all_b, all_q, [names[i] for i in order], [positions[i] for i in order],
+                                          L, options.min_quality, options.min_length, outcome_counter)
+
+
 def _as_str(x) -> str:
   return x.decode() if isinstance(x, (bytes, np.bytes_)) else str(x)
 

@@ -164,6 +164,50 @@ int dcb_stitch(dcb_engine* e, const uint8_t* bases, const uint8_t* quals, int32_
                const int32_t* zmw_start, int32_t n_zmw, uint32_t flags,
                uint8_t* seq_out, uint8_t* qual_out, int32_t* len_out);
 
+/* ---- the rest of the post-model stage on the device ------------------------------------------
+ * dcb_stitch_fastq = stitch_utils.stitch_to_fastq for a batch of reads (stitch_utils.py:131-189): dcb_stitch, then per
+ * read the missing-window check of get_full_sequence (window i must not start beyond i * L, stitch_utils.py:60-78), the
+ * only-gaps check, the quality filter round(avg_phred(quals), 5) >= min_quality (utils.py:88-106,
+ * stitch_utils.py:101-109), the length filter, and for the reads that pass the FASTQ record
+ * '@' name '\n' sequence "\n+\n" quality '\n' (stitch_utils.py:112-119) written at rec_off[z] of fastq_out.
+ *   window_pos [n_windows]   DCModelOutput.window_pos of every window (sorted within a read)
+ *   names / name_off         the read names, concatenated; read z is names[name_off[z] .. name_off[z+1])
+ *   fastq_out, fastq_cap     caller-sized; names + 2 * n_windows * L + 6 * n_zmw bytes always suffice
+ *   rec_off [n_zmw + 1]      byte offset of every read's record (rec_off[n_zmw] = total bytes written)
+ *   outcome [n_zmw]          DCB_READ_* -- the OutcomeCounter field the reference would bump
+ *   avg_q [n_zmw]            the read's average Phred (float64)
+ * bases / quals are host arrays, or device arrays with DCB_ROWS_ON_DEVICE (e.g. dcb_forward's DCB_OUT_ON_DEVICE
+ * outputs); every output is a host array.  A read whose average quality lies within 1e-7 of the filter threshold is
+ * reported with DCB_READ_BORDERLINE or-ed in (its record IS written): the caller re-evaluates that read with the
+ * reference's own float64 expression, because NumPy's pairwise sum and the histogram sum used here may differ in the
+ * last bits (deepconsensus_b200/stitch_gpu.py does). */
+#define DCB_READ_OK 0
+#define DCB_READ_EMPTY 1          /* OutcomeCounter.empty_sequence (a window is missing) */
+#define DCB_READ_ONLY_GAPS 2      /* OutcomeCounter.only_gaps */
+#define DCB_READ_LOW_QUALITY 3    /* OutcomeCounter.failed_quality_filter */
+#define DCB_READ_TOO_SHORT 4      /* OutcomeCounter.failed_length_filter */
+#define DCB_READ_BORDERLINE 0x80  /* flag: quality within 1e-7 of the threshold, caller decides */
+int dcb_stitch_fastq(dcb_engine* e, const uint8_t* bases, const uint8_t* quals, int32_t n_windows, int32_t L,
+                     const int32_t* zmw_start, int32_t n_zmw, const int32_t* window_pos,
+                     const uint8_t* names, const int32_t* name_off, double min_quality, int32_t min_length,
+                     uint32_t flags, uint8_t* fastq_out, int64_t fastq_cap, int64_t* rec_off, int32_t* outcome,
+                     double* avg_q);
+
+/* The skip decision of inference_on_n_zmws (quick_inference.py:663-672) for a batch of windows:
+ * mask[w] = avg_phred(ccs_bq[w, :]) > skip_windows_above (entries < 0 are spacing and are dropped, utils.py:88-106);
+ * 2 = within 1e-7 of the threshold, caller decides.  ccs_bq: host int16 [n_windows, L]. */
+int dcb_skip_mask(dcb_engine* e, const int16_t* ccs_bq, int32_t n_windows, int32_t L, double skip_windows_above,
+                  uint8_t* mask_out, double* avg_out /* nullable */);
+
+/* process_skipped_window (quick_inference.py:567-594) for k windows that bypass the model: window j adopts the CCS
+ * bases (ccs_ids, host u8 [k, L], ids 0..4 -> ' ATCG') and the CCS base qualities (ccs_bq, host int16 [k, L]) after
+ * calibrate_quality_scores (calibration_lib.py:77-99; float64) / min(., max_base_quality) / int32 truncation / +33,
+ * and is written to row dst_window[j] of bases / quals ([*, L]; device arrays with DCB_OUT_ON_DEVICE -- e.g. the arrays
+ * dcb_forward filled for the scored windows, so that dcb_stitch_fastq can run on them without a host round trip). */
+int dcb_fill_skipped(dcb_engine* e, const uint8_t* ccs_ids, const int16_t* ccs_bq, const int32_t* dst_window, int32_t k,
+                     int32_t L, int32_t calibration_enabled, double calibration_threshold, double calibration_w,
+                     double calibration_b, uint32_t flags, uint8_t* bases, uint8_t* quals);
+
 /* Device time of the last dcb_forward (milliseconds, CUDA events on the engine's stream). */
 int dcb_last_forward_ms(dcb_engine* e, float* ms);
 /* Number of engine kernels launched by the last dcb_forward. */

@@ -274,6 +274,66 @@ def test_run_model_and_stitch_merges_skipped_windows(engine_mod, golden_dir):
   model.close()
 
 
+@pytest.mark.parametrize("ccs_cal,min_q,min_len", [("skip", 0, 0), ("0,1.1,-0.5", 20, 0), ("30,0.9,2.0", 0, 450)])
+def test_device_post_model_stage_equals_reference_flow(engine_mod, golden_dir, ccs_cal, min_q, min_len):
+  """SURVEY.md 8(f)2 on the device: skip decision (dcb_skip_mask), process_skipped_window (dcb_fill_skipped), sort,
+  stitch + filters + FASTQ bytes (dcb_stitch_fastq) == the reference flow on per-window Python objects
+  (split_skipped_windows -> run_model_on_examples -> sorted -> stitch_to_fastq), read for read, counter for counter."""
+  import itertools
+  from deepconsensus_b200 import inference, stitch_utils
+  z = np.load(os.path.join(golden_dir, "real_windows_human_1m.npz"))
+  rows, names, pos = z["rows"], z["names"], z["window_pos"]
+  p = params_lib.synthetic_params(20, 100, num_hidden_layers=2)
+  w = weights_lib.init_weights(p, seed=25)
+  opts = inference.InferenceOptions(max_length=100, example_height=85, max_passes=20, min_quality=min_q, min_length=min_len,
+                                    batch_size=32, use_ccs_bq=False, cpus=0, skip_windows_above=45,
+                                    use_saved_model=False, max_base_quality=93,
+                                    dc_calibration_values=calibration.parse_calibration_string(CAL),
+                                    ccs_calibration_values=calibration.parse_calibration_string(ccs_cal))
+  model, p = inference.initialize_model("", p, opts, weights=w)
+  rng = np.random.default_rng(8)
+  by_zmw = {}
+  for i in range(len(rows)):
+    name = str(names[i])
+    k = len(by_zmw.get(name, []))
+    kind = rng.integers(0, 5)
+    ccs = rows[i][80]
+    bq = np.where(ccs == 0, -1, rng.integers(30 if kind == 1 else 5, 94 if kind == 1 else 60, size=100)).astype(np.int64)
+    if kind == 2:
+      bq[:] = np.where(ccs == 0, -1, 45)                      # average exactly at the threshold: not skipped (> 45)
+    fd = dict(subreads=rows[i][..., None], **{"subreads/num_passes": 3}, window_pos=k * 100, name=name,
+              ccs_base_quality_scores=bq, ec=1.0, np_num_passes=3, rq=0.99, rg="rg", overflow=bool(kind == 0))
+    by_zmw.setdefault(name, []).append(fd)
+  zmws = [by_zmw[k] for k in sorted(by_zmw)]
+  zmws[1][3]["window_pos"] += 100                             # a missing window in one read
+  for_model, skipped = inference.split_skipped_windows(zmws, opts)
+  assert len(skipped) > 20 and len(for_model) > 20
+  preds = sorted(inference.run_model_on_examples(for_model, model, p, opts) + skipped,
+                 key=lambda dc: (dc.molecule_name, dc.window_pos))
+  want, want_cnt = [], stitch_utils.OutcomeCounter()
+  for name, grp in itertools.groupby(preds, lambda dc: dc.molecule_name):
+    want.append(stitch_utils.stitch_to_fastq(name, list(grp), 100, min_q, min_len, want_cnt))
+  got_cnt = stitch_utils.OutcomeCounter()
+  got = inference.inference_on_zmw_windows(zmws, model, p, opts, got_cnt)
+  assert got == want and got_cnt.__dict__ == want_cnt.__dict__
+  assert got_cnt.empty_sequence >= 1
+  if min_q or min_len:
+    assert got_cnt.failed_quality_filter + got_cnt.failed_length_filter >= 1
+  else:
+    assert got_cnt.success >= 1
+  # the device predicate alone, against the NumPy expression, incl. all-gap and all-zero windows
+  bq = np.stack([np.asarray(fd["ccs_base_quality_scores"]) for zz in zmws for fd in zz]).astype(np.int16)
+  bq[0, :] = -1
+  bq[1, :] = 0
+  mask, avg = model.skip_mask(bq, 45)
+  from deepconsensus_b200 import utils as u
+  ref_avg = np.array([u.avg_phred(r) for r in bq])
+  assert np.abs(avg - ref_avg).max() < 1e-9
+  exact = mask != 2
+  assert np.array_equal(mask[exact].astype(bool), (ref_avg > 45)[exact]) and (mask == 2).sum() >= 1
+  model.close()
+
+
 def test_pipeline_survives_errors_and_mixed_use(engine_mod):
   """(1) a wait() that raises (out-of-range id) must not leave the younger submission in flight: the next call works;
   (2) a blocking forward() between two submit()s must not collide with the slot of the outstanding handle."""
