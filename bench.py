@@ -408,6 +408,38 @@ def main():
                  "oracle / reference-code goldens in tests/), all %d windows of one batch, on the device" % B)
     par["strict_ms_per_batch"] = model.last_ms
 
+  # ---- BASELINE configs[3]: the same step fed by ONE reader rank over NCCL (grouped send/recv of packed chunks,
+  # double-buffered; results gathered back) instead of every rank holding its own shard.  Secondary record: the
+  # natural split for this path is the replica form above (no data-path collective).
+  scatter_info = None
+  if world > 1:
+    from deepconsensus_b200 import parallel as parallel_lib
+    feeder = parallel_lib.ScatterFeeder(packed_bytes, 2 * B * L, reader=0, device=torch.device("cuda", local))
+    step_rows = None
+    if rank == 0:
+      one = torch.from_numpy(np.stack([ppin[i % NBUF][:packed_bytes] for i in range(2)])).to(feeder.device)   # 2 distinct steps
+      step_rows = [one[i].unsqueeze(0).expand(world, packed_bytes).contiguous() for i in range(2)]
+    res_ptr = feeder.results.data_ptr()
+
+    def run_scatter(steps):
+      feeder.scatter(0, step_rows[0] if rank == 0 else None)
+      for i in range(steps):
+        feeder.wait()                                             # chunk i landed (and results i-1 gathered)
+        if i + 1 < steps:
+          feeder.scatter((i + 1) & 1, step_rows[(i + 1) & 1] if rank == 0 else None)   # overlaps the kernels of step i
+        t = model.submit_packed_raw(feeder.inbox[i & 1].data_ptr(), B, FL, res_ptr, res_ptr + B * L)
+        model.wait_raw(t)
+        feeder.gather()
+      feeder.wait()
+    run_scatter(3)
+    sc_trials = [trial(run_scatter) for _ in range(3)]
+    dt_sc = sorted(t[0] for t in sc_trials)[1]
+    scatter_info = dict(value=B * world * args.steps / dt_sc, unit=UNIT, ms_per_step=dt_sc / args.steps * 1e3,
+                        bytes_scattered_per_step=packed_bytes * (world - 1), bytes_gathered_per_step=2 * B * L * (world - 1),
+                        call="rank 0 -> every rank: batch_isend_irecv (ncclGroupStart/Send/Recv/End) of packed chunks, "
+                             "double-buffered; dcb_submit_packed on the received device buffer; results gathered on rank 0",
+                        trials=[round(B * world * args.steps / t[0], 1) for t in sc_trials])
+
   # ---- the "next" row after the model path: per-read stitching of the outputs on the device (dcb_stitch), timed on
   # the device buffers the last forward wrote (128 reads of 8 windows), call-to-return including its own sync
   zs = np.arange(0, B + 1, 8, dtype=np.int32)
@@ -492,7 +524,7 @@ def main():
                                               % (row_bytes // B)),
                        blocking_value=total_windows / dt_e2e_blocking,
                        blocking_call="dcb_forward on float32 rows, one batch at a time"),
-              gpu_launches=launches, roofline=roof, parity=par, clocks=sampler.summary(), numa_node=numa, stitch=stitch_info)
+              gpu_launches=launches, roofline=roof, parity=par, nccl_scatter=scatter_info, clocks=sampler.summary(), numa_node=numa, stitch=stitch_info)
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     os.sched_setaffinity(0, full_affinity)   # the CPU arm may use every host core again
     cores = cpu_threads()

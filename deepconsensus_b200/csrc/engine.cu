@@ -260,6 +260,11 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   // window-aligned tiling: one window per 128-token tile when it fits (lets QKV + attention fuse);
   // otherwise windows are packed back to back
   if (align && e->L <= kTileM) e->Lw = kTileM;
+  // 128 < L <= 256: one window per tile PAIR, so that the one-kernel stack (a CTA pair per window, attention halo
+  // across the pair) applies -- when the rest of its conditions hold
+  else if (align && e->L <= 2 * kTileM && e->stack && cfg->attn_win_size > 0 && cfg->attn_win_size <= 16 &&
+           cfg->num_hidden_layers <= kMaxLayers)
+    e->Lw = 2 * kTileM;
   e->R = 4 * cfg->max_passes + (cfg->use_ccs_bq ? 6 : 5);  // data_providers.py:61-78
   e->pl = make_packed_layout(cfg->max_passes, cfg->max_length, cfg->use_ccs_bq ? 1 : 0);
   e->E = cfg->max_passes * (cfg->per_base_hidden_size + cfg->pw_hidden_size + cfg->ip_hidden_size +
@@ -871,7 +876,8 @@ static int submit_impl(dcb_engine* e, const float* rows, const uint8_t* packed, 
       hp.M = M; hp.L = L; hp.Lw = Lw;
       return hp;
     };
-    const bool use_stack = e->stack && e->fuse_qa && e->ffn_pair && e->fuse_oproj && e->fuse_embed && !e->debug && Lw == kTileM &&
+    const bool use_stack = e->stack && e->fuse_qa && e->ffn_pair && e->fuse_oproj && e->fuse_embed && !e->debug &&
+                           (Lw == kTileM || (Lw == 2 * kTileM && L > kTileM)) &&
                            c.attn_win_size > 0 && c.attn_win_size <= 16 && c.num_hidden_layers <= kMaxLayers;
     {
       RowEpi epi{};

@@ -2729,7 +2729,9 @@ cudaError_t kernels_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(ffn_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ffn2Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(stack_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StackCfg::kSmemBytes);
+  e = cudaFuncSetAttribute(stack_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, StackCfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(stack_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, StackCfg::kSmemBytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(ffn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg::kSmemBytes);
   if (e != cudaSuccess) return e;
@@ -2848,14 +2850,15 @@ void launch_stack(float* x, int ntiles, int L, int win, const StackParams& p, co
   if (!max_pairs) {
     cfg.gridDim = dim3(num_sms() / 2 * 2);
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, stack_pair_kernel, &cfg) != cudaSuccess || nc <= 0) nc = num_sms() / 2;
+    if (cudaOccupancyMaxActiveClusters(&nc, stack_pair_kernel<false>, &cfg) != cudaSuccess || nc <= 0) nc = num_sms() / 2;
     max_pairs = nc;
     if (dev_env("DCB_VERBOSE")) fprintf(stderr, "[dcb200] stack kernel: %d co-resident CTA pairs\n", nc);
   }
   int pairs = (ntiles + 1) / 2;
   if (pairs > max_pairs) pairs = max_pairs;
   cfg.gridDim = dim3(pairs * 2);
-  cudaLaunchKernelEx(&cfg, stack_pair_kernel, x, ntiles, L, win, p, hp);
+  if (L > kTileM) cudaLaunchKernelEx(&cfg, stack_pair_kernel<true>, x, ntiles, L, win, p, hp);   // one window per CTA pair
+  else cudaLaunchKernelEx(&cfg, stack_pair_kernel<false>, x, ntiles, L, win, p, hp);
 }
 
 void launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* att, int L, int Lw, int win, int nwindows,

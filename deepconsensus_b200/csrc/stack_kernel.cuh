@@ -21,6 +21,15 @@
 // producer, UMMA issuers and the peer's relay thread all walk): three dedicated slots, plus three more that live in the
 // tail of the q/k/v staging area and are used only while that area holds the (smaller) hidden tiles of the FFN phase.
 //
+// Windows longer than one tile (128 < L <= 256, template kWide): the window-aligned layout uses Lw = 256, so a CTA pair
+// owns exactly ONE window -- the leader its positions 0..127, the peer 128..255 (rows >= L are layout padding).  Every
+// sub-layer except attention is row-wise and needs nothing else.  In attention the band reaches across the cut: the
+// leader's last query block needs the peer's first 16 key / value rows and the peer's first block the leader's last
+// 16.  That one warp per CTA loads the mma.sync B fragments of the foreign key tile straight from the partner's
+// shared memory (ld.shared::cluster on mapa-translated addresses); `kv_peer` (one remote release-arrive per CTA and
+// head, acquire-wait by the boundary warp) orders it after the partner's q/k/v staging, and the existing att_ready ->
+// out-projection -> s_free chain keeps the partner from overwriting those rows before the reads are done.
+//
 // Cross-CTA protocol as in ffn_pair_kernel: the leader (cluster rank 0) issues every UMMA; tcgen05.commit multicasts
 // completion to both CTAs; what the peer's warps produce is signalled with one default-semantics remote arrive per
 // warp on the leader's barrier; the peer's relay thread forwards "my half of this stage has landed".
@@ -100,6 +109,32 @@ __device__ __forceinline__ void stack_wait(uint64_t* bar, uint32_t parity, int t
 #define SWC(bar, par, tag) mbar_wait_cluster(bar, par)
 #endif
 
+// remote (partner CTA) shared-memory loads for the wide-window attention halo
+__device__ __forceinline__ uint32_t peer_smem_addr(const void* local, uint32_t peer_rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local)), "r"(peer_rank));
+  return raddr;
+}
+__device__ __forceinline__ uint32_t ld_peer_b32(uint32_t raddr) {
+  uint32_t v;
+  asm volatile("ld.shared::cluster.b32 %0, [%1];" : "=r"(v) : "r"(raddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_peer_u16(uint32_t raddr) {
+  uint16_t v;
+  asm volatile("ld.shared::cluster.u16 %0, [%1];" : "=h"(v) : "r"(raddr) : "memory");
+  return (uint32_t)v;
+}
+// release-arrive on the partner's barrier: everything this CTA wrote to its shared memory before (ordered by the
+// preceding CTA barrier) is visible to a partner thread that acquire-waits on it
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint64_t* bar, uint32_t target_cta) {
+  dcb_jitter();
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(target_cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+
+template <bool kWide>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(StackCfg::kThreads, 1)
 stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __grid_constant__ StackParams P,
                   const __grid_constant__ HeadParams HP) {
@@ -121,7 +156,8 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
   uint64_t* hs_full = bars + 20;     // [2]
   uint64_t* hs_free = bars + 22;     // [2]
   uint64_t* y_full = bars + 24;      // FFN of the layer done (commit)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 25);
+  uint64_t* kv_peer = bars + 25;     // kWide: the partner CTA has staged q/k/v of the current head (remote release-arrive)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 26);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -151,6 +187,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
     mbar_init(&hs_free[0], 1);
     mbar_init(&hs_free[1], 1);
     mbar_init(y_full, 1);
+    mbar_init(kv_peer, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_holder, C::kTmemCols);
@@ -537,7 +574,8 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
       arrive_leader(a_ready);
     };
 
-    uint32_t k_acc = 0, k_sfree = 0, k_y = 0, nchunk = 0;
+    uint32_t k_acc = 0, k_sfree = 0, k_y = 0, nchunk = 0, k_kv = 0;
+    const int goff = kWide ? (int)rank * kTileM : 0;   // window position of this CTA's row 0
     for (int ti = 0; ti < rounds; ++ti) {
       const int tile_raw = tile_of(ti);
       const bool valid = tile_raw < ntiles;
@@ -594,6 +632,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
             }
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (kWide && ew == 0 && lane == 0) mbar_arrive_release_cluster(kv_peer, rank ^ 1u);   // my q/k/v of this head are staged
 
           // ---- banded attention of query block `ew` (rows 16*ew .. +15), two-pass softmax (win <= 16)
           {
@@ -609,10 +648,22 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
 #pragma unroll
             for (int nt = 0; nt < kDHP / 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
             float l0 = 0.f, l1 = 0.f;
-            int jlo = i0 - band; if (jlo < 0) jlo = 0; jlo &= ~15;
-            int jhi = i0 + 15 + band + 1; if (jhi > L) jhi = L;
+            // key range in window coordinates (gq = window position of the block's first query); a tile whose local
+            // row index falls outside [0, 128) lives in the partner CTA (kWide only: its rows 0..15 or 112..127)
+            const int gq = goff + i0;
+            int jlo = gq - band; if (jlo < 0) jlo = 0; jlo &= ~15;
+            int jhi = gq + 15 + band + 1; if (jhi > L) jhi = L;
             const int nkt = (jhi - jlo + 15) >> 4;
             constexpr int kMaxKT = 3;
+            const int lj0 = jlo - goff;                 // local row of key tile 0 (multiple of 16; -16 possible when kWide)
+            auto tile_remote = [&](int kt) { return kWide && (lj0 + kt * 16 < 0 || lj0 + kt * 16 >= kTileM); };
+            auto peer_row = [&](int kt) { return lj0 + kt * 16 < 0 ? lj0 + kt * 16 + kTileM : lj0 + kt * 16 - kTileM; };
+            if (kWide) {
+              bool any_remote = false;
+#pragma unroll
+              for (int kt = 0; kt < kMaxKT; ++kt) any_remote |= (kt < nkt) && tile_remote(kt);
+              if (any_remote) SWC(kv_peer, k_kv & 1, 1418);   // the partner's k / v rows of this head are in place
+            }
             float sc[kMaxKT][2][4];
 #pragma unroll
             for (int kt = 0; kt < kMaxKT; ++kt)
@@ -621,14 +672,33 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
 #pragma unroll
             for (int kt = 0; kt < kMaxKT; ++kt) {
               if (kt < nkt) {
-                // B fragments of 16 keys: one ldmatrix.x4 per 16 dims (keys 0-7 x dims 0-7 | 8-15, keys 8-15 x dims 0-7 | 8-15)
-                const uint32_t kaddr = smem_u32(sK + (size_t)(jlo + kt * 16 + (lane & 7) + (lane >> 4) * 8) * kS + ((lane >> 3) & 1) * 8);
+                if (tile_remote(kt)) {
+                  // the partner's key rows: B fragments by 32-bit remote loads (b0 = K[key g][dims 2t, 2t+1], b1 = dims + 8),
+                  // all issued before the first use
+                  const uint32_t kp = peer_smem_addr(sK + (size_t)(peer_row(kt) + g) * kS + 2 * t, rank ^ 1u);
+                  uint32_t kf[kDHP / 16][4];
 #pragma unroll
-                for (int ks = 0; ks < kDHP / 16; ++ks) {
-                  uint32_t a0, a1, c0, c1;
-                  ldmatrix_x4(a0, a1, c0, c1, kaddr + ks * 32);
-                  mma_bf16_16816(sc[kt][0], qa[ks], a0, a1);
-                  mma_bf16_16816(sc[kt][1], qa[ks], c0, c1);
+                  for (int ks = 0; ks < kDHP / 16; ++ks) {
+                    kf[ks][0] = ld_peer_b32(kp + ks * 32);
+                    kf[ks][1] = ld_peer_b32(kp + ks * 32 + 16);
+                    kf[ks][2] = ld_peer_b32(kp + 8 * kS * 2 + ks * 32);
+                    kf[ks][3] = ld_peer_b32(kp + 8 * kS * 2 + ks * 32 + 16);
+                  }
+#pragma unroll
+                  for (int ks = 0; ks < kDHP / 16; ++ks) {
+                    mma_bf16_16816(sc[kt][0], qa[ks], kf[ks][0], kf[ks][1]);
+                    mma_bf16_16816(sc[kt][1], qa[ks], kf[ks][2], kf[ks][3]);
+                  }
+                } else {
+                  // B fragments of 16 keys: one ldmatrix.x4 per 16 dims (keys 0-7 x dims 0-7 | 8-15, keys 8-15 x dims 0-7 | 8-15)
+                  const uint32_t kaddr = smem_u32(sK + (size_t)(lj0 + kt * 16 + (lane & 7) + (lane >> 4) * 8) * kS + ((lane >> 3) & 1) * 8);
+#pragma unroll
+                  for (int ks = 0; ks < kDHP / 16; ++ks) {
+                    uint32_t a0, a1, c0, c1;
+                    ldmatrix_x4(a0, a1, c0, c1, kaddr + ks * 32);
+                    mma_bf16_16816(sc[kt][0], qa[ks], a0, a1);
+                    mma_bf16_16816(sc[kt][1], qa[ks], c0, c1);
+                  }
                 }
               }
             }
@@ -639,7 +709,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
               for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const int i = (e < 2) ? r0 : r1;
+                  const int i = goff + ((e < 2) ? r0 : r1);
                   const int j = jlo + kt * 16 + nt * 8 + 2 * t + (e & 1);
                   const int dlt = i - j;
                   const bool ok = (kt < nkt) && (j < L) && (dlt <= band) && (dlt >= -band);
@@ -673,13 +743,34 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
 #pragma unroll
             for (int kt = 0; kt < kMaxKT; ++kt) {
               if (kt < nkt) {
-                const int vrow = jlo + kt * 16 + (lane & 15);
-                const uint32_t vbase = smem_u32(sV + (size_t)vrow * kS);
+                if (tile_remote(kt)) {
+                  // the partner's value rows: b0 = {V[key 2t][dim g], V[key 2t+1][dim g]}, b1 = keys + 8 -- 16-bit remote
+                  // loads, six dim blocks (24 loads) in flight at a time
+                  const uint32_t vp = peer_smem_addr(sV + (size_t)(peer_row(kt) + 2 * t) * kS + g, rank ^ 1u);
 #pragma unroll
-                for (int nt = 0; nt < kDHP / 8; ++nt) {
-                  uint32_t b0, b1;
-                  ldmatrix_x2_trans(b0, b1, vbase + nt * 16);
-                  mma_bf16_16816(o[nt], pa[kt], b0, b1);
+                  for (int nb = 0; nb < kDHP / 8; nb += 6) {
+                    uint32_t vf[6][4];
+#pragma unroll
+                    for (int u = 0; u < 6; ++u) {
+                      const uint32_t a = vp + (nb + u) * 16;
+                      vf[u][0] = ld_peer_u16(a);
+                      vf[u][1] = ld_peer_u16(a + kS * 2);
+                      vf[u][2] = ld_peer_u16(a + 8 * kS * 2);
+                      vf[u][3] = ld_peer_u16(a + 9 * kS * 2);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 6; ++u)
+                      mma_bf16_16816(o[nb + u], pa[kt], vf[u][0] | (vf[u][1] << 16), vf[u][2] | (vf[u][3] << 16));
+                  }
+                } else {
+                  const int vrow = lj0 + kt * 16 + (lane & 15);
+                  const uint32_t vbase = smem_u32(sV + (size_t)vrow * kS);
+#pragma unroll
+                  for (int nt = 0; nt < kDHP / 8; ++nt) {
+                    uint32_t b0, b1;
+                    ldmatrix_x2_trans(b0, b1, vbase + nt * 16);
+                    mma_bf16_16816(o[nt], pa[kt], b0, b1);
+                  }
                 }
               }
             }
@@ -688,7 +779,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
             l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
             l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
             // rows beyond the window (layout padding) contribute nothing to the out-projection
-            const float inv0 = r0 < L ? 1.f / l0 : 0.f, inv1 = r1 < L ? 1.f / l1 : 0.f;
+            const float inv0 = goff + r0 < L ? 1.f / l0 : 0.f, inv1 = goff + r1 < L ? 1.f / l1 : 0.f;
             // att_h as a KC16 operand tile [18 chunks][128 rows][8] over the (consumed) q area
             __nv_bfloat16* obase = sQ + 2 * t;
 #pragma unroll
@@ -699,6 +790,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
           }
           fence_proxy_async_smem();
           arrive_leader(att_ready);
+          if (kWide) ++k_kv;
         }
         SW(s_free, k_sfree & 1, 1015); ++k_sfree;   // out-projection of the last head done: Y = x_mid
         tc_fence_after();
@@ -828,10 +920,11 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
           for (int j = 0; j < kVocab; ++j) sL[r * 8 + j] = lg[j];
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (!halfsel && valid && r < L) {
+        if (!halfsel && valid && goff + r < L) {
 #pragma unroll
           for (int j = 0; j < kVocab; ++j) lg[j] += sL[r * 8 + j];
-          head_finish(HP, lg, (size_t)tile * L + r);       // window-aligned layout: tile == window, row == position
+          // window-aligned layout: tile == window (kWide: tile pair == window), row == position
+          head_finish(HP, lg, kWide ? (size_t)(tile >> 1) * L + goff + r : (size_t)tile * L + r);
         }
         asm volatile("bar.sync 2, 256;" ::: "memory");     // staging area free for the next tile
       }

@@ -41,3 +41,66 @@ def reduce_counters(counters: Dict[str, int], group=None) -> Dict[str, int]:
   t = torch.tensor([counters[k] for k in keys], dtype=torch.int64, device=dev)
   dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
   return {k: int(v) for k, v in zip(keys, t.tolist())}
+
+
+class ScatterFeeder:
+  """BASELINE configs[3]: ONE reader rank holds the packed rows of a whole step and deals one chunk to every rank
+  (itself included) -- grouped point-to-point sends / receives, i.e. ncclGroupStart; ncclSend(chunk_r -> r) for all r;
+  ncclRecv; ncclGroupEnd -- and collects every rank's base / quality characters the same way.
+
+  Double-buffered: `scatter(step)` posts the transfers of step k+1 asynchronously while the caller scores step k out of
+  the other buffer; `wait()` blocks the host until the posted transfers have landed (the engine runs on its own
+  stream, so completion is awaited on the host before the buffer's address is handed to dcb_submit_packed).
+
+  Tensors are torch uint8 tensors on the communication device ("cuda" with NCCL, "cpu" with gloo for the tests);
+  chunk bytes per rank = chunk_windows * packed_window_bytes, result bytes per rank = 2 * chunk_windows * L.
+  """
+
+  def __init__(self, chunk_bytes: int, result_bytes: int, reader: int = 0, device=None, group=None):
+    import torch
+    import torch.distributed as dist
+    self.torch, self.dist, self.group, self.reader = torch, dist, group, reader
+    self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+    if device is None:
+      device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    self.device = device
+    self.inbox = [torch.empty(chunk_bytes, dtype=torch.uint8, device=device) for _ in range(2)]   # my chunk, 2 buffers
+    self.results = torch.empty(result_bytes, dtype=torch.uint8, device=device)                    # my outputs
+    self.gathered = (torch.empty((self.world, result_bytes), dtype=torch.uint8, device=device)
+                     if self.rank == reader else None)
+    self._pending = []
+
+  def scatter(self, buf: int, step_rows=None) -> None:
+    """Post the transfer of one step: on the reader, `step_rows` is a uint8 tensor [world, chunk_bytes] (device
+    resident); every rank receives its chunk into inbox[buf]."""
+    dist, ops = self.dist, []
+    if self.rank == self.reader:
+      for r in range(self.world):
+        if r == self.rank:
+          self.inbox[buf].copy_(step_rows[r], non_blocking=True)
+        else:
+          ops.append(dist.P2POp(dist.isend, step_rows[r], r, self.group))
+    else:
+      ops.append(dist.P2POp(dist.irecv, self.inbox[buf], self.reader, self.group))
+    self._pending += dist.batch_isend_irecv(ops) if ops else []
+
+  def gather(self) -> None:
+    """Post the collection of every rank's `results` on the reader (row r of `gathered`)."""
+    dist, ops = self.dist, []
+    if self.rank == self.reader:
+      for r in range(self.world):
+        if r == self.rank:
+          self.gathered[r].copy_(self.results, non_blocking=True)
+        else:
+          ops.append(dist.P2POp(dist.irecv, self.gathered[r], r, self.group))
+    else:
+      ops.append(dist.P2POp(dist.isend, self.results, self.reader, self.group))
+    self._pending += dist.batch_isend_irecv(ops) if ops else []
+
+  def wait(self) -> None:
+    """Host-blocking: every posted transfer has completed (and, on CUDA, its stream work has finished)."""
+    for w in self._pending:
+      w.wait()
+    self._pending = []
+    if str(self.device).startswith("cuda"):
+      self.torch.cuda.current_stream().synchronize()

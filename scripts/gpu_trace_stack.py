@@ -6,10 +6,11 @@ from deepconsensus_b200 import params as P, weights as W, synthetic, engine
 p = P.synthetic_params(20, 120); w = W.init_weights(p, seed=1)
 B = 1024
 rows = synthetic.make_rows(p, B, seed=7)
-m = engine.B200Model(p, w, max_batch=B)
+# DCB_OUT=libdcb200_trace.so DCB_EXTRA_FLAGS=-DDCB_TRACE bash deepconsensus_b200/csrc/build.sh
+lib = engine._load(os.path.join(os.path.dirname(engine.library_path()), "libdcb200_trace.so"))
+m = engine.B200Model(p, w, max_batch=B, library=lib)
 for _ in range(3): m.forward(rows)
 print("device ms", m.last_ms)
-lib = engine.load_library()
 buf = (ctypes.c_uint64 * (256 * 16))()
 lib.dcb_debug_trace(buf, 256 * 16)
 a = np.array(buf[:], dtype=np.float64).reshape(256, 16)[:148:2]
