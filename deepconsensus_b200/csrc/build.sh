@@ -16,9 +16,10 @@ build_one() {   # $1 = output .so, $2 = extra flags
   $NVCC $flags -c kernels.cu -o $tag.kernels.o & pids+=($!)
   $NVCC $flags -c strict_kernels.cu -o $tag.strict.o & pids+=($!)
   $NVCC $flags -c post_kernels.cu -o $tag.post.o & pids+=($!)
+  $NVCC $flags -Xcompiler -fvisibility=default -c bam_prep.cpp -o $tag.bam.o & pids+=($!)
   $NVCC $flags -Xcompiler -fvisibility=default -c engine.cu -o $tag.engine.o & pids+=($!)
   for p in "${pids[@]}"; do wait $p; done     # a failed compile fails the build (set -e)
-  $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $out $tag.kernels.o $tag.strict.o $tag.post.o $tag.engine.o -Xlinker -soname=$out
+  $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $out $tag.kernels.o $tag.strict.o $tag.post.o $tag.bam.o $tag.engine.o -lz -Xlinker -soname=$out
   echo "built $(pwd)/$out"
 }
 

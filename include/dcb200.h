@@ -208,6 +208,40 @@ int dcb_fill_skipped(dcb_engine* e, const uint8_t* ccs_ids, const int16_t* ccs_b
                      int32_t L, int32_t calibration_enabled, double calibration_threshold, double calibration_w,
                      double calibration_b, uint32_t flags, uint8_t* bases, uint8_t* quals);
 
+/* ---- feature construction from BAM (host C++, htslib-free, needs no GPU) -----------------------
+ * What `deepconsensus run` does in front of the model: stream the subreads-to-CCS BAM ZMW by ZMW (SubreadGrouper,
+ * pre_lib.py:50-91), expand / clip / indent every subread (expand_clip_indent with trim_insertions, :1061-1239), fetch
+ * the CCS read (:966-998,1322-1330), space all reads out (space_out_subreads, :1242-1276), cut windows of max_length
+ * columns (DcExample.iter_examples, :625-697) and lay the feature rows out (extract_features, :704-744) -- as float32
+ * rows and / or directly as packed rows.  Errors: negative return code, message from dcb_prep_last_error(). */
+typedef struct dcb_prep dcb_prep;
+typedef struct dcb_zmw_info {
+  int32_t n_windows;          /* windows of this ZMW (examples without any CCS position are dropped, as the reference does) */
+  int32_t n_subreads;         /* mapped subreads in the BAM (the first max_passes are used) */
+  const char* name;           /* CCS read name = reference name of the subread alignments; valid until the next call */
+  int32_t has_ec, has_np, has_rq;
+  float ec, rq;               /* aux tags of the CCS read (construct_ccs_read) */
+  int32_t np_num_passes;
+  const char* rg;             /* RG tag or NULL */
+  int32_t ccs_length, spaced_width;
+} dcb_zmw_info;
+int dcb_prep_open(const char* subreads_to_ccs_bam, const char* ccs_bam, int32_t max_passes, int32_t max_length,
+                  int32_t use_ccs_bq, int32_t ins_trim, dcb_prep** out);
+int dcb_prep_next_zmw(dcb_prep* p, dcb_zmw_info* info);   /* 1 = a ZMW is loaded, 0 = end of file, < 0 = error */
+/* The windows of the loaded ZMW; every output may be NULL.  rows float32 [n, R, L]; packed [n, dcb_packed_window_bytes];
+ * window_pos / num_passes int32 [n]; overflow u8 [n]; ccs_bq int16 [n, L] (-1 at gaps and padding). */
+int dcb_prep_get_windows(dcb_prep* p, float* rows, uint8_t* packed, int32_t* window_pos, uint8_t* overflow,
+                         int16_t* ccs_bq, int32_t* num_passes);
+const char* dcb_prep_ccs_header(dcb_prep* p);             /* SAM header text of the CCS BAM */
+void dcb_prep_close(dcb_prep* p);
+const char* dcb_prep_last_error(void);
+/* Unaligned BAM output as quick_inference.py:742-760,892-897 writes it (flag 4, mapq 255, tags ec:f np:i rq:f RG:Z zm:i). */
+typedef struct dcb_bamw dcb_bamw;
+int dcb_bamw_open(const char* path, const char* header_text, dcb_bamw** out);
+int dcb_bamw_write(dcb_bamw* w, const char* name, const uint8_t* seq, const uint8_t* qual_phred33, int32_t len,
+                   int32_t has_ec, float ec, int32_t np_num_passes, float rq, const char* rg);
+int dcb_bamw_close(dcb_bamw* w);
+
 /* Device time of the last dcb_forward (milliseconds, CUDA events on the engine's stream). */
 int dcb_last_forward_ms(dcb_engine* e, float* ms);
 /* Number of engine kernels launched by the last dcb_forward. */

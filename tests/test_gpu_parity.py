@@ -335,6 +335,59 @@ def test_device_post_model_stage_equals_reference_flow(engine_mod, golden_dir, c
   model.close()
 
 
+def test_run_from_bam_fixtures_end_to_end(engine_mod, golden_dir, tmp_path):
+  """BASELINE configs[0] (plumbing): `deepconsensus run` on the reference's own BAM fixtures (testdata/human_1m, 10 ZMWs,
+  1 593 windows) -- BAM -> features (C++) -> skip / model / fill / stitch (CUDA) -> FASTQ and BAM.  The fixture model
+  directory ships without its data shard, so the variables are seeded; the check is that the whole native flow gives
+  the records the reference flow on per-window Python objects gives, and that FASTQ and BAM outputs agree."""
+  import gzip, itertools, shutil
+  from deepconsensus_b200 import inference, preprocess, run as run_lib, stitch_utils
+  d = os.path.join(golden_dir, "human_1m")
+  ck = tmp_path / "model"
+  shutil.copytree(os.path.join(golden_dir, "ckpt", "model"), ck)
+  args = dict(subreads_to_ccs=os.path.join(d, "subreads_to_ccs.bam"), ccs_bam=os.path.join(d, "ccs.bam"),
+              checkpoint=str(ck / "checkpoint-1"), batch_zmws=4, batch_size=256, min_quality=0, random_weights=3)
+  fq = str(tmp_path / "out.fastq")
+  cnt = run_lib.run(output=fq, **args)
+  bam = str(tmp_path / "out.bam")
+  cnt2 = run_lib.run(output=bam, **args)
+  assert cnt.__dict__ == cnt2.__dict__ and cnt.success + cnt.failed_quality_filter + cnt.empty_sequence + cnt.only_gaps == 10
+  got = open(fq).read()
+  # reference flow from per-window objects
+  p = params_lib.read_params_from_json(str(ck / "checkpoint-1"))
+  opts = inference.InferenceOptions(max_length=100, example_height=85, max_passes=20, min_quality=0, min_length=0,
+                                    batch_size=256, use_ccs_bq=False, cpus=0, skip_windows_above=45, use_saved_model=False,
+                                    max_base_quality=93,
+                                    dc_calibration_values=calibration.parse_calibration_string(p.get("dc_calibration", "skip")),
+                                    ccs_calibration_values=calibration.parse_calibration_string("skip"))
+  params_lib.modify_params(p, max_length=100)
+  model, p = inference.initialize_model("", p, opts, weights=weights_lib.init_weights(p, seed=3))
+  zmws = list(preprocess.stream_zmw_windows(args["subreads_to_ccs"], args["ccs_bam"], 20, 100))
+  for_model, skipped = inference.split_skipped_windows(zmws, opts)
+  preds = sorted(inference.run_model_on_examples(for_model, model, p, opts) + skipped,
+                 key=lambda dc: (dc.molecule_name, dc.window_pos))
+  model.close()
+  want, want_cnt = [], stitch_utils.OutcomeCounter()
+  for name, grp in itertools.groupby(preds, lambda dc: dc.molecule_name):
+    rec = stitch_utils.stitch_to_fastq(name, list(grp), 100, 0, 0, want_cnt)
+    if rec:
+      want.append(rec)
+  # the run processes ZMWs in batches of 4 in file order and sorts within a batch; compare as sets of records
+  assert sorted(got.split("@")[1:]) == sorted("".join(want).split("@")[1:])
+  assert cnt.__dict__ == want_cnt.__dict__ and cnt.success >= 8
+  # BAM output: same names / sequences / qualities as the FASTQ
+  raw = open(bam, "rb").read()
+  plain, pos = b"", 0
+  while pos < len(raw):
+    bs = raw[pos + 16] | (raw[pos + 17] << 8)
+    plain += gzip.decompress(raw[pos:pos + bs + 1])
+    pos += bs + 1
+  for rec in want:
+    name, seq, _, qual = rec.splitlines()
+    assert name[1:].encode() + b"\0" in plain
+    assert bytes(ord(c) - 33 for c in qual[:50]) in plain
+
+
 def test_pipeline_survives_errors_and_mixed_use(engine_mod):
   """(1) a wait() that raises (out-of-range id) must not leave the younger submission in flight: the next call works;
   (2) a blocking forward() between two submit()s must not collide with the slot of the outstanding handle."""
