@@ -363,10 +363,12 @@ def main():
     step_resident(i)
   sampler = ClockSampler(local)
   sampler.start()
-  res_trials = [trial(run_resident_pipelined) for _ in range(TRIALS)]          # per-kernel events OFF
-  res_f32 = [trial(lambda n: run_resident_pipelined(n, packed=False)) for _ in range(3)]
   run_e2e_pipelined(3)
-  e2e_trials = [trial(run_e2e_pipelined) for _ in range(TRIALS)]
+  res_trials, e2e_trials = [], []
+  for _ in range(TRIALS):       # resident and host-buffer trials alternate, so both see the same thermal / power state
+    res_trials.append(trial(run_resident_pipelined))                             # per-kernel events OFF
+    e2e_trials.append(trial(run_e2e_pipelined))
+  res_f32 = [trial(lambda n: run_resident_pipelined(n, packed=False)) for _ in range(3)]
   run_e2e_pipelined(3, packed=False)
   f32_trials = [trial(lambda n: run_e2e_pipelined(n, packed=False)) for _ in range(3)]
   dt_e2e_f32 = sorted(t[0] for t in f32_trials)[1]
@@ -522,7 +524,8 @@ def main():
               config=config_dict(world, B),
               resident_float32_rows=dict(value=total_windows / sorted(t[0] for t in res_f32)[1],
                                          note="same region with float32 [B,R,L] rows resident instead of packed rows"),
-              timing=dict(trials=TRIALS, reported="median trial; every trial = exactly %d steps between barrier+sync" % args.steps,
+              timing=dict(trials=TRIALS, reported="median trial; every trial = exactly %d steps between barrier+sync; value and "
+                                                  "e2e trials alternate (same thermal / power state)" % args.steps,
                           value_trials=[round(total_windows / t[0], 1) for t in res_trials],
                           e2e_trials=[round(total_windows / t[0], 1) for t in e2e_trials],
                           l2="inputs rotate over %d resident packed batches (%.0f MB of addresses > 126 MB L2); every step also "

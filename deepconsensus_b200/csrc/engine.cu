@@ -49,11 +49,14 @@ struct dcb_engine {
   int num_sms = 148;
   cudaStream_t stream = nullptr;        // compute (+ result D2H)
   cudaStream_t copy_stream = nullptr;   // H2D of the rows of the NEXT submission, overlapping the kernels of the current one
+  cudaStream_t out_stream = nullptr;    // D2H of the results of the PREVIOUS submission, off the compute stream
   // Two-deep submission pipeline (dcb_submit / dcb_wait): only the input rows and the status word are per slot; every
   // other buffer is reused in stream order.
   struct Slot {
     float* d_rows = nullptr;
     uint8_t* d_packed = nullptr;        // packed rows of a dcb_submit_packed call (allocated on first use)
+    uint8_t *d_bases = nullptr, *d_quals = nullptr;   // per slot: the results of batch i are copied out on `out_stream`
+    float *d_probs = nullptr, *d_logits = nullptr;    // while the kernels of batch i+1 already write the other slot's
     int* d_status = nullptr;
     int* h_status = nullptr;            // pinned
     cudaEvent_t rows_ready = nullptr, ev0 = nullptr, ev1 = nullptr, done = nullptr;
@@ -101,8 +104,6 @@ struct dcb_engine {
   float* d_x = nullptr;
   __nv_bfloat16* d_xb = nullptr;
   __nv_bfloat16* d_att = nullptr;
-  uint8_t *d_bases = nullptr, *d_quals = nullptr;
-  float *d_probs = nullptr, *d_logits = nullptr;
   // stitch scratch (grown on demand)
   uint8_t *d_st_in = nullptr, *d_st_out = nullptr;   // [2][cap] each: bases|quals, seq|qual
   int32_t *d_st_start = nullptr, *d_st_len = nullptr;
@@ -284,6 +285,7 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   CUC(cudaSetDevice(cfg->device));
   CUC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUC(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&e->out_stream, cudaStreamNonBlocking));
   for (auto& sl : e->slots) {
     CUC(cudaEventCreateWithFlags(&sl.rows_ready, cudaEventDisableTiming));
     CUC(cudaEventCreate(&sl.ev0));
@@ -307,8 +309,10 @@ int dcb_create(const dcb_config* cfg, dcb_engine** out) {
   TRY(dev_alloc(e, &e->d_xb, T * act_image_elems(kDP)));
   TRY(dev_alloc(e, &e->d_att, T * act_image_elems(kDP)));
   const size_t mtok = (size_t)cfg->max_batch * e->L;
-  TRY(dev_alloc(e, &e->d_bases, mtok));
-  TRY(dev_alloc(e, &e->d_quals, mtok));
+  for (auto& sl : e->slots) {
+    TRY(dev_alloc(e, &sl.d_bases, mtok));
+    TRY(dev_alloc(e, &sl.d_quals, mtok));
+  }
 #undef TRY
 #undef CUC
   *out = e;
@@ -320,6 +324,7 @@ void dcb_destroy(dcb_engine* e) {
   cudaSetDevice(e->cfg.device);
   if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->out_stream) cudaStreamSynchronize(e->out_stream);
   for (void* p : e->owned) cudaFree(p);
   if (e->d_st_in) cudaFree(e->d_st_in);
   if (e->d_st_out) cudaFree(e->d_st_out);
@@ -339,6 +344,7 @@ void dcb_destroy(dcb_engine* e) {
     if (sl.h_status) cudaFreeHost(sl.h_status);
   }
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  if (e->out_stream) cudaStreamDestroy(e->out_stream);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -780,8 +786,8 @@ static int submit_impl(dcb_engine* e, const float* rows, const uint8_t* packed, 
   if (packed && (c.pw_max > 255 || c.ip_max > 255)) return fail(e, DCB_ERR_INVALID, "packed rows need PW_MAX, IP_MAX <= 255");
   const int L = e->L, R = e->R;
   const size_t mtok = (size_t)c.max_batch * L;
-  if (probs_out && !e->d_probs) { int rc = dev_alloc(e, &e->d_probs, mtok * kVocab); if (rc) return rc; }
-  if (logits_out && !e->d_logits) { int rc = dev_alloc(e, &e->d_logits, mtok * kVocab); if (rc) return rc; }
+  if (probs_out && !sl.d_probs) { int rc = dev_alloc(e, &sl.d_probs, mtok * kVocab); if (rc) return rc; }
+  if (logits_out && !sl.d_logits) { int rc = dev_alloc(e, &sl.d_logits, mtok * kVocab); if (rc) return rc; }
   const bool rows_dev = flags & DCB_ROWS_ON_DEVICE;
   const bool out_dev = flags & DCB_OUT_ON_DEVICE;
   if ((flags & DCB_STRICT_FP32) && (flags & DCB_FAST_BF16)) return fail(e, DCB_ERR_INVALID, "DCB_STRICT_FP32 and DCB_FAST_BF16 are exclusive");
@@ -843,10 +849,10 @@ static int submit_impl(dcb_engine* e, const float* rows, const uint8_t* packed, 
     HeadParams hp{};
     hp.x = e->d_x; hp.ln_g = e->d_fln_g; hp.ln_b = e->d_fln_b; hp.wfc = e->d_wfc; hp.bfc = e->d_bfc;
     const size_t t0 = (size_t)w0 * L;
-    hp.bases = (out_dev ? bases_out : e->d_bases) + t0;
-    hp.quals = (out_dev ? quals_out : e->d_quals) + t0;
-    hp.probs = probs_out ? ((out_dev ? probs_out : e->d_probs) + t0 * kVocab) : nullptr;
-    hp.logits = logits_out ? ((out_dev ? logits_out : e->d_logits) + t0 * kVocab) : nullptr;
+    hp.bases = (out_dev ? bases_out : sl.d_bases) + t0;
+    hp.quals = (out_dev ? quals_out : sl.d_quals) + t0;
+    hp.probs = probs_out ? ((out_dev ? probs_out : sl.d_probs) + t0 * kVocab) : nullptr;
+    hp.logits = logits_out ? ((out_dev ? logits_out : sl.d_logits) + t0 * kVocab) : nullptr;
     hp.calib_enabled = c.calibration_enabled;
     hp.calib_thr = (float)c.calibration_threshold; hp.calib_w = (float)c.calibration_w; hp.calib_b = (float)c.calibration_b;
     hp.calib_thr64 = c.calibration_threshold; hp.calib_w64 = c.calibration_w; hp.calib_b64 = c.calibration_b;
@@ -990,15 +996,18 @@ static int submit_impl(dcb_engine* e, const float* rows, const uint8_t* packed, 
     e->last_chunk_tokens = M;
   }
   CU(e, cudaEventRecord(sl.ev1, st));
+  // results and status go back on their own stream: the compute stream is free for the next submission's kernels
+  cudaStream_t os = e->out_stream;
+  CU(e, cudaStreamWaitEvent(os, sl.ev1, 0));
   if (!out_dev) {
     const size_t ntok = (size_t)batch * L;
-    CU(e, cudaMemcpyAsync(bases_out, e->d_bases, ntok, cudaMemcpyDeviceToHost, st));
-    CU(e, cudaMemcpyAsync(quals_out, e->d_quals, ntok, cudaMemcpyDeviceToHost, st));
-    if (probs_out) CU(e, cudaMemcpyAsync(probs_out, e->d_probs, ntok * kVocab * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (logits_out) CU(e, cudaMemcpyAsync(logits_out, e->d_logits, ntok * kVocab * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(e, cudaMemcpyAsync(bases_out, sl.d_bases, ntok, cudaMemcpyDeviceToHost, os));
+    CU(e, cudaMemcpyAsync(quals_out, sl.d_quals, ntok, cudaMemcpyDeviceToHost, os));
+    if (probs_out) CU(e, cudaMemcpyAsync(probs_out, sl.d_probs, ntok * kVocab * sizeof(float), cudaMemcpyDeviceToHost, os));
+    if (logits_out) CU(e, cudaMemcpyAsync(logits_out, sl.d_logits, ntok * kVocab * sizeof(float), cudaMemcpyDeviceToHost, os));
   }
-  CU(e, cudaMemcpyAsync(sl.h_status, sl.d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CU(e, cudaEventRecord(sl.done, st));
+  CU(e, cudaMemcpyAsync(sl.h_status, sl.d_status, sizeof(int), cudaMemcpyDeviceToHost, os));
+  CU(e, cudaEventRecord(sl.done, os));
   CU(e, cudaGetLastError());
   sl.launches = launches;
   sl.busy = true;
