@@ -313,8 +313,10 @@ def main():
         t = model.submit_raw(pin_addr[i % NBUF], B, 0, outs[i % 2], outs[i % 2] + B * L)
       if pending is not None:
         model.wait_raw(pending)
+        run_resident_pipelined.dev_ms += model.last_forward_ms()
       pending = t
     model.wait_raw(pending)
+    run_resident_pipelined.dev_ms += model.last_forward_ms()
 
   def barrier():
     torch.cuda.synchronize()
@@ -379,7 +381,8 @@ def main():
   sampler.join(timeout=2)
   med = sorted(range(TRIALS), key=lambda i: res_trials[i][0])[TRIALS // 2]
   dt, dev_ms = res_trials[med]
-  dt_e2e = sorted(t[0] for t in e2e_trials)[TRIALS // 2]
+  med_e = sorted(range(TRIALS), key=lambda i: e2e_trials[i][0])[TRIALS // 2]
+  dt_e2e, dev_ms_e2e = e2e_trials[med_e]
   launches = model.last_forward_launches() * args.steps
 
   # ---- per-kernel device times (CUDA events around every launch on the engine's stream): a separate pass of the
@@ -534,6 +537,7 @@ def main():
                           gflop_per_window=F / 1e9),
               e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=packed_bytes * world,
                        d2h_bytes_per_step=2 * B * L * world, ms_per_step=dt_e2e / args.steps * 1e3,
+                       device_ms_per_step=dev_ms_e2e / args.steps,
                        call="dcb_submit_packed/dcb_wait from pinned host memory, 2 batches in flight (as "
                             "inference.run_model_on_examples); input = packed rows, %d B/window "
                             "(include/dcb200.h), results = base + quality characters back on the host" % stride,

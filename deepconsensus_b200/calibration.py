@@ -1,6 +1,6 @@
 """Base-quality calibration (mirror of `quality_calibration/calibration_lib.py:35-99`).
 
-The device epilogue applies the same linear map (see csrc/head.cu); this module
+The device epilogue applies the same linear map (csrc/head_finish.cuh, csrc/post_kernels.cu); this module
 is the host-side parser plus a NumPy implementation for skipped windows and tests.
 """
 from __future__ import annotations

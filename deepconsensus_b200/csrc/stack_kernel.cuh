@@ -575,6 +575,10 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
     };
 
     uint32_t k_acc = 0, k_sfree = 0, k_y = 0, nchunk = 0, k_kv = 0;
+#ifdef DCB_TRACE
+    // worker-side cycle trace (warp 4 of every CTA): slots 8..15 of g_ffn_trace
+    long long w_rowpass = 0, w_stage = 0, w_qk = 0, w_soft = 0, w_pv = 0, w_store = 0, w_wait = 0, w_hid = 0;
+#endif
     const int goff = kWide ? (int)rank * kTileM : 0;   // window position of this CTA's row 0
     for (int ti = 0; ti < rounds; ++ti) {
       const int tile_raw = tile_of(ti);
@@ -601,10 +605,12 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
           SW(y_full, k_y & 1, 912); ++k_y;
           tc_fence_after();
         }
-        row_pass(n > 0 ? P.b2[n - 1] : nullptr, P.ln_g0[n], P.ln_b0[n]);
+        { TRACE_T0(); row_pass(n > 0 ? P.b2[n - 1] : nullptr, P.ln_g0[n], P.ln_b0[n]); TRACE_ADD(w_rowpass); }
 
         for (int h = 0; h < kHeads; ++h) {
+          TRACE_T0();
           if (h > 0) { SW(s_free, k_sfree & 1, 1013); ++k_sfree; }   // att_{h-1} consumed by its out-projection
+          TRACE_ADD(w_wait);
           // ---- q, k, v blocks: TMEM -> bf16 -> padded shared-memory rows
           for (int m = 0; m < 3; ++m) {
             SW(acc_full, k_acc & 1, 1114); ++k_acc;
@@ -632,6 +638,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
             }
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
+          TRACE_ADD(w_stage);
           if (kWide && ew == 0 && lane == 0) mbar_arrive_release_cluster(kv_peer, rank ^ 1u);   // my q/k/v of this head are staged
 
           // ---- banded attention of query block `ew` (rows 16*ew .. +15), two-pass softmax (win <= 16)
@@ -702,6 +709,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
                 }
               }
             }
+            TRACE_ADD(w_qk);
             float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
             for (int kt = 0; kt < kMaxKT; ++kt)
@@ -740,6 +748,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
               pa[kt][2] = pack_bf16x2(p[1][0], p[1][1]);
               pa[kt][3] = pack_bf16x2(p[1][2], p[1][3]);
             }
+            TRACE_ADD(w_soft);
 #pragma unroll
             for (int kt = 0; kt < kMaxKT; ++kt) {
               if (kt < nkt) {
@@ -774,6 +783,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
                 }
               }
             }
+            TRACE_ADD(w_pv);
             l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
             l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
             l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
@@ -790,13 +800,14 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
           }
           fence_proxy_async_smem();
           arrive_leader(att_ready);
+          TRACE_ADD(w_store);
           if (kWide) ++k_kv;
         }
-        SW(s_free, k_sfree & 1, 1015); ++k_sfree;   // out-projection of the last head done: Y = x_mid
+        { TRACE_T0(); SW(s_free, k_sfree & 1, 1015); ++k_sfree; TRACE_ADD(w_wait); }   // out-projection of the last head done: Y = x_mid
         tc_fence_after();
 
         // ---- P5: operand tile of the FFN
-        row_pass(nullptr, P.ln_g1[n], P.ln_b1[n]);
+        { TRACE_T0(); row_pass(nullptr, P.ln_g1[n], P.ln_b1[n]); TRACE_ADD(w_rowpass); }
 
         // ---- hidden-chunk epilogue: H (+b1, ReLU) -> bf16 -> shared memory operand of GEMM2
         const float* __restrict__ b1 = P.b1[n];
@@ -805,6 +816,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
           SW(h_full, nchunk & 1, 1216);
           tc_fence_after();
           SW(&hs_free[b], ((nchunk >> 1) & 1) ^ 1, 1317);
+          TRACE_T0();
           uint4* hrow = reinterpret_cast<uint4*>(sS + b * C::kHBytes) + r;
           const float* bias = b1 + c * kFFChunk + halfsel * (kFFChunk / 2);
           uint32_t acc[kFFChunk / 32][16];
@@ -833,6 +845,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
           }
           fence_proxy_async_smem();
           arrive_leader(&hs_full[b]);
+          TRACE_ADD(w_hid);
         }
       }
 
@@ -930,6 +943,12 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
       }
       tc_fence_before();
     }
+#ifdef DCB_TRACE
+    if (warp == 4 && lane == 0 && blockIdx.x < 256) {
+      unsigned long long* tr = g_ffn_trace + blockIdx.x * 16 + 8;
+      tr[0] = w_rowpass; tr[1] = w_stage; tr[2] = w_qk; tr[3] = w_soft; tr[4] = w_pv; tr[5] = w_store; tr[6] = w_wait; tr[7] = w_hid;
+    }
+#endif
   }
   tc_fence_before();
   __syncthreads();

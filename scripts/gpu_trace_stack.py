@@ -14,7 +14,9 @@ print("device ms", m.last_ms)
 buf = (ctypes.c_uint64 * (256 * 16))()
 lib.dcb_debug_trace(buf, 256 * 16)
 a = np.array(buf[:], dtype=np.float64).reshape(256, 16)[:148:2]
-names = ["total", "wait_a_ready_P1", "wait_acc_free", "qkv_issue", "wait_att_ready", "oproj_issue", "wait_a_ready_P5", "ffn_g1_loop"]
+names = ["total", "wait_a_ready_P1", "wait_acc_free", "qkv_issue", "wait_att_ready", "oproj_issue", "wait_a_ready_P5", "ffn_g1_loop",
+         "W row passes (2/layer)", "W q/k/v staging incl. waits (2 heads)", "W attention: q frags + QK^T", "W softmax", "W PV",
+         "W att_h store + arrive", "W wait s_free", "W hidden epilogue (16 chunks, excl. waits)"]
 units = 7 * 6
 for i, nme in enumerate(names):
     col = a[:, i]
