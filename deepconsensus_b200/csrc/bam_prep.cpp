@@ -24,7 +24,12 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dcb200.h"
@@ -427,48 +432,95 @@ inline float encode_base(char c) {          // dc_constants.SEQ_VOCAB = ' ATCG'
   switch (c) { case 'A': return 1.f; case 'T': return 2.f; case 'C': return 3.f; case 'G': return 4.f; default: return 0.f; }
 }
 
-}  // namespace
-
-struct dcb_prep {
-  BamReader sub, ccs;
-  int P = 0, L = 0, bq = 0, ins_trim = 0, R = 0;
-  dcb::PackedLayout pl{};
-  bool have_pending = false, sub_eof = false;
-  BamRecord pending;
-  int64_t pending_zm = 0;
-  // current ZMW
+// Everything derived from one ZMW (what a DcExample holds after space_out_subreads + the window list)
+struct ZmwState {
   std::vector<Read> reads;        // subreads..., ccs (spaced)
   std::string name, rg;
   float ec = 0, rq = 0;
   int has_ec = 0, has_np = 0, has_rq = 0, has_rg = 0;
-  int32_t np_passes = 0;
+  int32_t np_passes = 0, n_subreads = 0, ccs_length = 0;
   std::vector<int32_t> win_start; // column of every emitted window
+  int rc = DCB_OK;                // error of the processing step (message in `error`)
+  std::string error;
 };
 
-extern "C" {
+struct ZmwJob {
+  std::vector<BamRecord> group;
+  BamRecord ccs;
+  std::string name;
+};
 
-const char* dcb_prep_last_error(void) { return g_prep_error.c_str(); }
+struct PrepCfg { int P = 0, L = 0, bq = 0, ins_trim = 0, R = 0; dcb::PackedLayout pl{}; };
 
-int dcb_prep_open(const char* subreads_to_ccs_bam, const char* ccs_bam, int32_t max_passes, int32_t max_length,
-                  int32_t use_ccs_bq, int32_t ins_trim, dcb_prep** out) {
-  if (!subreads_to_ccs_bam || !ccs_bam || !out || max_passes <= 0 || max_length <= 0) return pfail(DCB_ERR_INVALID, "dcb_prep_open: bad argument");
-  dcb_prep* p = new dcb_prep();
-  p->P = max_passes; p->L = max_length; p->bq = use_ccs_bq ? 1 : 0; p->ins_trim = ins_trim;
-  p->R = 4 * max_passes + 5 + p->bq;
-  p->pl = dcb::make_packed_layout(max_passes, max_length, p->bq);
-  int rc = p->sub.open(subreads_to_ccs_bam);
-  if (!rc) rc = p->ccs.open(ccs_bam);
-  if (rc) { delete p; return rc; }
-  *out = p;
-  return DCB_OK;
+// CPU-heavy part, no I/O: expand_clip_indent per subread, construct_ccs_read, space_out_subreads, window list
+void process_zmw(const PrepCfg& cfg, ZmwJob* job, ZmwState* st) {
+  st->name = job->name;
+  st->n_subreads = (int32_t)job->group.size();
+  st->reads.clear();
+  st->reads.resize(job->group.size() + 1);
+  for (size_t i = 0; i < job->group.size(); ++i) {
+    const int rc = expand_clip_indent(&job->group[i], cfg.ins_trim, &st->reads[i]);
+    if (rc) { st->rc = rc; st->error = g_prep_error; return; }
+  }
+  const BamRecord& c = job->ccs;
+  construct_ccs_read(c, &st->reads.back());
+  Tag t;
+  st->has_ec = c.find("ec", &t); if (st->has_ec) st->ec = (float)BamRecord::scalar(t);
+  st->has_np = c.find("np", &t); if (st->has_np) st->np_passes = (int32_t)BamRecord::scalar(t);
+  st->has_rq = c.find("rq", &t); if (st->has_rq) st->rq = (float)BamRecord::scalar(t);
+  st->has_rg = c.find("RG", &t) && t.type == 'Z'; if (st->has_rg) st->rg = reinterpret_cast<const char*>(t.p);
+  st->ccs_length = (int32_t)c.seq.size();
+  space_out(st->reads);
+  // DcExample.iter_examples (pre_lib.py:625-697), fixed-width windows
+  const Read& ccs = st->reads.back();
+  const int width = (int)ccs.bases.size();
+  int ccs_width = width;
+  while (ccs_width > 0 && (ccs.bases[ccs_width - 1] == ' ' || ccs.bases[ccs_width - 1] == '\t' || ccs.bases[ccs_width - 1] == '\n')) --ccs_width;
+  const int nwin = (ccs_width + cfg.L - 1) / cfg.L;
+  st->win_start.clear();
+  int start = 0;
+  for (int w = 0; w < nwin; ++w) {
+    if (start > ccs_width) break;
+    const int s0 = start;
+    start += cfg.L;
+    bool any = false;
+    for (int i = s0; i < std::min(s0 + cfg.L, width); ++i) any |= ccs.ccs_idx[i] >= 0;
+    if (!any) continue;                                         // n_examples_no_ccs_idx
+    st->win_start.push_back(s0);
+  }
 }
 
-void dcb_prep_close(dcb_prep* p) { delete p; }
+}  // namespace
 
-// Advances to the next ZMW that has mapped subreads.  Returns 1 and fills `info`, 0 at the end of the file, < 0 on error.
-int dcb_prep_next_zmw(dcb_prep* p, dcb_zmw_info* info) {
-  if (!p || !info) return pfail(DCB_ERR_INVALID, "dcb_prep_next_zmw: null argument");
-  std::vector<BamRecord> group;
+struct dcb_prep {
+  BamReader sub, ccs;
+  PrepCfg cfg;
+  bool have_pending = false, sub_eof = false;
+  BamRecord pending;
+  int64_t pending_zm = 0;
+  ZmwState cur;                   // the ZMW handed out by the last dcb_prep_next_zmw
+  // optional worker pool (dcb_prep_set_threads): one reader thread decodes and groups, n workers process, results are
+  // handed out in file order
+  int n_threads = 0;
+  bool started = false, stop = false;
+  std::thread reader;
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv_job, cv_res, cv_space;
+  std::deque<std::pair<int64_t, ZmwJob>> jobs;
+  std::map<int64_t, ZmwState> results;
+  int64_t next_seq = 0, total = -1;   // total: number of ZMWs once the reader hit the end (or an error)
+  int reader_rc = DCB_OK;
+  std::string reader_error;
+};
+
+namespace {
+
+// Sequential I/O: the next group of mapped subreads with one zm (SubreadGrouper, pre_lib.py:50-91) and its CCS record
+// (pre_lib.py:1322-1330).  1 = job filled, 0 = end of file, < 0 = error.
+int read_job(dcb_prep* p, ZmwJob* job) {
+  std::vector<BamRecord>& group = job->group;
+  group.clear();
   int64_t zm = 0;
   bool have_zm = false;
   auto zm_of = [&](const BamRecord& r, int64_t* v) {
@@ -477,8 +529,8 @@ int dcb_prep_next_zmw(dcb_prep* p, dcb_zmw_info* info) {
     *v = (int64_t)BamRecord::scalar(t);
     return true;
   };
-  // SubreadGrouper (pre_lib.py:50-91): consecutive records with the same zm; unmapped records are dropped, but the very
-  // first record of the file sets the first group's zm even when it is unmapped
+  // consecutive records with the same zm; unmapped records are dropped, but the very first record of the file sets the
+  // first group's zm even when it is unmapped
   if (p->have_pending) { group.push_back(p->pending); zm = p->pending_zm; have_zm = true; p->have_pending = false; }
   while (!p->sub_eof) {
     BamRecord r;
@@ -496,55 +548,146 @@ int dcb_prep_next_zmw(dcb_prep* p, dcb_zmw_info* info) {
   if (group.empty()) return 0;
   const int32_t refid = group[0].refid;
   if (refid < 0 || refid >= (int32_t)p->sub.refs.size()) return pfail(DCB_ERR_INVALID, "%s: no reference name", group[0].qname.c_str());
-  p->name = p->sub.refs[refid];
-  p->reads.clear();
-  p->reads.resize(group.size() + 1);
-  for (size_t i = 0; i < group.size(); ++i) {
-    const int rc = expand_clip_indent(&group[i], p->ins_trim, &p->reads[i]);
-    if (rc) return rc;
-  }
-  // the CCS read: advance in the CCS BAM until the names match (pre_lib.py:1322-1330)
-  BamRecord c;
+  job->name = p->sub.refs[refid];
   for (;;) {
-    const int rc = p->ccs.next(&c);
+    const int rc = p->ccs.next(&job->ccs);
     if (rc < 0) return rc;
-    if (rc == 0) return pfail(DCB_ERR_INVALID, "ccs bam does not contain %s", p->name.c_str());
-    if (c.qname == p->name) break;
+    if (rc == 0) return pfail(DCB_ERR_INVALID, "ccs bam does not contain %s", job->name.c_str());
+    if (job->ccs.qname == job->name) break;
   }
-  construct_ccs_read(c, &p->reads.back());
-  Tag t;
-  p->has_ec = c.find("ec", &t); if (p->has_ec) p->ec = (float)BamRecord::scalar(t);
-  p->has_np = c.find("np", &t); if (p->has_np) p->np_passes = (int32_t)BamRecord::scalar(t);
-  p->has_rq = c.find("rq", &t); if (p->has_rq) p->rq = (float)BamRecord::scalar(t);
-  p->has_rg = c.find("RG", &t) && t.type == 'Z'; if (p->has_rg) p->rg = reinterpret_cast<const char*>(t.p);
-  space_out(p->reads);
-  // DcExample.iter_examples (pre_lib.py:625-697), fixed-width windows
-  const Read& ccs = p->reads.back();
-  const int width = (int)ccs.bases.size();
-  int ccs_width = width;
-  while (ccs_width > 0 && (ccs.bases[ccs_width - 1] == ' ' || ccs.bases[ccs_width - 1] == '\t' || ccs.bases[ccs_width - 1] == '\n')) --ccs_width;
-  const int nwin = (ccs_width + p->L - 1) / p->L;
-  p->win_start.clear();
-  int start = 0;
-  for (int w = 0; w < nwin; ++w) {
-    if (start > ccs_width) break;
-    const int s = start;
-    start += p->L;
-    bool any = false;
-    for (int i = s; i < std::min(s + p->L, width); ++i) any |= ccs.ccs_idx[i] >= 0;
-    if (!any) continue;                                         // n_examples_no_ccs_idx
-    p->win_start.push_back(s);
+  return 1;
+}
+
+void reader_main(dcb_prep* p) {
+  int64_t seq = 0;
+  for (;;) {
+    ZmwJob job;
+    const int rc = read_job(p, &job);
+    std::unique_lock<std::mutex> lk(p->mu);
+    if (rc <= 0) {
+      if (rc < 0) { p->reader_rc = rc; p->reader_error = g_prep_error; }
+      p->total = seq;
+      p->cv_job.notify_all();
+      p->cv_res.notify_all();
+      return;
+    }
+    p->cv_space.wait(lk, [&] { return p->stop || (int64_t)(p->jobs.size() + p->results.size()) < 4ll * p->n_threads + 4; });
+    if (p->stop) return;
+    p->jobs.emplace_back(seq++, std::move(job));
+    p->cv_job.notify_one();
   }
+}
+
+void worker_main(dcb_prep* p) {
+  for (;;) {
+    std::pair<int64_t, ZmwJob> item;
+    {
+      std::unique_lock<std::mutex> lk(p->mu);
+      p->cv_job.wait(lk, [&] { return p->stop || !p->jobs.empty() || p->total >= 0; });
+      if (p->stop) return;
+      if (p->jobs.empty()) return;                 // reader finished and nothing left
+      item = std::move(p->jobs.front());
+      p->jobs.pop_front();
+    }
+    ZmwState st;
+    process_zmw(p->cfg, &item.second, &st);
+    {
+      std::lock_guard<std::mutex> lk(p->mu);
+      p->results.emplace(item.first, std::move(st));
+    }
+    p->cv_res.notify_all();
+  }
+}
+
+void stop_threads(dcb_prep* p) {
+  if (!p->started) return;
+  {
+    std::lock_guard<std::mutex> lk(p->mu);
+    p->stop = true;
+  }
+  p->cv_job.notify_all(); p->cv_res.notify_all(); p->cv_space.notify_all();
+  if (p->reader.joinable()) p->reader.join();
+  for (auto& w : p->workers) if (w.joinable()) w.join();
+  p->started = false;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dcb_prep_last_error(void) { return g_prep_error.c_str(); }
+
+int dcb_prep_open(const char* subreads_to_ccs_bam, const char* ccs_bam, int32_t max_passes, int32_t max_length,
+                  int32_t use_ccs_bq, int32_t ins_trim, dcb_prep** out) {
+  if (!subreads_to_ccs_bam || !ccs_bam || !out || max_passes <= 0 || max_length <= 0) return pfail(DCB_ERR_INVALID, "dcb_prep_open: bad argument");
+  dcb_prep* p = new dcb_prep();
+  PrepCfg& c = p->cfg;
+  c.P = max_passes; c.L = max_length; c.bq = use_ccs_bq ? 1 : 0; c.ins_trim = ins_trim;
+  c.R = 4 * max_passes + 5 + c.bq;
+  c.pl = dcb::make_packed_layout(max_passes, max_length, c.bq);
+  int rc = p->sub.open(subreads_to_ccs_bam);
+  if (!rc) rc = p->ccs.open(ccs_bam);
+  if (rc) { delete p; return rc; }
+  *out = p;
+  return DCB_OK;
+}
+
+// Process ZMWs on `n_threads` worker threads (plus one thread that decodes the BAMs); results still come out of
+// dcb_prep_next_zmw in file order.  Call before the first dcb_prep_next_zmw; n_threads <= 0 keeps everything on the caller.
+int dcb_prep_set_threads(dcb_prep* p, int32_t n_threads) {
+  if (!p) return pfail(DCB_ERR_INVALID, "dcb_prep_set_threads: null handle");
+  if (p->started || p->next_seq) return pfail(DCB_ERR_STATE, "dcb_prep_set_threads: the stream has already started");
+  p->n_threads = n_threads > 0 ? std::min(n_threads, 256) : 0;
+  return DCB_OK;
+}
+
+void dcb_prep_close(dcb_prep* p) {
+  if (!p) return;
+  stop_threads(p);
+  delete p;
+}
+
+// Advances to the next ZMW that has mapped subreads.  Returns 1 and fills `info`, 0 at the end of the file, < 0 on error.
+int dcb_prep_next_zmw(dcb_prep* p, dcb_zmw_info* info) {
+  if (!p || !info) return pfail(DCB_ERR_INVALID, "dcb_prep_next_zmw: null argument");
+  if (p->n_threads > 0) {
+    if (!p->started) {
+      p->started = true;
+      p->reader = std::thread(reader_main, p);
+      for (int i = 0; i < p->n_threads; ++i) p->workers.emplace_back(worker_main, p);
+    }
+    std::unique_lock<std::mutex> lk(p->mu);
+    p->cv_res.wait(lk, [&] { return p->results.count(p->next_seq) || (p->total >= 0 && p->next_seq >= p->total); });
+    auto it = p->results.find(p->next_seq);
+    if (it == p->results.end()) {
+      if (p->reader_rc) { g_prep_error = p->reader_error; return p->reader_rc; }
+      return 0;
+    }
+    p->cur = std::move(it->second);
+    p->results.erase(it);
+    ++p->next_seq;
+    lk.unlock();
+    p->cv_space.notify_all();
+  } else {
+    ZmwJob job;
+    const int rc = read_job(p, &job);
+    if (rc <= 0) return rc;
+    p->cur = ZmwState();
+    process_zmw(p->cfg, &job, &p->cur);
+    ++p->next_seq;
+  }
+  if (p->cur.rc) { g_prep_error = p->cur.error; return p->cur.rc; }
+  const ZmwState& st = p->cur;
   memset(info, 0, sizeof *info);
-  info->n_windows = (int32_t)p->win_start.size();
-  info->n_subreads = (int32_t)group.size();
-  info->name = p->name.c_str();
-  info->has_ec = p->has_ec; info->ec = p->ec;
-  info->has_np = p->has_np; info->np_num_passes = p->np_passes;
-  info->has_rq = p->has_rq; info->rq = p->rq;
-  info->rg = p->has_rg ? p->rg.c_str() : nullptr;
-  info->ccs_length = (int32_t)c.seq.size();
-  info->spaced_width = width;
+  info->n_windows = (int32_t)st.win_start.size();
+  info->n_subreads = st.n_subreads;
+  info->name = st.name.c_str();
+  info->has_ec = st.has_ec; info->ec = st.ec;
+  info->has_np = st.has_np; info->np_num_passes = st.np_passes;
+  info->has_rq = st.has_rq; info->rq = st.rq;
+  info->rg = st.has_rg ? st.rg.c_str() : nullptr;
+  info->ccs_length = st.ccs_length;
+  info->spaced_width = (int32_t)st.reads.back().bases.size();
   return 1;
 }
 
@@ -554,19 +697,22 @@ int dcb_prep_next_zmw(dcb_prep* p, dcb_zmw_info* info) {
 int dcb_prep_get_windows(dcb_prep* p, float* rows, uint8_t* packed, int32_t* window_pos, uint8_t* overflow,
                          int16_t* ccs_bq, int32_t* num_passes) {
   if (!p) return pfail(DCB_ERR_INVALID, "dcb_prep_get_windows: null handle");
-  const int L = p->L, P = p->P, R = p->R;
-  const size_t nsub = p->reads.size() - 1;
+  const ZmwState& st = p->cur;
+  if (st.reads.empty()) return pfail(DCB_ERR_STATE, "dcb_prep_get_windows: no ZMW loaded");
+  const PrepCfg& cf = p->cfg;
+  const int L = cf.L, P = cf.P, R = cf.R;
+  const size_t nsub = st.reads.size() - 1;
   const int keep = (int)std::min<size_t>(P, nsub);
-  const Read& ccs = p->reads.back();
+  const Read& ccs = st.reads.back();
   const int width = (int)ccs.bases.size();
-  for (size_t w = 0; w < p->win_start.size(); ++w) {
-    const int s = p->win_start[w];
+  for (size_t w = 0; w < st.win_start.size(); ++w) {
+    const int s = st.win_start[w];
     const int n = std::min(L, width - s);                      // columns present; the rest is padding
     if (rows) {
       float* d = rows + w * (size_t)R * L;
       memset(d, 0, sizeof(float) * (size_t)R * L);
       for (int k = 0; k < keep; ++k) {
-        const Read& r = p->reads[k];
+        const Read& r = st.reads[k];
         for (int i = 0; i < n; ++i) {
           d[(size_t)k * L + i] = encode_base(r.bases[s + i]);
           d[(size_t)(P + k) * L + i] = (float)r.pw[s + i];
@@ -575,16 +721,16 @@ int dcb_prep_get_windows(dcb_prep* p, float* rows, uint8_t* packed, int32_t* win
         for (int i = 0; i < L; ++i) d[(size_t)(3 * P + k) * L + i] = (float)r.strand;   // repeated over the whole width
       }
       for (int i = 0; i < n; ++i) d[(size_t)4 * P * L + i] = encode_base(ccs.bases[s + i]);
-      if (p->bq)
+      if (cf.bq)
         for (int i = 0; i < L; ++i) d[(size_t)(4 * P + 1) * L + i] = (i < n && ccs.bq_any) ? (float)ccs.bq[s + i] : -1.f;
       for (int j = 0; j < 4; ++j)
-        for (int i = 0; i < L; ++i) d[(size_t)(R - 4 + j) * L + i] = p->reads[0].sn[j];
+        for (int i = 0; i < L; ++i) d[(size_t)(R - 4 + j) * L + i] = st.reads[0].sn[j];
     }
     if (packed) {
-      uint8_t* o = packed + w * (size_t)p->pl.stride;
-      memset(o, 0, p->pl.stride);
+      uint8_t* o = packed + w * (size_t)cf.pl.stride;
+      memset(o, 0, cf.pl.stride);
       for (int k = 0; k < keep; ++k) {
-        const Read& r = p->reads[k];
+        const Read& r = st.reads[k];
         for (int i = 0; i < L; ++i) {
           const int base = i < n ? (int)encode_base(r.bases[s + i]) : 0;
           o[k * L + i] = (uint8_t)(base | (r.strand << 3));
@@ -592,9 +738,9 @@ int dcb_prep_get_windows(dcb_prep* p, float* rows, uint8_t* packed, int32_t* win
         for (int i = 0; i < n; ++i) { o[(P + k) * L + i] = r.pw[s + i]; o[(2 * P + k) * L + i] = r.ip[s + i]; }
       }
       for (int i = 0; i < n; ++i) o[3 * P * L + i] = (uint8_t)encode_base(ccs.bases[s + i]);
-      if (p->bq)
+      if (cf.bq)
         for (int i = 0; i < L; ++i) o[(3 * P + 1) * L + i] = (uint8_t)(((i < n && ccs.bq_any) ? ccs.bq[s + i] : -1) + 1);
-      memcpy(o + p->pl.sn_off, p->reads[0].sn, 16);
+      memcpy(o + cf.pl.sn_off, st.reads[0].sn, 16);
     }
     if (window_pos) {
       int32_t mn = 0;

@@ -260,6 +260,56 @@ def inference_on_zmw_windows(feature_dicts_for_zmws: Iterable[Iterable[Dict[str,
                                           L, options.min_quality, options.min_length, outcome_counter)
 
 
+def inference_on_packed_zmws(zmws: List[Dict[str, Any]], model: engine_lib.B200Model, model_params: params_lib.Params,
+                             options: InferenceOptions, outcome_counter: stitch_utils.OutcomeCounter
+                             ) -> Tuple[bytes, np.ndarray, np.ndarray, List[str]]:
+  """`inference_on_zmw_windows` without any per-window Python object: `zmws` are the per-ZMW array bundles of
+  `preprocess.BamFeatureStream.next_zmw(want_rows=False, want_packed=True)` (packed rows, window_pos, ccs_bq, overflow,
+  name).  Skip decision, model (dcb_forward_packed), skipped-window fill, sort and stitch as there.
+
+  Returns (fastq bytes, rec_off, passed, names): read z (sorted-name order) has the record
+  fastq[rec_off[z]:rec_off[z + 1]] when passed[z].
+  """
+  from deepconsensus_b200 import stitch_gpu
+  L, P = int(model_params.max_length), int(model_params.max_passes)
+  zmws = [z for z in zmws if len(z["window_pos"])]
+  if not zmws:
+    return b"", np.zeros(1, np.int64), np.zeros(0, bool), []
+  packed = np.concatenate([z["packed"] for z in zmws])
+  pos = np.concatenate([z["window_pos"] for z in zmws]).astype(np.int64)
+  bq = np.concatenate([z["ccs_bq"] for z in zmws])
+  skip = np.concatenate([z["overflow"] for z in zmws]).astype(bool)
+  counts = np.array([len(z["window_pos"]) for z in zmws])
+  names_z = [z["name"] for z in zmws]
+  n = len(pos)
+  if options.skip_windows_above:
+    mask, _ = model.skip_mask(bq, options.skip_windows_above)
+    for i in np.nonzero(mask == 2)[0]:
+      mask[i] = utils.avg_phred(bq[i].astype(np.int64)) > options.skip_windows_above
+    skip |= mask.astype(bool)
+  # sort by (name, window_pos): ZMW order by name, windows inside a ZMW by position (quick_inference.py:721-728)
+  zorder = sorted(range(len(zmws)), key=lambda k: names_z[k])
+  starts = np.concatenate([[0], np.cumsum(counts)])
+  order = np.concatenate([starts[k] + np.argsort(pos[starts[k]:starts[k + 1]], kind="stable") for k in zorder])
+  dest = np.empty(n, np.int64)
+  dest[order] = np.arange(n)
+  all_b, all_q = np.empty((n, L), np.uint8), np.empty((n, L), np.uint8)
+  scored = np.nonzero(~skip)[0]
+  for b0 in range(0, len(scored), options.batch_size):          # batch_examples (quick_inference.py:304-338)
+    idx = scored[b0:b0 + options.batch_size]
+    out = model.forward_packed(packed[idx])
+    all_b[dest[idx]], all_q[dest[idx]] = out["bases"], out["quals"]
+  skipped = np.nonzero(skip)[0]
+  if len(skipped):
+    ccs_ids = packed[skipped][:, 3 * P * L:3 * P * L + L]        # the CCS plane of the packed rows
+    model.fill_skipped(ccs_ids, bq[skipped], dest[skipped].astype(np.int32), all_b, all_q,
+                       calibration=options.ccs_calibration_values)
+  names_sorted = [names_z[k] for k in zorder for _ in range(counts[k])]
+  fastq, rec_off, passed = stitch_gpu.stitch_batch_to_fastq_bytes(model, all_b, all_q, names_sorted, pos[order].tolist(), L,
+                                                                  options.min_quality, options.min_length, outcome_counter)
+  return fastq, rec_off, passed, [names_z[k] for k in zorder]
+
+
 def _as_str(x) -> str:
   return x.decode() if isinstance(x, (bytes, np.bytes_)) else str(x)
 

@@ -40,6 +40,7 @@ def _lib():
   if not getattr(lib, "_prep_bound", False):
     vp, i32 = ctypes.c_void_p, ctypes.c_int32
     lib.dcb_prep_open.argtypes = [ctypes.c_char_p, ctypes.c_char_p, i32, i32, i32, i32, ctypes.POINTER(vp)]
+    lib.dcb_prep_set_threads.argtypes = [vp, i32]
     lib.dcb_prep_next_zmw.argtypes = [vp, ctypes.POINTER(DcbZmwInfo)]
     lib.dcb_prep_get_windows.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.dcb_prep_ccs_header.argtypes = [vp]
@@ -59,7 +60,9 @@ class BamFeatureStream:
   iter_examples, pre_lib.py:1279-1384,625-697)."""
 
   def __init__(self, subreads_to_ccs: str, ccs_bam: str, max_passes: int, max_length: int, use_ccs_bq: bool = False,
-               ins_trim: int = 5):
+               ins_trim: int = 5, threads: int = 0):
+    """threads > 0: ZMWs are processed by that many native worker threads (plus one BAM-decoding thread) while the
+    caller consumes them; the order of the ZMWs is the file's either way (`--cpus` of `deepconsensus run`)."""
     self._lib = _lib()
     self._h = ctypes.c_void_p()
     self.max_passes, self.max_length, self.use_ccs_bq = int(max_passes), int(max_length), bool(use_ccs_bq)
@@ -67,6 +70,8 @@ class BamFeatureStream:
     rc = self._lib.dcb_prep_open(subreads_to_ccs.encode(), ccs_bam.encode(), self.max_passes, self.max_length,
                                  int(self.use_ccs_bq), int(ins_trim), ctypes.byref(self._h))
     if rc:
+      raise PrepError(self._lib.dcb_prep_last_error().decode())
+    if threads > 0 and self._lib.dcb_prep_set_threads(self._h, int(threads)):
       raise PrepError(self._lib.dcb_prep_last_error().decode())
     p = params_lib.Params(max_passes=self.max_passes, max_length=self.max_length, use_ccs_bq=self.use_ccs_bq,
                           PW_MAX=255, IP_MAX=255, SN_MAX=500, CCS_BQ_MAX=95, STRAND_MAX=2)

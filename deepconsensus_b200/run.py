@@ -30,7 +30,7 @@ from deepconsensus_b200 import weights as weights_lib
 def run(subreads_to_ccs: str, ccs_bam: str, checkpoint: str, output: str, batch_zmws: int = 100, batch_size: int = 1024,
         min_quality: int = 20, min_length: int = 0, skip_windows_above: int = 45, ins_trim: int = 5,
         max_base_quality: int = 93, dc_calibration: Optional[str] = None, ccs_calibration: str = "skip",
-        limit: int = 0, random_weights: Optional[int] = None, precision: str = "bf16", device: int = 0
+        limit: int = 0, random_weights: Optional[int] = None, precision: str = "bf16", device: int = 0, cpus: int = 0
         ) -> stitch_utils.OutcomeCounter:
   """One inference run; returns the OutcomeCounter (quick_inference.run's return value)."""
   params = params_lib.read_params_from_json(checkpoint)
@@ -48,37 +48,46 @@ def run(subreads_to_ccs: str, ccs_bam: str, checkpoint: str, output: str, batch_
     weights = weights_lib.init_weights(params, seed=random_weights)
   model, params = inference.initialize_model(checkpoint, params, options, weights=weights, device=device, precision=precision)
   counter = stitch_utils.OutcomeCounter()
-  stream = preprocess.stream_zmw_windows(subreads_to_ccs, ccs_bam, options.max_passes, options.max_length,
-                                         options.use_ccs_bq, ins_trim, limit)
+  stream = preprocess.BamFeatureStream(subreads_to_ccs, ccs_bam, options.max_passes, options.max_length,
+                                       options.use_ccs_bq, ins_trim, threads=cpus)
   as_bam = output.endswith(".bam")
-  if as_bam:
-    hdr = preprocess.BamFeatureStream(subreads_to_ccs, ccs_bam, options.max_passes, options.max_length)
-    writer: Any = preprocess.BamWriter(output, hdr.ccs_header)
-    hdr.close()
-  else:
-    writer = open(output, "w")
-  stats = dict(zmws=0, windows=0, seconds_model_and_stitch=0.0)
+  writer: Any = preprocess.BamWriter(output, stream.ccs_header) if as_bam else open(output, "wb")
+  stats = dict(zmws=0, windows=0, seconds_features=0.0, seconds_model_and_stitch=0.0)
   try:
-    while True:
-      batch = list(itertools.islice(stream, batch_zmws))
+    done = False
+    while not done:
+      t0 = time.time()
+      batch = []                      # per-ZMW array bundles: packed rows + metadata, no per-window objects
+      while len(batch) < batch_zmws:
+        z = stream.next_zmw(want_rows=False, want_packed=True)
+        if z is None or (limit and stats["zmws"] + len(batch) >= limit):
+          done = True
+          break
+        batch.append(z)
+      stats["seconds_features"] += time.time() - t0
       if not batch:
         break
       t0 = time.time()
-      tags = {z[0]["name"]: z[0] for z in batch if z}
-      records = inference.inference_on_zmw_windows(batch, model, params, options, counter)
+      fastq, rec_off, passed, names = inference.inference_on_packed_zmws(batch, model, params, options, counter)
       stats["seconds_model_and_stitch"] += time.time() - t0
       stats["zmws"] += len(batch)
-      stats["windows"] += sum(len(z) for z in batch)
-      for rec in records:
-        if rec is None:
-          continue
-        if as_bam:
-          t = tags[rec.split("\n", 1)[0][1:]]
-          writer.write_fastq_record(rec, t["ec"], t["np_num_passes"], t["rq"], t["rg"])
-        else:
-          writer.write(rec)
+      stats["windows"] += sum(len(z["window_pos"]) for z in batch)
+      tags = {z["name"]: z for z in batch}
+      if as_bam:
+        for k, name in enumerate(names):
+          if passed[k]:
+            t = tags[name]
+            writer.write_fastq_record(fastq[int(rec_off[k]):int(rec_off[k + 1])].decode("latin-1"), t["ec"],
+                                      t["np_num_passes"], t["rq"], t["rg"])
+      elif passed.all():
+        writer.write(fastq)           # every read passed: the device's byte buffer IS the FASTQ text of the batch
+      else:
+        for k in range(len(names)):
+          if passed[k]:
+            writer.write(fastq[int(rec_off[k]):int(rec_off[k + 1])])
   finally:
     writer.close()
+    stream.close()
     model.close()
   with open(output + ".inference.json", "w") as f:                               # save_counters (quick_inference.py:790-797)
     json.dump(dict(counter.__dict__, **stats), f, indent=True)
@@ -103,6 +112,7 @@ def main(argv: Optional[List[str]] = None) -> None:
   ap.add_argument("--limit", type=int, default=0)
   ap.add_argument("--random_weights", type=int, default=None)
   ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+  ap.add_argument("--cpus", type=int, default=0, help="native feature-construction threads (0: on the calling thread)")
   a = ap.parse_args(argv)
   c = run(**vars(a))
   print(json.dumps(c.__dict__))

@@ -227,6 +227,9 @@ typedef struct dcb_zmw_info {
 } dcb_zmw_info;
 int dcb_prep_open(const char* subreads_to_ccs_bam, const char* ccs_bam, int32_t max_passes, int32_t max_length,
                   int32_t use_ccs_bq, int32_t ins_trim, dcb_prep** out);
+/* Process ZMWs on n_threads worker threads plus one BAM-decoding thread (results still come out in file order); call
+ * before the first dcb_prep_next_zmw.  n_threads <= 0: everything on the calling thread. */
+int dcb_prep_set_threads(dcb_prep* p, int32_t n_threads);
 int dcb_prep_next_zmw(dcb_prep* p, dcb_zmw_info* info);   /* 1 = a ZMW is loaded, 0 = end of file, < 0 = error */
 /* The windows of the loaded ZMW; every output may be NULL.  rows float32 [n, R, L]; packed [n, dcb_packed_window_bytes];
  * window_pos / num_passes int32 [n]; overflow u8 [n]; ccs_bq int16 [n, L] (-1 at gaps and padding). */

@@ -160,3 +160,39 @@ def test_errors_are_reported(tmp_path, bam_dir):
   with pytest.raises(preprocess.PrepError):
     for _ in s:
       pass
+
+
+def test_threaded_stream_equals_the_serial_one(bam_dir):
+  """dcb_prep_set_threads: worker threads process ZMWs out of order, results come back in file order and identical."""
+  a = preprocess.BamFeatureStream(os.path.join(bam_dir, "subreads_to_ccs.bam"), os.path.join(bam_dir, "ccs.bam"), 20, 100, True, 5)
+  b = preprocess.BamFeatureStream(os.path.join(bam_dir, "subreads_to_ccs.bam"), os.path.join(bam_dir, "ccs.bam"), 20, 100, True, 5,
+                                  threads=4)
+  n = 0
+  while True:
+    za, zb = a.next_zmw(want_packed=True), b.next_zmw(want_packed=True)
+    assert (za is None) == (zb is None)
+    if za is None:
+      break
+    n += 1
+    assert za["name"] == zb["name"] and za["ec"] == zb["ec"] and za["rg"] == zb["rg"]
+    for k in ("rows", "packed", "window_pos", "ccs_bq", "num_passes", "overflow"):
+      np.testing.assert_array_equal(za[k], zb[k])
+  assert n == 10
+  a.close()
+  # closing a threaded stream that was only partly consumed must not hang
+  c = preprocess.BamFeatureStream(os.path.join(bam_dir, "subreads_to_ccs.bam"), os.path.join(bam_dir, "ccs.bam"), 20, 100, False, 5,
+                                  threads=3)
+  assert c.next_zmw() is not None
+  c.close()
+  b.close()
+  # errors surface in order from the threaded stream too
+  raw = open(os.path.join(bam_dir, "subreads_to_ccs.bam"), "rb").read()
+  import tempfile
+  with tempfile.TemporaryDirectory() as d:
+    path = os.path.join(d, "trunc.bam")
+    open(path, "wb").write(raw[:len(raw) // 3])
+    s = preprocess.BamFeatureStream(path, os.path.join(bam_dir, "ccs.bam"), 20, 100, threads=2)
+    with pytest.raises(preprocess.PrepError):
+      for _ in s:
+        pass
+    s.close()
