@@ -535,6 +535,9 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
   }
   for (int i = threadIdx.x; i < table_elems; i += blockDim.x) s_tab[i] = tables[i];
   for (int i = threadIdx.x; i < echunks * 8; i += blockDim.x) s_cols[i] = cols[i];
+  __shared__ EmbedRow s_meta[160];                 // per input row: clip / shift / vocabulary (R <= 160: max_passes <= 38)
+  const EmbedRow* __restrict__ rmeta = R <= 160 ? s_meta : rowmeta;
+  if (R <= 160) for (int i = threadIdx.x; i < R; i += blockDim.x) s_meta[i] = rowmeta[i];
   if (warp == 1) tmem_alloc(tmem_holder, C::kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -647,7 +650,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
           if (pr < PR) {
             // reference row this plane feeds (a base|strand byte feeds two)
             const int ru = pr < 3 * P ? pr : (pr == 3 * P ? 4 * P : 4 * P + 1);
-            const EmbedRow m = rowmeta[ru];
+            const EmbedRow m = rmeta[ru];
             const int hi = m.clip_hi > 0.f ? (int)m.clip_hi : 255;
             uint32_t ids[4], ids2[4];
             bool bad = false;
@@ -659,7 +662,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
               ids[q4] = (uint32_t)id;
               int sid = (b >> 3) & 3;
               if (pr < P) {
-                const int sv = rowmeta[3 * P + pr].vocab;
+                const int sv = rmeta[3 * P + pr].vocab;
                 if ((b >> 5) != 0 || sid >= sv) { bad = true; sid = sid >= sv ? sv - 1 : sid; }
               }
               ids2[q4] = (uint32_t)sid;
@@ -675,7 +678,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
           const int ri = bt >> 5, g = bt & 31, ru = R - 4 + ri;
           uint32_t id = 0;
           if (wvalid && g < L4) {
-            const EmbedRow m = rowmeta[ru];
+            const EmbedRow m = rmeta[ru];
             float v = __ldg(reinterpret_cast<const float*>(wbase + pl.sn_off) + ri);
             if (m.clip_hi > 0.f) v = fminf(fmaxf(v, 0.f), m.clip_hi);
             v += (float)m.shift;
@@ -709,7 +712,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
           const int item = bt + k * 256;
           const int ru = item >> 5, g = item & 31;
           if (ru < R) {
-            const EmbedRow m = rowmeta[ru];
+            const EmbedRow m = rmeta[ru];
             const float vals[4] = {cur.x, cur.y, cur.z, cur.w};
             uint32_t ids[4];
 #pragma unroll
@@ -751,7 +754,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
             if (ru < R) {
               int id = 0;
               if (tvalid) {
-                const EmbedRow m = rowmeta[ru];
+                const EmbedRow m = rmeta[ru];
                 float v = f[u];
                 if (m.clip_hi > 0.f) v = fminf(fmaxf(v, 0.f), m.clip_hi);  // format_rows (data_providers.py:151-162)
                 v += (float)m.shift;                                         // networks.py:495
@@ -2743,7 +2746,7 @@ cudaError_t kernels_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(qkv_attn_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QaCfg::kSmemBytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(embed_condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(embed_condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);   // + 2 KB static
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(qkv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Qkv2Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
@@ -2789,7 +2792,7 @@ bool launch_embed_condense(const float* rows, const uint8_t* packed, const Packe
                            const EmbedRow* rowmeta, const __nv_bfloat16* tables, int table_elems,
                            const __nv_bfloat16* wc_img, const RowEpi& epi, int* status, cudaStream_t st) {
   const size_t smem = embed_condense_smem_bytes(R, echunks, table_elems);
-  if (smem > 227 * 1024) return false;
+  if (smem > 225 * 1024) return false;
   if (packed && !embed_condense_reads_packed(L, Lw)) return false;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
   embed_condense_kernel<<<grid, EmbCfg::kThreads, smem, st>>>(rows, packed, pl, R, L, Lw, M, ntiles, echunks, cols, rowmeta,

@@ -650,7 +650,6 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
             uint32_t qa[kDHP / 16][4];
 #pragma unroll
             for (int ks = 0; ks < kDHP / 16; ++ks) ldmatrix_x4(qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], qaddr + ks * 32);
-            asm volatile("bar.sync 2, 256;" ::: "memory");   // every warp holds its q fragments: the q area may be overwritten
             float o[kDHP / 8][4];
 #pragma unroll
             for (int nt = 0; nt < kDHP / 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
@@ -790,7 +789,9 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
             l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
             // rows beyond the window (layout padding) contribute nothing to the out-projection
             const float inv0 = goff + r0 < L ? 1.f / l0 : 0.f, inv1 = goff + r1 < L ? 1.f / l1 : 0.f;
-            // att_h as a KC16 operand tile [18 chunks][128 rows][8] over the (consumed) q area
+            // att_h as a KC16 operand tile [18 chunks][128 rows][8] over the (consumed) q area: every warp must hold its q
+            // fragments before the first store (they were loaded at the start of the phase, so nobody waits here)
+            asm volatile("bar.sync 2, 256;" ::: "memory");
             __nv_bfloat16* obase = sQ + 2 * t;
 #pragma unroll
             for (int nt = 0; nt < kDHP / 8; ++nt) {

@@ -8,9 +8,13 @@ from deepconsensus_b200 import params as P, weights as W, synthetic, engine
 p = P.synthetic_params(20, 120); w = W.init_weights(p, seed=1)
 B = 1024
 rows = synthetic.make_rows(p, B, seed=7)
-m = engine.B200Model(p, w, max_batch=B)
-for _ in range(3): m.forward(rows)
-lib = engine.load_library()
+lib = engine._load(os.path.join(os.path.dirname(engine.library_path()), "libdcb200_trace.so"))
+m = engine.B200Model(p, w, max_batch=B, library=lib)
+packed = "--packed" in sys.argv
+pk = m.pack_rows(rows)
+for _ in range(3):
+  m.forward_packed(pk) if packed else m.forward(rows)
+print("packed rows" if packed else "float32 rows")
 buf = (ctypes.c_uint64 * (256 * 16))()
 lib.dcb_debug_trace(buf, 256 * 16)
 a = np.array(buf[:], dtype=np.float64).reshape(256, 16)[1:148:2]   # odd blocks: the stack kernel's issuer writes even blocks only
