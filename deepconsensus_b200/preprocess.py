@@ -73,10 +73,7 @@ class BamFeatureStream:
       raise PrepError(self._lib.dcb_prep_last_error().decode())
     if threads > 0 and self._lib.dcb_prep_set_threads(self._h, int(threads)):
       raise PrepError(self._lib.dcb_prep_last_error().decode())
-    p = params_lib.Params(max_passes=self.max_passes, max_length=self.max_length, use_ccs_bq=self.use_ccs_bq,
-                          PW_MAX=255, IP_MAX=255, SN_MAX=500, CCS_BQ_MAX=95, STRAND_MAX=2)
-    self._stride = ((3 * self.max_passes + 1 + int(self.use_ccs_bq)) * self.max_length + 15) // 16 * 16 + 16
-    del p
+    self._stride = ((3 * self.max_passes + 1 + int(self.use_ccs_bq)) * self.max_length + 15) // 16 * 16 + 16   # PackedLayout
 
   @property
   def ccs_header(self) -> str:
