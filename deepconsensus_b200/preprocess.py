@@ -70,9 +70,9 @@ class BamFeatureStream:
     rc = self._lib.dcb_prep_open(subreads_to_ccs.encode(), ccs_bam.encode(), self.max_passes, self.max_length,
                                  int(self.use_ccs_bq), int(ins_trim), ctypes.byref(self._h))
     if rc:
-      raise PrepError(self._lib.dcb_prep_last_error().decode())
+      raise PrepError(self._lib.dcb_prep_last_error().decode("utf-8", "replace"))
     if threads > 0 and self._lib.dcb_prep_set_threads(self._h, int(threads)):
-      raise PrepError(self._lib.dcb_prep_last_error().decode())
+      raise PrepError(self._lib.dcb_prep_last_error().decode("utf-8", "replace"))
     self._stride = ((3 * self.max_passes + 1 + int(self.use_ccs_bq)) * self.max_length + 15) // 16 * 16 + 16   # PackedLayout
 
   @property
@@ -100,15 +100,15 @@ class BamFeatureStream:
     info = DcbZmwInfo()
     rc = self._lib.dcb_prep_next_zmw(self._h, ctypes.byref(info))
     if rc < 0:
-      raise PrepError(self._lib.dcb_prep_last_error().decode())
+      raise PrepError(self._lib.dcb_prep_last_error().decode("utf-8", "replace"))
     if rc == 0:
       return None
     n, L, R = int(info.n_windows), self.max_length, self.total_rows
-    out: Dict[str, Any] = dict(name=info.name.decode(), n_subreads=int(info.n_subreads),
+    out: Dict[str, Any] = dict(name=info.name.decode("utf-8", "replace"), n_subreads=int(info.n_subreads),
                                ec=float(info.ec) if info.has_ec else None,
                                np_num_passes=int(info.np_num_passes) if info.has_np else None,
                                rq=float(info.rq) if info.has_rq else None,
-                               rg=info.rg.decode() if info.rg else None,
+                               rg=info.rg.decode("utf-8", "replace") if info.rg else None,
                                window_pos=np.zeros(n, np.int32), overflow=np.zeros(n, np.uint8),
                                num_passes=np.zeros(n, np.int32), ccs_bq=np.zeros((n, L), np.int16))
     if want_rows:
@@ -120,7 +120,7 @@ class BamFeatureStream:
                                         vp(out["packed"]) if want_packed else None, vp(out["window_pos"]),
                                         vp(out["overflow"]), vp(out["ccs_bq"]), vp(out["num_passes"]))
     if rc:
-      raise PrepError(self._lib.dcb_prep_last_error().decode())
+      raise PrepError(self._lib.dcb_prep_last_error().decode("utf-8", "replace"))
     return out
 
   def __iter__(self):
@@ -157,7 +157,7 @@ class BamWriter:
     self._lib = _lib()
     self._h = ctypes.c_void_p()
     if self._lib.dcb_bamw_open(path.encode(), header_text.encode("latin-1"), ctypes.byref(self._h)):
-      raise PrepError(self._lib.dcb_prep_last_error().decode())
+      raise PrepError(self._lib.dcb_prep_last_error().decode("utf-8", "replace"))
 
   def write_fastq_record(self, fastq_string: str, ec: Optional[float], np_num_passes: Optional[int], rq: Optional[float],
                          rg: Optional[str]) -> None:
@@ -166,11 +166,11 @@ class BamWriter:
     rc = self._lib.dcb_bamw_write(self._h, name[1:].encode(), s, q, len(s), int(ec is not None), float(ec or 0.0),
                                   int(np_num_passes or 0), float(rq or 0.0), rg.encode() if rg is not None else None)
     if rc:
-      raise PrepError(self._lib.dcb_prep_last_error().decode())
+      raise PrepError(self._lib.dcb_prep_last_error().decode("utf-8", "replace"))
 
   def close(self) -> None:
     if self._h and self._h.value:
       rc = self._lib.dcb_bamw_close(self._h)
       self._h = ctypes.c_void_p()
       if rc:
-        raise PrepError(self._lib.dcb_prep_last_error().decode())
+        raise PrepError(self._lib.dcb_prep_last_error().decode("utf-8", "replace"))

@@ -196,3 +196,51 @@ def test_threaded_stream_equals_the_serial_one(bam_dir):
       for _ in s:
         pass
     s.close()
+
+
+def test_corrupted_bams_fail_cleanly(tmp_path, bam_dir):
+  """The BAM decoder parses untrusted bytes: random corruption of the record stream (re-compressed as valid BGZF) must
+  end in PrepError or in a normal result, never in a crash or a hang (serial and threaded streams)."""
+  import gzip, random, struct, zlib
+  raw = open(os.path.join(bam_dir, "subreads_to_ccs.bam"), "rb").read()
+  plain = b"".join(gzip.decompress(m) for m in _members(raw))
+  pos = 4
+  pos += 4 + struct.unpack_from("<i", plain, pos)[0]
+  n_ref = struct.unpack_from("<i", plain, pos)[0]
+  pos += 4
+  for _ in range(n_ref):
+    pos += 4 + struct.unpack_from("<i", plain, pos)[0] + 4
+  while pos < 300000:                                   # a record boundary ~300 KB in (two ZMWs)
+    pos += 4 + struct.unpack_from("<i", plain, pos)[0]
+  base = plain[:pos]
+
+  def bgzf(data):
+    out = bytearray()
+    for i in range(0, len(data), 0xff00):
+      blk = data[i:i + 0xff00]
+      c = zlib.compressobj(1, zlib.DEFLATED, -15)
+      comp = c.compress(blk) + c.flush()
+      bs = len(comp) + 25
+      out += bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, bs & 255, bs >> 8]) + comp
+      out += struct.pack("<II", zlib.crc32(blk), len(blk))
+    return bytes(out) + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+  rng = random.Random(7)
+  ok = err = 0
+  for it in range(40):
+    b = bytearray(base)
+    for _ in range(rng.choice([1, 1, 2, 5, 20])):
+      b[rng.randrange(4, len(b))] = rng.randrange(256)
+    if rng.random() < 0.2:
+      b = b[:rng.randrange(100, len(b))]
+    path = str(tmp_path / "f.bam")
+    open(path, "wb").write(bgzf(bytes(b)))
+    try:
+      s = preprocess.BamFeatureStream(path, os.path.join(bam_dir, "ccs.bam"), 20, 100, True, 5, threads=rng.choice([0, 2]))
+      for z in s:
+        assert z["rows"].shape[1:] == (86, 100)
+      s.close()
+      ok += 1
+    except preprocess.PrepError:
+      err += 1
+  assert ok + err == 40 and err >= 5 and ok >= 5
