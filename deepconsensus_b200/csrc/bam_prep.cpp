@@ -204,6 +204,7 @@ struct BamReader {
     const int rc = z.read(&bs, 4);
     if (rc == 0) return 0;
     if (rc < 0 || bs < 32) return pfail(DCB_ERR_INVALID, "truncated BAM record");
+    if (bs > (64 << 20)) return pfail(DCB_ERR_INVALID, "implausible BAM record size %d", bs);
     std::vector<uint8_t> b(bs);
     if (z.read(b.data(), bs) != 1) return pfail(DCB_ERR_INVALID, "truncated BAM record");
     int32_t l_seq;
@@ -214,6 +215,7 @@ struct BamReader {
     memcpy(&n_cig, &b[12], 2);
     memcpy(&r->flag, &b[14], 2);
     memcpy(&l_seq, &b[16], 4);
+    if (l_seq < 0) return pfail(DCB_ERR_INVALID, "corrupt BAM record");
     size_t o = 32;
     if (o + l_name + 4ull * n_cig + (l_seq + 1) / 2 + l_seq > (size_t)bs) return pfail(DCB_ERR_INVALID, "corrupt BAM record");
     r->qname.assign(reinterpret_cast<const char*>(&b[o]), l_name ? l_name - 1 : 0);
@@ -309,6 +311,13 @@ int expand_clip_indent(BamRecord* rec, int ins_trim, Read* out) {
   std::vector<double> pw, ip;
   if (rec->find("pw", &t) && t.type == 'B') { pw.resize(t.count); for (size_t i = 0; i < t.count; ++i) pw[i] = BamRecord::element(t, i); }
   if (rec->find("ip", &t) && t.type == 'B') { ip.resize(t.count); for (size_t i = 0; i < t.count; ++i) ip[i] = BamRecord::element(t, i); }
+  {
+    // sanity before anything is sized from the record: alignments to a CCS read span at most a few hundred kilobases
+    uint64_t cols = 0;
+    for (uint32_t c : rec->cigar) cols += c >> 4;
+    if (cols > (1u << 24) || rec->pos < 0 || rec->pos > (1 << 24))
+      return pfail(DCB_ERR_INVALID, "%s: implausible alignment (cigar / position)", rec->qname.c_str());
+  }
   trim_insertions(rec, &pw, &ip, ins_trim);
   std::vector<int32_t> read_idx, ccs_idx;
   aligned_pairs(rec->cigar, rec->pos, &read_idx, &ccs_idx);
