@@ -333,7 +333,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
                       const int kstep = st * C::kWoStageK + kk;
 #pragma unroll
                       for (int j = 0; j < 2; ++j)
-                        umma_bf16_ss_pair_warp(tmem_base + C::kTmemY + j * kNC, adesc_s + kstep * 256,
+                        umma_bf16_ss_pair_warp(tmem_base + C::kTmemY + j * kNC, adesc_s + h * (C::kMatBytes >> 4) + kstep * 256,
                                                bdesc_144 + (sb + kk * (C::kWoStepBytes >> 4) + j * (kNC / 2)), idesc_y, true);
                     }
                     release(sa);
@@ -609,7 +609,17 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
 
         for (int h = 0; h < kHeads; ++h) {
           TRACE_T0();
-          if (h > 0) { SW(s_free, k_sfree & 1, 1013); ++k_sfree; }   // att_{h-1} consumed by its out-projection
+          // Staging areas rotate with the head: matrix m of head h lives in area (m + h) % 3, att_h over its q area.
+          // Head 1's q and k therefore go over head 0's k and v (free once every worker of this CTA has finished the
+          // attention of head 0) and only its v goes over att_0 (free once the out-projection of head 0 has read it): the
+          // drain of the q block of head 1 overlaps the out-projection UMMAs instead of waiting for them.
+          __nv_bfloat16* const qb = sQ + (size_t)((0 + h) % 3) * kTileM * kS;
+          __nv_bfloat16* const kb = sQ + (size_t)((1 + h) % 3) * kTileM * kS;
+          __nv_bfloat16* const vb = sQ + (size_t)((2 + h) % 3) * kTileM * kS;
+          if (h > 0) {
+            if (kWide) { SW(s_free, k_sfree & 1, 1013); ++k_sfree; }   // the partner's boundary warp may still read my k / v rows
+            else asm volatile("bar.sync 1, 256;" ::: "memory");
+          }
           TRACE_ADD(w_wait);
           // ---- q, k, v blocks: TMEM -> bf16 -> padded shared-memory rows
           for (int m = 0; m < 3; ++m) {
@@ -623,7 +633,8 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
             tmem_ld_wait();
             tc_fence_before();
             arrive_leader(acc_free);
-            __nv_bfloat16* dst = sQ + (size_t)m * kTileM * kS + (size_t)r * kS;
+            if (!kWide && h > 0 && m == 2) { SW(s_free, k_sfree & 1, 1013); ++k_sfree; }   // att_{h-1} consumed by its out-projection
+            __nv_bfloat16* dst = sQ + (size_t)((m + h) % 3) * kTileM * kS + (size_t)r * kS;
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
               if (j < nb) {
@@ -646,7 +657,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
             const int i0 = ew * 16;
             const int r0 = i0 + g, r1 = r0 + 8;
             // A fragments of the 16 query rows: one ldmatrix.x4 per 16 dims (matrices: rows 0-7 | 8-15 x dims 0-7 | 8-15)
-            const uint32_t qaddr = smem_u32(sQ + (size_t)(i0 + (lane & 7) + ((lane >> 3) & 1) * 8) * kS + (lane >> 4) * 8);
+            const uint32_t qaddr = smem_u32(qb + (size_t)(i0 + (lane & 7) + ((lane >> 3) & 1) * 8) * kS + (lane >> 4) * 8);
             uint32_t qa[kDHP / 16][4];
 #pragma unroll
             for (int ks = 0; ks < kDHP / 16; ++ks) ldmatrix_x4(qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], qaddr + ks * 32);
@@ -681,7 +692,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
                 if (tile_remote(kt)) {
                   // the partner's key rows: B fragments by 32-bit remote loads (b0 = K[key g][dims 2t, 2t+1], b1 = dims + 8),
                   // all issued before the first use
-                  const uint32_t kp = peer_smem_addr(sK + (size_t)(peer_row(kt) + g) * kS + 2 * t, rank ^ 1u);
+                  const uint32_t kp = peer_smem_addr(kb + (size_t)(peer_row(kt) + g) * kS + 2 * t, rank ^ 1u);
                   uint32_t kf[kDHP / 16][4];
 #pragma unroll
                   for (int ks = 0; ks < kDHP / 16; ++ks) {
@@ -697,7 +708,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
                   }
                 } else {
                   // B fragments of 16 keys: one ldmatrix.x4 per 16 dims (keys 0-7 x dims 0-7 | 8-15, keys 8-15 x dims 0-7 | 8-15)
-                  const uint32_t kaddr = smem_u32(sK + (size_t)(lj0 + kt * 16 + (lane & 7) + (lane >> 4) * 8) * kS + ((lane >> 3) & 1) * 8);
+                  const uint32_t kaddr = smem_u32(kb + (size_t)(lj0 + kt * 16 + (lane & 7) + (lane >> 4) * 8) * kS + ((lane >> 3) & 1) * 8);
 #pragma unroll
                   for (int ks = 0; ks < kDHP / 16; ++ks) {
                     uint32_t a0, a1, c0, c1;
@@ -754,7 +765,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
                 if (tile_remote(kt)) {
                   // the partner's value rows: b0 = {V[key 2t][dim g], V[key 2t+1][dim g]}, b1 = keys + 8 -- 16-bit remote
                   // loads, six dim blocks (24 loads) in flight at a time
-                  const uint32_t vp = peer_smem_addr(sV + (size_t)(peer_row(kt) + 2 * t) * kS + g, rank ^ 1u);
+                  const uint32_t vp = peer_smem_addr(vb + (size_t)(peer_row(kt) + 2 * t) * kS + g, rank ^ 1u);
 #pragma unroll
                   for (int nb = 0; nb < kDHP / 8; nb += 6) {
                     uint32_t vf[6][4];
@@ -772,7 +783,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
                   }
                 } else {
                   const int vrow = lj0 + kt * 16 + (lane & 15);
-                  const uint32_t vbase = smem_u32(sV + (size_t)vrow * kS);
+                  const uint32_t vbase = smem_u32(vb + (size_t)vrow * kS);
 #pragma unroll
                   for (int nt = 0; nt < kDHP / 8; ++nt) {
                     uint32_t b0, b1;
@@ -792,7 +803,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
             // att_h as a KC16 operand tile [18 chunks][128 rows][8] over the (consumed) q area: every warp must hold its q
             // fragments before the first store (they were loaded at the start of the phase, so nobody waits here)
             asm volatile("bar.sync 2, 256;" ::: "memory");
-            __nv_bfloat16* obase = sQ + 2 * t;
+            __nv_bfloat16* obase = qb + 2 * t;
 #pragma unroll
             for (int nt = 0; nt < kDHP / 8; ++nt) {
               *reinterpret_cast<uint32_t*>(obase + (size_t)nt * kChunkElems + r0 * 8) = pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
