@@ -99,6 +99,7 @@ struct dcb_engine {
   float* d_pe_img = nullptr;   // same table in residual-image order (window-aligned layout only)
   std::vector<LayerDev> layers;
   float *d_fln_g = nullptr, *d_fln_b = nullptr, *d_wfc = nullptr, *d_bfc = nullptr;
+  float *d_head_gw8 = nullptr, *d_head_ab = nullptr;   // head_kernel: gamma * Wfc (padded to 8) and the A / B sums
   // workspace
   __nv_bfloat16* d_embqkv = nullptr;
   float* d_x = nullptr;
@@ -629,6 +630,18 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
     if ((rc = upload(e, &e->d_fln_b, pad288(b)))) return rc;
     if ((rc = upload(e, &e->d_wfc, std::vector<float>(w, w + kD * kVocab)))) return rc;
     if ((rc = upload(e, &e->d_bfc, std::vector<float>(bb, bb + kVocab)))) return rc;
+    // head_kernel folds the final LayerNorm into the fc1 sums (one pass over the row): logits_j = rstd * (sum_c y_c g_c W_cj
+    // - mean_y * A_j) + B_j + bfc_j.  The products are formed here once, in float32 in the same order the kernel used to.
+    std::vector<float> gw8((size_t)kD * 8, 0.f), ab(16, 0.f);
+    for (int cc = 0; cc < kD; ++cc)
+      for (int j = 0; j < kVocab; ++j) gw8[(size_t)cc * 8 + j] = g[cc] * w[cc * kVocab + j];
+    for (int j = 0; j < kVocab; ++j) {
+      float a = 0.f, bsum = 0.f;
+      for (int cc = 0; cc < kD; ++cc) { a += g[cc] * w[cc * kVocab + j]; bsum += b[cc] * w[cc * kVocab + j]; }
+      ab[j] = a; ab[8 + j] = bsum;
+    }
+    if ((rc = upload(e, &e->d_head_gw8, gw8))) return rc;
+    if ((rc = upload(e, &e->d_head_ab, ab))) return rc;
   }
   // ---- strict-fp32 path: every variable once more as float32, in the reference's own shapes
   {
@@ -848,6 +861,7 @@ static int submit_impl(dcb_engine* e, const float* rows, const uint8_t* packed, 
   auto make_head_at = [&](int w0) {
     HeadParams hp{};
     hp.x = e->d_x; hp.ln_g = e->d_fln_g; hp.ln_b = e->d_fln_b; hp.wfc = e->d_wfc; hp.bfc = e->d_bfc;
+    hp.gw8 = e->d_head_gw8; hp.ab = e->d_head_ab;
     const size_t t0 = (size_t)w0 * L;
     hp.bases = (out_dev ? bases_out : sl.d_bases) + t0;
     hp.quals = (out_dev ? quals_out : sl.d_quals) + t0;

@@ -2642,18 +2642,11 @@ head_kernel(HeadParams p) {
   //          = rstd * (sum_c y_c * (g_c W_cj) - mean_y * A_j) + B_j + bfc_j,   y = x - shift, A_j = sum_c g_c W_cj,
   //            B_j = sum_c b_c W_cj
   // so ONE pass over the row accumulates sum y, sum y^2 and the five sums y * gW_j (the residual image is read once).
-  __shared__ float sGW[kD * kVocab];
+  __shared__ __align__(16) float sGW[kD * 8];
   __shared__ float sA[kVocab], sBj[kVocab];
-  for (int i = threadIdx.x; i < kD * kVocab; i += blockDim.x) sGW[i] = p.ln_g[i / kVocab] * p.wfc[i];
-  if (threadIdx.x < kVocab) {
-    float a = 0.f, bsum = 0.f;
-    for (int c = 0; c < kD; ++c) {
-      a += p.ln_g[c] * p.wfc[c * kVocab + threadIdx.x];
-      bsum += p.ln_b[c] * p.wfc[c * kVocab + threadIdx.x];
-    }
-    sA[threadIdx.x] = a;
-    sBj[threadIdx.x] = bsum;
-  }
+  for (int i = threadIdx.x; i < kD * 2; i += blockDim.x)
+    reinterpret_cast<float4*>(sGW)[i] = __ldg(reinterpret_cast<const float4*>(p.gw8) + i);
+  if (threadIdx.x < kVocab) { sA[threadIdx.x] = p.ab[threadIdx.x]; sBj[threadIdx.x] = p.ab[8 + threadIdx.x]; }
   __syncthreads();
   const int tile = blockIdx.x, r = threadIdx.x;
   const int tok = tile * kTileM + r;
@@ -2683,8 +2676,10 @@ head_kernel(HeadParams p) {
         const int col = (c0 + u) * 4 + i;
         s1 += ys[i];
         s2 = fmaf(ys[i], ys[i], s2);
-#pragma unroll
-        for (int j = 0; j < kVocab; ++j) t[j] = fmaf(ys[i], sGW[col * kVocab + j], t[j]);
+        const float4 w0 = *reinterpret_cast<const float4*>(&sGW[col * 8]);       // two 16-byte broadcast reads per element
+        const float w4 = sGW[col * 8 + 4];
+        t[0] = fmaf(ys[i], w0.x, t[0]); t[1] = fmaf(ys[i], w0.y, t[1]); t[2] = fmaf(ys[i], w0.z, t[2]);
+        t[3] = fmaf(ys[i], w0.w, t[3]); t[4] = fmaf(ys[i], w4, t[4]);
       }
     }
   }
