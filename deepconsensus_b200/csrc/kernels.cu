@@ -533,8 +533,18 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
     mbar_init(acc_empty, 128);
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < table_elems; i += blockDim.x) s_tab[i] = tables[i];
-  for (int i = threadIdx.x; i < echunks * 8; i += blockDim.x) s_cols[i] = cols[i];
+  // tables (the blob is padded to 8 elements per table, the device allocation is 256-byte aligned) and column
+  // descriptors with wide copies
+  {
+    const int nvec = table_elems / 8;
+    const uint4* tv = reinterpret_cast<const uint4*>(tables);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) reinterpret_cast<uint4*>(s_tab)[i] = __ldg(tv + i);
+    for (int i = nvec * 8 + threadIdx.x; i < table_elems; i += blockDim.x) s_tab[i] = tables[i];
+    static_assert(sizeof(EmbedCol) % 4 == 0, "EmbedCol is copied word by word");
+    const uint32_t* cv = reinterpret_cast<const uint32_t*>(cols);
+    const int nw = echunks * 8 * (int)(sizeof(EmbedCol) / 4);
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) reinterpret_cast<uint32_t*>(s_cols)[i] = __ldg(cv + i);
+  }
   __shared__ EmbedRow s_meta[160];                 // per input row: clip / shift / vocabulary (R <= 160: max_passes <= 38)
   const EmbedRow* __restrict__ rmeta = R <= 160 ? s_meta : rowmeta;
   if (R <= 160) for (int i = threadIdx.x; i < R; i += blockDim.x) s_meta[i] = rowmeta[i];
