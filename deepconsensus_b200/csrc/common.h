@@ -119,12 +119,15 @@ struct StackParams {
   const uint8_t* wq3[kMaxLayers];    // per layer: [head][rank][q|k|v] x [36 k-chunks][72 rows][8] bf16
   const uint8_t* wo2[kMaxLayers];    // per layer: [rank][36][144][8] (ReZero alpha folded in)
   const uint8_t* wffn2[kMaxLayers];  // per layer: [chunk][rank]{[36][64][8], [16][144][8]}
-  const float* b1[kMaxLayers];       // [ff]
   const float* b2[kMaxLayers];       // [288] (alpha folded in)
-  const float* ln_g0[kMaxLayers];    // pre-norm of the attention sub-layer, or null (ReZero)
-  const float* ln_b0[kMaxLayers];
-  const float* ln_g1[kMaxLayers];    // pre-norm of the FFN sub-layer, or null
-  const float* ln_b1[kMaxLayers];
+  // The eight padding rows 280..287 of the q/k/v and W1 images carry rank-1 terms as bf16 hi / lo pairs, against which the
+  // row pass writes operand columns 280..287 = (-dmean) hi, hi, lo, lo, (1 / rstd) hi, hi, lo, lo:
+  //   rows 280..283 = cs_hi, cs_lo, cs_hi, cs_lo    rows 284..287 = bw_hi, bw_lo, bw_hi, bw_lo
+  // ReZero models: dmean = 0, rstd = 1, cs = 0 and bw = b1 for W1 (0 for q/k/v) -- the GEMM adds the bias, the hidden
+  // epilogue loads nothing.  Pre-LayerNorm models (deferred_ln = 1): the normalisation is DEFERRED -- the operand tile is
+  // bf16(x - shift), gamma is folded into rows 0..279, cs = column sums of the rounded folded weights, bw = beta^T W
+  // (+ b1 for W1), dmean = mean - shift; the accumulator is (LN(x) W + bw) / rstd and its reader multiplies by rstd.
+  int deferred_ln;
   int num_layers;
   int ff;
 };

@@ -31,6 +31,7 @@ struct LayerDev {
   __nv_bfloat16* wo = nullptr;    // [36][288][8]
   uint8_t* wffn = nullptr;        // per ff chunk: [36][128][8] then [16][288][8]
   uint8_t* wffn2 = nullptr;       // CTA-pair image: per (chunk, rank): [36][64][8] then [16][144][8]
+  uint8_t* wffn2s = nullptr;      // the stack kernel's copy: b1 / deferred-LayerNorm terms in the padding rows (common.h, StackParams)
   uint8_t* wo2 = nullptr;         // CTA-pair out-proj image: per rank [36][144][8]
   float* b1 = nullptr;            // [ff]
   float* b2 = nullptr;            // [288] (gain folded)
@@ -466,6 +467,26 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
     snprintf(pre, sizeof pre, "model/encoder_stack/layers/%d", n_);
     const std::string P0 = std::string(pre) + "/0", P1 = std::string(pre) + "/1";
     float alpha0 = 1.f, alpha1 = 1.f;
+    const float *gam[2] = {nullptr, nullptr}, *bet[2] = {nullptr, nullptr};   // pre-LN gamma / beta of the two sub-layers
+    // Padding rows 280..287 of a stack-kernel [kDP/8][n][8] image (common.h, StackParams).  beta != null: deferred
+    // LayerNorm, rows 0..279 hold bf16(gamma * W), wcol(k, nn) = the unfolded weight, extra(nn) = a bias that joins
+    // beta^T W.  beta == null (ReZero): only the bias rows.
+    auto deferred_rows = [&](std::vector<__nv_bfloat16>& part, int n, const float* beta,
+                             const std::function<float(int, int)>& wcol, const std::function<float(int)>& extra) {
+      for (int nn = 0; nn < n; ++nn) {
+        float cs = 0.f, bw = extra(nn);
+        for (int k = 0; beta && k < kD; ++k) {
+          cs += __bfloat162float(part[((size_t)(k / 8) * n + nn) * 8 + k % 8]);
+          bw += beta[k] * wcol(k, nn);
+        }
+        const __nv_bfloat16 ch = __float2bfloat16(cs), cl = __float2bfloat16(cs - __bfloat162float(ch));
+        const __nv_bfloat16 bh = __float2bfloat16(bw), bl = __float2bfloat16(bw - __bfloat162float(bh));
+        __nv_bfloat16* row = &part[((size_t)(kD / 8) * n + nn) * 8];
+        row[0] = ch; row[1] = cl; row[2] = ch; row[3] = cl;
+        row[4] = bh; row[5] = bl; row[6] = bh; row[7] = bl;
+      }
+    };
+    static_assert(kDP - kD == 8 && kD % 8 == 0, "deferred LayerNorm uses the eight padding rows of the operand tile");
     if (c.rezero) {
       const float* a0 = tm.get(P0 + "/alpha", std::initializer_list<int64_t>{}, &rc); if (rc) return rc;
       const float* a1 = tm.get(P1 + "/alpha", std::initializer_list<int64_t>{}, &rc); if (rc) return rc;
@@ -475,6 +496,7 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
         const std::string P = s ? P1 : P0;
         const float* g = tm.get(P + "/layer_norm/gamma", {kD}, &rc); if (rc) return rc;
         const float* b = tm.get(P + "/layer_norm/beta", {kD}, &rc); if (rc) return rc;
+        gam[s] = g; bet[s] = b;
         if ((rc = upload(e, &ld.ln_g[s], pad288(g)))) return rc;
         if ((rc = upload(e, &ld.ln_b[s], pad288(b)))) return rc;
       }
@@ -539,13 +561,17 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
       for (int h = 0; h < kHeads; ++h)
         for (int rk = 0; rk < 2; ++rk)
           for (int m = 0; m < 3; ++m) {
-            auto part = pack_b(kDP, kDHP / 2, [&](int k, int nn) {
+            auto wval = [&](int k, int nn) {
               const int dd = rk * (kDHP / 2) + nn;
               if (k >= kD || dd >= kDH) return 0.f;
               const float* w = m == 0 ? wq : (m == 1 ? wk : wv);
               const float v = w[((size_t)k * kHeads + h) * kDH + dd];
               return m == 0 ? v * qscale : v;
+            };
+            auto part = pack_b(kDP, kDHP / 2, [&](int k, int nn) {
+              return (gam[0] && k < kD) ? gam[0][k] * wval(k, nn) : wval(k, nn);     // pre-LN: gamma_0 folded into the rows
             });
+            if (gam[0]) deferred_rows(part, kDHP / 2, bet[0], wval, [](int) { return 0.f; });
             img3.insert(img3.end(), part.begin(), part.end());
           }
       __nv_bfloat16* dptr3 = nullptr;
@@ -616,6 +642,27 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
       __nv_bfloat16* dptr = nullptr;
       if ((rc = upload(e, &dptr, img))) return rc;
       ld.wffn2 = reinterpret_cast<uint8_t*>(dptr);
+      {
+        // the stack kernel's copy: b1 in the padding rows of W1; pre-LN models: gamma_1 folded in, deferred-LayerNorm rows
+        std::vector<__nv_bfloat16> imgs;
+        imgs.reserve(img.size());
+        for (int ch = 0; ch < ff / kFFChunk; ++ch)
+          for (int rk = 0; rk < 2; ++rk) {
+            const int c0 = ch * kFFChunk + rk * (kFFChunk / 2);
+            auto w1col = [&](int k, int nn) { return k < kD ? w1[(size_t)k * ff + c0 + nn] : 0.f; };
+            auto p1 = pack_b(kDP, kFFChunk / 2, [&](int k, int nn) { return (gam[1] && k < kD) ? gam[1][k] * w1col(k, nn) : w1col(k, nn); });
+            deferred_rows(p1, kFFChunk / 2, bet[1], w1col, [&](int nn) { return b1[c0 + nn]; });
+            auto p2 = pack_b(kFFChunk, kDP / 2, [&](int k, int nn) {
+              const int col = (nn / (kNC / 2)) * kNC + rk * (kNC / 2) + nn % (kNC / 2);
+              return col < kD ? w2[(size_t)(ch * kFFChunk + k) * kD + col] * alpha1 : 0.f;
+            });
+            imgs.insert(imgs.end(), p1.begin(), p1.end());
+            imgs.insert(imgs.end(), p2.begin(), p2.end());
+          }
+        __nv_bfloat16* dps = nullptr;
+        if ((rc = upload(e, &dps, imgs))) return rc;
+        ld.wffn2s = reinterpret_cast<uint8_t*>(dps);
+      }
     }
     if ((rc = upload(e, &ld.b1, std::vector<float>(b1, b1 + ff)))) return rc;
     if ((rc = upload(e, &ld.b2, pad288(b2, alpha1)))) return rc;
@@ -933,12 +980,11 @@ static int submit_impl(dcb_engine* e, const float* rows, const uint8_t* packed, 
       StackParams sp{};
       sp.num_layers = c.num_hidden_layers;
       sp.ff = c.filter_size;
+      sp.deferred_ln = c.rezero ? 0 : 1;
       for (int n_ = 0; n_ < c.num_hidden_layers; ++n_) {
         const LayerDev& ld = e->layers[n_];
-        sp.wq3[n_] = ld.wq3; sp.wo2[n_] = ld.wo2; sp.wffn2[n_] = ld.wffn2;
-        sp.b1[n_] = ld.b1; sp.b2[n_] = ld.b2;
-        sp.ln_g0[n_] = c.rezero ? nullptr : ld.ln_g[0]; sp.ln_b0[n_] = c.rezero ? nullptr : ld.ln_b[0];
-        sp.ln_g1[n_] = c.rezero ? nullptr : ld.ln_g[1]; sp.ln_b1[n_] = c.rezero ? nullptr : ld.ln_b[1];
+        sp.wq3[n_] = ld.wq3; sp.wo2[n_] = ld.wo2; sp.wffn2[n_] = ld.wffn2s;
+        sp.b2[n_] = ld.b2;
       }
       HeadParams hs{};
       if (e->fuse_head) { hs = make_head(); }

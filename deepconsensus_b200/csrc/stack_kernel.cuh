@@ -480,34 +480,26 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
       }
     };
 
-    // Row pass: Y (+= bias, written back) -> [LayerNorm] -> bf16 operand tile sA.  Two threads per row.
-    // Both loops are software-pipelined over two register buffers: the tcgen05.ld of column block cb + 1 is in flight
+    // Row pass: Y (+= bias, written back) -> bf16 operand tile sA.  Two threads per row.
+    // The loops are software-pipelined over two register buffers: the tcgen05.ld of column block cb + 1 is in flight
     // while block cb is processed (the serial ld -> wait -> math -> store form exposed one TMEM round trip per block:
     // measured 5.2 k cycles for 9 blocks).
-    auto row_pass = [&](const float* __restrict__ bias, const float* __restrict__ lg, const float* __restrict__ lb) {
-      float mean = 0.f, rstd = 1.f;
+    //
+    // Pre-LayerNorm models: the normalisation is DEFERRED so that Y is read from TMEM once, not twice (common.h,
+    // StackParams::deferred_ln).  The operand tile is bf16(x - shift) with shift = the row's exact mean at the PREVIOUS row
+    // pass (the first pass of a tile takes one extra pass for it); the weights carry gamma in rows 0..279 and the column
+    // sums / beta^T W (+ b1) in the padding rows 280..287, against which this pass writes -(mean - shift) and 1 / rstd as
+    // bf16 hi / lo pairs.  The accumulator then holds (LN(x) W + bw) / rstd and its reader multiplies by ln_rstd.
+    // Centring on the previous mean keeps |x - shift| ~ |x - mean|, so the bf16 rounding error is that of the normalised
+    // activations whatever the row's offset.
+    float ln_shift = 0.f, ln_rstd = 1.f;
+    auto row_pass = [&](const float* __restrict__ bias, const bool ln, const bool first) {
       const uint32_t ycol = tmem_row + C::kTmemY + cb0 * 16;
-      if (lg) {
-        float s1 = 0.f, s2 = 0.f, shift = 0.f;
-        auto stats = [&](uint32_t (&acc)[16], int cb) {
-          if (bias) {
+      if (ln && first) {
+        float s1 = 0.f;
+        auto sum = [&](uint32_t (&acc)[16], int cb) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + (cb0 + cb) * 16) + i);
-              acc[4 * i + 0] = __float_as_uint(__uint_as_float(acc[4 * i + 0]) + b4.x);
-              acc[4 * i + 1] = __float_as_uint(__uint_as_float(acc[4 * i + 1]) + b4.y);
-              acc[4 * i + 2] = __float_as_uint(__uint_as_float(acc[4 * i + 2]) + b4.z);
-              acc[4 * i + 3] = __float_as_uint(__uint_as_float(acc[4 * i + 3]) + b4.w);
-            }
-            tmem_st16(ycol + cb * 16, acc);
-          }
-          if (cb == 0) shift = __uint_as_float(acc[0]);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float dlt = ((cb0 + cb) * 16 + i < kD) ? __uint_as_float(acc[i]) - shift : 0.f;
-            s1 += dlt;
-            s2 += dlt * dlt;
-          }
+          for (int i = 0; i < 16; ++i) s1 += ((cb0 + cb) * 16 + i < kD) ? __uint_as_float(acc[i]) : 0.f;
         };
         uint32_t a[16], b[16];
         tmem_ld16(ycol, a);
@@ -515,38 +507,37 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
         for (int cb = 0; cb < 8; cb += 2) {
           tmem_ld_wait();
           tmem_ld16(ycol + (cb + 1) * 16, b);
-          stats(a, cb);
+          sum(a, cb);
           tmem_ld_wait();
           tmem_ld16(ycol + (cb + 2) * 16, a);
-          stats(b, cb + 1);
+          sum(b, cb + 1);
         }
         tmem_ld_wait();
-        stats(a, 8);
-        if (bias) tmem_st_wait();
-        sStat[halfsel * kTileM + r] = make_float4(shift, s1, s2, 0.f);
+        sum(a, 8);
+        sStat[2 * kTileM + halfsel * kTileM + r] = make_float4(s1, 0.f, 0.f, 0.f);
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float4 o = sStat[(1 - halfsel) * kTileM + r];
-        const float n_me = halfsel ? (float)(kD - 144) : 144.f, n_o = halfsel ? 144.f : (float)(kD - 144);
-        mean = (n_me * shift + s1 + n_o * o.x + o.y) * (1.f / kD);
-        const float d_me = mean - shift, d_o = mean - o.x;
-        const float ss = (s2 - 2.f * d_me * s1 + n_me * d_me * d_me) + (o.z - 2.f * d_o * o.y + n_o * d_o * d_o);
-        rstd = rsqrtf(fmaxf(ss * (1.f / kD), 0.f) + 1e-6f);
+        ln_shift = (s1 + sStat[2 * kTileM + (1 - halfsel) * kTileM + r].x) * (1.f / kD);
       }
       uint4* arow = reinterpret_cast<uint4*>(sA) + r;
-      const bool add_here = bias && !lg;
+      float s1 = 0.f, s2 = 0.f;
       auto emit = [&](uint32_t (&acc)[16], int cb) {
-        if (add_here) {
+        if (bias) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __ldg(bias + (cb0 + cb) * 16 + i));
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + (cb0 + cb) * 16) + i);
+            acc[4 * i + 0] = __float_as_uint(__uint_as_float(acc[4 * i + 0]) + b4.x);
+            acc[4 * i + 1] = __float_as_uint(__uint_as_float(acc[4 * i + 1]) + b4.y);
+            acc[4 * i + 2] = __float_as_uint(__uint_as_float(acc[4 * i + 2]) + b4.z);
+            acc[4 * i + 3] = __float_as_uint(__uint_as_float(acc[4 * i + 3]) + b4.w);
+          }
           tmem_st16(ycol + cb * 16, acc);
         }
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int col = (cb0 + cb) * 16 + i;
-          float x = __uint_as_float(acc[i]);
-          if (lg) x = (x - mean) * rstd * __ldg(lg + col) + __ldg(lb + col);
-          v[i] = col < kD ? x : 0.f;
+          v[i] = col < kD ? __uint_as_float(acc[i]) - ln_shift : 0.f;     // ln_shift == 0 for ReZero models
+          if (ln) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
         }
         arow[(size_t)((cb0 + cb) * 2) * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                                              pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
@@ -568,7 +559,25 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
         tmem_ld_wait();
         emit(a, 8);
       }
-      if (add_here) tmem_st_wait();
+      if (bias) tmem_st_wait();
+      float dmean = 0.f, sd = 1.f;
+      if (ln) {
+        // statistics of (x - shift) over the row's two halves; the staging area is idle until a_ready is signalled
+        sStat[halfsel * kTileM + r] = make_float4(s1, s2, 0.f, 0.f);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float4 o = sStat[(1 - halfsel) * kTileM + r];
+        dmean = (s1 + o.x) * (1.f / kD);                                  // mean - shift
+        sd = sqrtf(fmaxf((s2 + o.y) * (1.f / kD) - dmean * dmean, 0.f) + 1e-6f);
+        ln_rstd = 1.f / sd;
+        ln_shift += dmean;                                                // this pass's mean: the next pass's shift
+      }
+      if (halfsel) {
+        // operand columns 280..287 against the weights' padding rows: -dmean and 1 / rstd, each as hi, hi, lo, lo
+        // (ReZero: 0 and 1 -- the rows then only add b1 in the FFN)
+        const float dh = __bfloat162float(__float2bfloat16(-dmean)), ih = __bfloat162float(__float2bfloat16(sd));
+        arow[(size_t)(kD / 8) * kTileM] = make_uint4(pack_bf16x2(dh, dh), pack_bf16x2(-dmean - dh, -dmean - dh),
+                                                     pack_bf16x2(ih, ih), pack_bf16x2(sd - ih, sd - ih));
+      }
       tc_fence_before();
       fence_proxy_async_smem();
       arrive_leader(a_ready);
@@ -600,12 +609,13 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
       tmem_st_wait();
 
       for (int n = 0; n < NL; ++n) {
+        const bool ln = P.deferred_ln != 0;           // pre-LayerNorm model (deferred normalisation, see row_pass)
         // ---- P1: operand tile of the attention sub-layer (+ b2 of the previous layer's FFN)
         if (n > 0) {
           SW(y_full, k_y & 1, 912); ++k_y;
           tc_fence_after();
         }
-        { TRACE_T0(); row_pass(n > 0 ? P.b2[n - 1] : nullptr, P.ln_g0[n], P.ln_b0[n]); TRACE_ADD(w_rowpass); }
+        { TRACE_T0(); row_pass(n > 0 ? P.b2[n - 1] : nullptr, ln, n == 0); TRACE_ADD(w_rowpass); }
 
         for (int h = 0; h < kHeads; ++h) {
           TRACE_T0();
@@ -640,7 +650,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
               if (j < nb) {
                 float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[j][i]);
+                for (int i = 0; i < 16; ++i) v[i] = ln_rstd * __uint_as_float(acc[j][i]);     // ln_rstd == 1 for ReZero
                 *reinterpret_cast<uint4*>(dst + (2 * (b0 + j)) * 8) =
                     make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
                 *reinterpret_cast<uint4*>(dst + (2 * (b0 + j) + 1) * 8) =
@@ -819,10 +829,9 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
         tc_fence_after();
 
         // ---- P5: operand tile of the FFN
-        { TRACE_T0(); row_pass(nullptr, P.ln_g1[n], P.ln_b1[n]); TRACE_ADD(w_rowpass); }
+        { TRACE_T0(); row_pass(nullptr, ln, false); TRACE_ADD(w_rowpass); }
 
         // ---- hidden-chunk epilogue: H (+b1, ReLU) -> bf16 -> shared memory operand of GEMM2
-        const float* __restrict__ b1 = P.b1[n];
         for (int c = 0; c < nchunks; ++c, ++nchunk) {
           const uint32_t b = nchunk & 1;
           SW(h_full, nchunk & 1, 1216);
@@ -830,7 +839,6 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
           SW(&hs_free[b], ((nchunk >> 1) & 1) ^ 1, 1317);
           TRACE_T0();
           uint4* hrow = reinterpret_cast<uint4*>(sS + b * C::kHBytes) + r;
-          const float* bias = b1 + c * kFFChunk + halfsel * (kFFChunk / 2);
           uint32_t acc[kFFChunk / 32][16];
 #pragma unroll
           for (int cc = 0; cc < kFFChunk / 32; ++cc)
@@ -844,11 +852,11 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
             float v[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cc * 16) + i);
-              v[4 * i + 0] = fmaxf(__uint_as_float(acc[cc][4 * i + 0]) + b4.x, 0.f);
-              v[4 * i + 1] = fmaxf(__uint_as_float(acc[cc][4 * i + 1]) + b4.y, 0.f);
-              v[4 * i + 2] = fmaxf(__uint_as_float(acc[cc][4 * i + 2]) + b4.z, 0.f);
-              v[4 * i + 3] = fmaxf(__uint_as_float(acc[cc][4 * i + 3]) + b4.w, 0.f);
+              // b1 sits in the padding rows of W1 (StackParams): H = relu(rstd * acc), nothing to load
+              v[4 * i + 0] = fmaxf(ln_rstd * __uint_as_float(acc[cc][4 * i + 0]), 0.f);
+              v[4 * i + 1] = fmaxf(ln_rstd * __uint_as_float(acc[cc][4 * i + 1]), 0.f);
+              v[4 * i + 2] = fmaxf(ln_rstd * __uint_as_float(acc[cc][4 * i + 2]), 0.f);
+              v[4 * i + 3] = fmaxf(ln_rstd * __uint_as_float(acc[cc][4 * i + 3]), 0.f);
             }
             hrow[(size_t)(cb * 2) * kTileM] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                                          pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));

@@ -8,6 +8,7 @@ threshold, the share of identical quality characters, the largest quality differ
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, Optional
 
 import numpy as np
@@ -44,11 +45,16 @@ def compare(test: Dict[str, np.ndarray], ref: Dict[str, np.ndarray], margin: flo
       d = np.asarray(test["logits"], np.float64) - np.asarray(ref["logits"], np.float64)
       out["max_logit_err"] = float(np.abs(d).max()) if d.size else 0.0
       out["rms_logit_err"] = float(np.sqrt((d * d).mean())) if d.size else 0.0
+      # How many argmax flips the measured logit error predicts: a position flips when the error of the difference of
+      # its two leading logits (sd = sqrt(2) * rms for independent errors) exceeds the reference margin.  Near-ties
+      # are a property of the model's margins, not of the arithmetic; this puts the mismatch count on that scale.
+      sd = math.sqrt(2.0) * out["rms_logit_err"]
+      out["expected_flips"] = float(sum(0.5 * math.erfc(x / (sd * math.sqrt(2.0))) for x in m.ravel().tolist())) if sd > 0 else 0.0
   return out
 
 
 def summary(stats: Dict[str, float], digits: int = 4) -> Dict[str, float]:
   """The four numbers BASELINE.md section 3.4 asks to travel with every throughput number (+ their context)."""
   keys = ("bases_identical_pct", "qv_exact_pct", "max_dq", "max_logit_err", "rms_logit_err", "positions",
-          "base_mismatches", "base_mismatches_outside_margin", "largest_margin_of_a_mismatch", "margin")
+          "base_mismatches", "base_mismatches_outside_margin", "largest_margin_of_a_mismatch", "margin", "expected_flips")
   return {k: (round(v, digits) if isinstance(v, float) else v) for k, v in stats.items() if k in keys}

@@ -151,8 +151,46 @@ def band_mask(length: int, attn_win_size: Optional[int]) -> torch.Tensor:
   return (idx[:, None] - idx[None, :]).abs() <= attn_win_size
 
 
+class DeferredLN:
+  """emulate="bf16", pre-LayerNorm models: the engine's deferred normalisation (stack_kernel.cuh, row_pass).
+
+  The tensor-core operand is bf16(x - shift) with shift = the row's mean at the previous sub-layer (the exact mean for
+  the first one); gamma is folded into the weight rows before rounding; the rank-1 terms -(mean - shift) * colsum and
+  (beta @ W + bias) / rstd ride in the operand's eight padding columns as bf16 hi / lo pairs; the accumulator is
+  multiplied by rstd when it is read.
+  """
+
+  def __init__(self, h2: torch.Tensor, shift: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
+    mean = h2.mean(-1, keepdim=True)
+    self.shift = mean if shift is None else shift
+    self.d = h2 - self.shift
+    self.dmean = self.d.mean(-1, keepdim=True)
+    var = ((self.d * self.d).mean(-1, keepdim=True) - self.dmean * self.dmean).clamp_min(0.0)
+    self.sd = torch.sqrt(var + 1e-6)
+    self.next_shift = self.shift + self.dmean
+    self.gamma, self.beta = gamma, beta
+
+  @staticmethod
+  def _split(x: torch.Tensor):
+    hi = _bf16(x)
+    return hi, _bf16(x - hi)
+
+  def mm(self, wmat: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    wf = _bf16(self.gamma[:, None] * wmat)
+    bw = self.beta @ wmat
+    if bias is not None:
+      bw = bw + bias
+    ch, cl = self._split(wf.sum(0)[None])
+    bh, bl = self._split(bw[None])
+    dh, dl = self._split(-self.dmean)
+    ih, il = self._split(self.sd)
+    acc = _bf16(self.d) @ wf + (dh + dl) * (ch + cl) + (ih + il) * (bh + bl)
+    return acc / self.sd
+
+
 def attention(y: torch.Tensor, pre: str, params: params_lib.Params, w: weights_lib.Weights,
-              emulate: Optional[str], gain: float, collect: Optional[dict]) -> torch.Tensor:
+              emulate: Optional[str], gain: float, collect: Optional[dict],
+              dln: Optional[DeferredLN] = None) -> torch.Tensor:
   """`Attention.call` (attention_layer.py:169-221) on y [B, L, d]."""
   nh = params.num_heads
   d = params.hidden_size
@@ -164,7 +202,9 @@ def attention(y: torch.Tensor, pre: str, params: params_lib.Params, w: weights_l
   wo = _t(w[pre + "/output_dense_layer/kernel"]).reshape(d, d)
   scale = dh ** -0.5
   y2 = y.reshape(B * L, d)
-  if emulate:
+  if dln is not None:
+    q, k, v = _bf16(dln.mm(wq * scale)), _bf16(dln.mm(wk)), _bf16(dln.mm(wv))
+  elif emulate:
     # engine folds the query scale into Wq and the ReZero gain into Wo before rounding
     q = _mm(y2, wq * scale, emulate)
     k = _mm(y2, wk, emulate)
@@ -197,7 +237,7 @@ def attention(y: torch.Tensor, pre: str, params: params_lib.Params, w: weights_l
 
 
 def ffn(y: torch.Tensor, pre: str, w: weights_lib.Weights, emulate: Optional[str],
-        gain: float) -> torch.Tensor:
+        gain: float, dln: Optional[DeferredLN] = None) -> torch.Tensor:
   """`FeedForwardNetwork.call`: relu(y W1 + b1) W2 + b2 (ffn_layer.py:83-86)."""
   B, L, d = y.shape
   w1 = _t(w[pre + "/filter_dense_layer/kernel"])
@@ -205,7 +245,12 @@ def ffn(y: torch.Tensor, pre: str, w: weights_lib.Weights, emulate: Optional[str
   w2 = _t(w[pre + "/output_dense_layer/kernel"])
   b2 = _t(w[pre + "/output_dense_layer/bias"])
   y2 = y.reshape(B * L, d)
-  if emulate:
+  if dln is not None:
+    h = torch.relu(dln.mm(w1, b1))
+    out = _mm(h, w2 * gain, emulate) + b2 * gain
+  elif emulate:
+    if emulate == "bf16":
+      b1 = sum(DeferredLN._split(b1))       # the engine adds b1 inside the GEMM, as a bf16 hi / lo pair
     h = torch.relu(_mm(y2, w1, emulate) + b1)
     out = _mm(h, w2 * gain, emulate) + b2 * gain
   else:
@@ -243,6 +288,7 @@ def forward(rows: np.ndarray, params: params_lib.Params, w: weights_lib.Weights,
       h = h + _t(positional_encoding(L, d))[None]
     if inter is not None:
       inter["embedded"] = h.numpy().copy()
+    shift = None
     for n in range(params.num_hidden_layers):
       pre = "model/encoder_stack/layers/%d" % n
       for sub, fn in ((0, "attn"), (1, "ffn")):
@@ -252,11 +298,15 @@ def forward(rows: np.ndarray, params: params_lib.Params, w: weights_lib.Weights,
         else:
           y = layer_norm(h, _t(w[spre + "/layer_norm/gamma"]), _t(w[spre + "/layer_norm/beta"]))
           alpha = 1.0
+        dln = None
+        if emulate == "bf16" and not params.rezero:
+          dln = DeferredLN(h.reshape(B * L, d), shift, _t(w[spre + "/layer_norm/gamma"]), _t(w[spre + "/layer_norm/beta"]))
+          shift = dln.next_shift
         gain = alpha if emulate else 1.0     # engine folds alpha into Wo / W2 / b2
         if fn == "attn":
-          out = attention(y, spre + "/layer", params, w, emulate, gain, inter)
+          out = attention(y, spre + "/layer", params, w, emulate, gain, inter, dln)
         else:
-          out = ffn(y, spre + "/layer", w, emulate, gain)
+          out = ffn(y, spre + "/layer", w, emulate, gain, dln)
         if emulate:
           h = h + out
         else:

@@ -40,6 +40,7 @@ LOGIT_RMS_FP32 = 0.02
 LOGIT_TOL_EMU = 0.12
 MARGIN = 0.25
 BASES_MIN = 0.99
+BASES_MIN_POSITIONS = 2000       # below this one near-tie is 0.05 % or more: the count gate applies instead
 QV_EXACT_MIN = 0.96
 CAL = "0,1.197654,-0.99781"
 
@@ -82,7 +83,11 @@ def _assert_strict(out, ref, what=""):
 def _assert_default(out, ref, what=""):
   st = parity.compare(out, ref, margin=MARGIN)
   assert st["max_logit_err"] <= LOGIT_TOL_FP32 and st["rms_logit_err"] <= LOGIT_RMS_FP32, (what, st)
-  assert st["base_mismatches_outside_margin"] == 0 and st["bases_identical_pct"] >= 100 * BASES_MIN, (what, st)
+  assert st["base_mismatches_outside_margin"] == 0, (what, st)
+  # share of identical calls: 99 % on samples large enough for a percentage to mean something; on every sample the
+  # mismatch count must be what the measured logit error predicts from the reference's own margins (parity.compare)
+  assert st["positions"] < BASES_MIN_POSITIONS or st["bases_identical_pct"] >= 100 * BASES_MIN, (what, st)
+  assert st["base_mismatches"] <= 3 * st["expected_flips"] + 3, (what, st)
   assert st["qv_exact_pct"] >= 100 * QV_EXACT_MIN and st["max_dq_outside_margin"] <= 1, (what, st)
   return st
 
