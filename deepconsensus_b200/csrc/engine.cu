@@ -881,7 +881,8 @@ static int submit_impl(dcb_engine* e, const float* rows, const uint8_t* packed, 
   const uint8_t* packed_base = packed ? (rows_dev ? packed : sl.d_packed) : nullptr;
   // the embedding kernel reads packed rows directly on the window-aligned fast path; every other path gets the float32
   // rows they stand for
-  const bool packed_direct = packed_base && !strict && e->fuse_embed && embed_condense_reads_packed(L, e->Lw);
+  const bool packed_direct = packed_base && !strict && e->fuse_embed && embed_condense_reads_packed(L, e->Lw) &&
+                             embed_condense_smem_bytes(R, e->echunks, e->table_elems, e->pl.stride) <= 225 * 1024;
   if (packed_base && !packed_direct) launch_unpack_rows(packed_base, e->pl, batch, sl.d_rows, st);
   const float* rows_base = packed ? sl.d_rows : (rows_dev ? rows : sl.d_rows);
   CU(e, cudaMemsetAsync(sl.d_status, 0, sizeof(int), st));

@@ -290,30 +290,44 @@ __device__ __forceinline__ RowStats row_epilogue_pass1(const RowEpi& e, uint32_t
 __device__ __forceinline__ void row_epilogue_embed_lean(const RowEpi& e, uint32_t tmem_row_base, int tile, int r) {
   float4* xrow = reinterpret_cast<float4*>(e.x + (size_t)tile * x_image_elems()) + r;
   const float4* pi = reinterpret_cast<const float4*>(e.pe_img) + r;
-  float4 pcur[4], pnxt[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) pcur[i] = __ldg(pi + (size_t)i * kTileM);
-#pragma unroll 1
-  for (int cb = 0; cb < kDP / 16; ++cb) {
-    uint32_t acc[16];
+  // two register buffers: the tcgen05.ld and the positional rows of block cb + 1 are in flight while block cb is stored
+  uint32_t a[16], b[16];
+  float4 pa[4], pb[4];
+  auto fetch = [&](uint32_t (&acc)[16], float4 (&p)[4], int cb) {
     tmem_ld16(tmem_row_base + cb * 16, acc);
-    if (cb + 1 < kDP / 16) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) pnxt[i] = __ldg(pi + (size_t)((cb + 1) * 4 + i) * kTileM);
-    }
-    tmem_ld_wait();
+    for (int i = 0; i < 4; ++i)
+#ifdef DCB_EXP_NOPE
+      p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#else
+      p[i] = __ldg(pi + (size_t)(cb * 4 + i) * kTileM);
+#endif
+  };
+  auto emit = [&](const uint32_t (&acc)[16], const float4 (&p)[4], int cb) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int col = cb * 16 + 4 * i;
       float4 o;
-      o.x = col + 0 < kD ? __uint_as_float(acc[4 * i + 0]) + pcur[i].x : 0.f;
-      o.y = col + 1 < kD ? __uint_as_float(acc[4 * i + 1]) + pcur[i].y : 0.f;
-      o.z = col + 2 < kD ? __uint_as_float(acc[4 * i + 2]) + pcur[i].z : 0.f;
-      o.w = col + 3 < kD ? __uint_as_float(acc[4 * i + 3]) + pcur[i].w : 0.f;
+      o.x = col + 0 < kD ? __uint_as_float(acc[4 * i + 0]) + p[i].x : 0.f;
+      o.y = col + 1 < kD ? __uint_as_float(acc[4 * i + 1]) + p[i].y : 0.f;
+      o.z = col + 2 < kD ? __uint_as_float(acc[4 * i + 2]) + p[i].z : 0.f;
+      o.w = col + 3 < kD ? __uint_as_float(acc[4 * i + 3]) + p[i].w : 0.f;
+#ifdef DCB_EXP_NOSTORE
+      if (o.x == 123.456f)
+#endif
       xrow[(size_t)(cb * 4 + i) * kTileM] = o;
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) pcur[i] = pnxt[i];
+  };
+  static_assert((kDP / 16) % 2 == 0, "block pairs");
+  fetch(a, pa, 0);
+#pragma unroll 1
+  for (int cb = 0; cb < kDP / 16; cb += 2) {
+    tmem_ld_wait();
+    fetch(b, pb, cb + 1);
+    emit(a, pa, cb);
+    tmem_ld_wait();
+    if (cb + 2 < kDP / 16) fetch(a, pa, cb + 2);
+    emit(b, pb, cb + 1);
   }
 }
 
@@ -494,7 +508,7 @@ struct EmbCfg {
   static constexpr int kTmemCols = 512;
 };
 
-__global__ void __launch_bounds__(EmbCfg::kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EmbCfg::kThreads, 1)
 embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict__ packed, PackedLayout pl, int R, int L,
                       int Lw, int M, int ntiles, int echunks,
                       const EmbedCol* __restrict__ cols, const EmbedRow* __restrict__ rowmeta,
@@ -502,13 +516,24 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
                       const __nv_bfloat16* __restrict__ wc_img, RowEpi epi, int* __restrict__ status) {
   using C = EmbCfg;
   extern __shared__ __align__(1024) uint8_t smem[];
+#ifdef DCB_TRACE
+  const long long t_entry = clock64();
+#endif
   const int tab_bytes = (table_elems * 2 + 127) & ~127;
-  const int cols_bytes = (echunks * 8 * (int)sizeof(EmbedCol) + 127) & ~127;
+  const int cols_only = (echunks * 8 * (int)sizeof(EmbedCol) + 15) & ~15;
+  const int cols_bytes = (cols_only + echunks * 8 + 127) & ~127;          // + one 8-byte descriptor per K-chunk
   const int ids_bytes = (R * kTileM * 2 + 127) & ~127;
   __nv_bfloat16* s_tab = reinterpret_cast<__nv_bfloat16*>(smem);
   EmbedCol* s_cols = reinterpret_cast<EmbedCol*>(smem + tab_bytes);
+  // per 16-byte K-chunk: .x = source row | kind << 16 | width << 24, .y = table offset (elements).  kind 0: zeros,
+  // 1: one row of a width-8 table, 3: 8 / width consecutive rows of one width-2 / width-4 table, 2: anything else
+  uint2* s_chunk = reinterpret_cast<uint2*>(smem + tab_bytes + cols_only);
   uint16_t* s_ids = reinterpret_cast<uint16_t*>(smem + tab_bytes + cols_bytes);
-  uint8_t* sAslab = smem + ((tab_bytes + cols_bytes + ids_bytes + 1023) & ~1023);
+  // packed rows: the next window's bytes are staged here by one bulk copy while the current tile's slabs are built, so
+  // the id phase reads shared memory instead of waiting on dependent batches of global loads
+  const int raw_bytes = packed ? ((pl.stride + 127) & ~127) : 0;
+  uint8_t* s_raw = smem + tab_bytes + cols_bytes + ids_bytes;
+  uint8_t* sAslab = smem + ((tab_bytes + cols_bytes + ids_bytes + raw_bytes + 1023) & ~1023);
   uint8_t* sB = sAslab + 2 * C::kASlabBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * C::kBSlabBytes);
   uint64_t* a_full = bars;          // [2] builders -> MMA
@@ -518,19 +543,31 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
   uint64_t* acc_full = bars + 8;
   uint64_t* acc_empty = bars + 9;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* raw_full = bars + 11;   // bulk copy -> builders
+  uint64_t* raw_empty = bars + 12;  // builders -> copy issuer
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ksteps = echunks / 2;
   const int nslabs = (ksteps + C::kSlabK - 1) / C::kSlabK;
+  // CTA pairs share the condenser-weight stream: each CTA fetches half of every slab and multicasts it to both (an SM
+  // ingests only 30-50 B/cycle from L2, and 322 KB of weights per 128-token tile made that the pace of the slab loop).
+  // Both CTAs of a pair therefore run the same number of rounds; a CTA whose tile index falls past the end rebuilds the
+  // last tile and drops the result.
+  const uint32_t rank = cluster_ctarank();
+  const int rounds = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_of = [&](int ti) { return min(ti * (int)gridDim.x + (int)blockIdx.x, ntiles - 1); };
+  auto tile_valid = [&](int ti) { return ti * (int)gridDim.x + (int)blockIdx.x < ntiles; };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 256);
+      mbar_init(&a_full[i], 8);     // one arrive per builder warp
       mbar_init(&a_empty[i], 1);
       mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&b_empty[i], 2);    // the UMMA warps of both CTAs of the pair
     }
+    mbar_init(raw_full, 1);
+    mbar_init(raw_empty, 1);
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 128);
+    mbar_init(acc_empty, 4);        // one arrive per epilogue warp
     mbar_fence_init();
   }
   // tables (the blob is padded to 8 elements per table, the device allocation is 256-byte aligned) and column
@@ -540,17 +577,37 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
     const uint4* tv = reinterpret_cast<const uint4*>(tables);
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) reinterpret_cast<uint4*>(s_tab)[i] = __ldg(tv + i);
     for (int i = nvec * 8 + threadIdx.x; i < table_elems; i += blockDim.x) s_tab[i] = tables[i];
-    static_assert(sizeof(EmbedCol) % 4 == 0, "EmbedCol is copied word by word");
-    const uint32_t* cv = reinterpret_cast<const uint32_t*>(cols);
-    const int nw = echunks * 8 * (int)(sizeof(EmbedCol) / 4);
-    for (int i = threadIdx.x; i < nw; i += blockDim.x) reinterpret_cast<uint32_t*>(s_cols)[i] = __ldg(cv + i);
+    // column descriptors: 8 per K-chunk = 160 bytes = ten 16-byte words (the device allocation is 256-byte aligned)
+    static_assert((8 * sizeof(EmbedCol)) % 16 == 0, "EmbedCol is copied in 16-byte words");
+    const uint4* cv = reinterpret_cast<const uint4*>(cols);
+    const int nw = echunks * (int)(8 * sizeof(EmbedCol) / 16);
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) reinterpret_cast<uint4*>(s_cols)[i] = __ldg(cv + i);
   }
   __shared__ EmbedRow s_meta[160];                 // per input row: clip / shift / vocabulary (R <= 160: max_passes <= 38)
   const EmbedRow* __restrict__ rmeta = R <= 160 ? s_meta : rowmeta;
   if (R <= 160) for (int i = threadIdx.x; i < R; i += blockDim.x) s_meta[i] = rowmeta[i];
   if (warp == 1) tmem_alloc(tmem_holder, C::kTmemCols);
+  __syncthreads();
+  for (int kc = threadIdx.x; kc < echunks; kc += blockDim.x) {
+    const EmbedCol* cc = s_cols + kc * 8;
+    const EmbedCol c0 = cc[0];
+    uint32_t kind = 2;
+    bool none = true;
+    for (int j = 0; j < 8; ++j) none = none && cc[j].src_row < 0;
+    if (none) kind = 0;
+    else if (c0.src_row >= 0 && c0.col == 0 && c0.width == 8) kind = 1;
+    else if (c0.src_row >= 0 && c0.col == 0 && (c0.width == 2 || c0.width == 4)) {
+      bool ok = true;
+      for (int j = 0; j < 8; ++j)
+        ok = ok && cc[j].src_row == c0.src_row + j / c0.width && cc[j].col == j % c0.width && cc[j].width == c0.width &&
+             cc[j].table_off == c0.table_off;
+      if (ok) kind = 3;
+    }
+    s_chunk[kc] = make_uint2((uint32_t)(uint16_t)c0.src_row | (kind << 16) | ((uint32_t)c0.width << 24), (uint32_t)c0.table_off);
+  }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();               // the partner's barriers are initialised before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
@@ -560,15 +617,16 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
     // ------------------------------------------------------------- condenser-weight producer
     if (lane == 0) {
       uint32_t n = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      for (int ti = 0; ti < rounds; ++ti)
         for (int sl = 0; sl < nslabs; ++sl, ++n) {
           const uint32_t b = n & 1;
           const int kh = min(C::kSlabK, ksteps - sl * C::kSlabK);
-          mbar_wait(&b_empty[b], ((n >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&b_full[b], kh * 2 * kDP * 16);
-          bulk_g2s(sB + b * C::kBSlabBytes,
-                   reinterpret_cast<const uint8_t*>(wc_img) + (size_t)sl * C::kBSlabBytes, kh * 2 * kDP * 16,
-                   &b_full[b]);
+          const uint32_t half = (uint32_t)kh * kDP * 16;           // this CTA's half of the slab (multiple of 16 bytes)
+          mbar_wait(&b_empty[b], ((n >> 1) & 1) ^ 1);              // slot free in BOTH CTAs
+          mbar_arrive_expect_tx(&b_full[b], 2 * half);
+          bulk_g2s_multicast(sB + b * C::kBSlabBytes + rank * half,
+                             reinterpret_cast<const uint8_t*>(wc_img) + (size_t)sl * C::kBSlabBytes + rank * half, half,
+                             &b_full[b], (uint16_t)3);
         }
     }
   } else if (warp == 1) {
@@ -576,7 +634,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
     {
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, kNC);
       uint32_t n = 0, it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      for (int ti = 0; ti < rounds; ++ti, ++it) {
         mbar_wait(acc_empty, (it & 1) ^ 1);
         tc_fence_after();
         for (int sl = 0; sl < nslabs; ++sl, ++n) {
@@ -596,7 +654,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
             }
           }
           umma_commit_warp(&a_empty[b]);
-          umma_commit_warp(&b_empty[b]);
+          umma_commit_multicast_warp(&b_empty[b], (uint16_t)3);
         }
         umma_commit_warp(acc_full);
       }
@@ -606,16 +664,24 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
     // dependent global-load batches and runs at L2 instead of HBM latency that way.  One tile ahead (paced by acc_full).
     const int pt = threadIdx.x - 64;   // 0..63
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int nxt = tile + gridDim.x;
+    if (packed) {
+      // one bulk copy per round, a round ahead: window of round ti goes out as soon as the id phase of round ti - 1 is over
+      if (pt == 0)
+        for (int ti = 0; ti < rounds; ++ti) {
+          if (ti > 0) mbar_wait(raw_empty, (ti - 1) & 1);
+          mbar_arrive_expect_tx(raw_full, (uint32_t)pl.stride);
+          bulk_g2s(s_raw, packed + (size_t)tile_of(ti) * pl.stride, (uint32_t)pl.stride, raw_full);
+        }
+    } else
+    for (int ti = 0; ti < rounds; ++ti, ++it) {
+      const int nxt = (ti + 1) * (int)gridDim.x + (int)blockIdx.x;
       if (nxt < ntiles) {
         const int w_lo = (nxt * kTileM) / Lw;
         int w_hi = (nxt * kTileM + kTileM - 1) / Lw;
         const int nwin = (M + Lw - 1) / Lw;
         if (w_hi > nwin - 1) w_hi = nwin - 1;
-        const uint8_t* base = packed ? packed + (size_t)w_lo * pl.stride
-                                     : reinterpret_cast<const uint8_t*>(rows + (size_t)w_lo * R * L);
-        const size_t bytes = packed ? (size_t)(w_hi - w_lo + 1) * pl.stride : (size_t)(w_hi - w_lo + 1) * R * L * sizeof(float);
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(rows + (size_t)w_lo * R * L);
+        const size_t bytes = (size_t)(w_hi - w_lo + 1) * R * L * sizeof(float);
         for (size_t off = (size_t)pt * 128; off < bytes; off += 64 * 128)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
       }
@@ -629,7 +695,8 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
     uint32_t n = 0;
     long long t_ids = 0, t_aempty = 0, t_build = 0;
     const long long t_begin = clock64();
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int ti = 0; ti < rounds; ++ti) {
+      const int tile = tile_of(ti);
       TRACE_T0();
       // every slab of the previous tile has been built (program order), but its last reads of s_ids
       // happen in other builder threads: synchronise the builders before overwriting the ids
@@ -640,14 +707,15 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
         // warp reads 128 contiguous bytes.  Ids are what tf.cast(format_rows(value)) would give for the float32 rows
         // the packed form stands for (data_providers.py:151-162, networks.py:457-507).
         const bool wvalid = (size_t)tile * kTileM < (size_t)M;
-        const uint8_t* wbase = packed + (size_t)(wvalid ? tile : 0) * pl.stride;
+        mbar_wait(raw_full, ti & 1);                     // this round's window is in shared memory
+        const uint8_t* wbase = s_raw;
         const uint32_t* base32 = reinterpret_cast<const uint32_t*>(wbase);
         const int P = pl.P, PR = 3 * P + 1 + pl.bq, L4 = L >> 2;
         const int nitems = (PR * 32 + 255) / 256;
         auto load_item = [&](int k) -> uint32_t {
           const int item = bt + k * 256;
           const int pr = item >> 5, g = item & 31;
-          if (k < nitems && pr < PR && wvalid && g < L4) return __ldg(base32 + (size_t)pr * L4 + g);
+          if (k < nitems && pr < PR && wvalid && g < L4) return base32[pr * L4 + g];
           return 0u;
         };
         uint32_t f0 = load_item(0), f1 = load_item(1), f2 = load_item(2);
@@ -660,27 +728,29 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
           if (pr < PR) {
             // reference row this plane feeds (a base|strand byte feeds two)
             const int ru = pr < 3 * P ? pr : (pr == 3 * P ? 4 * P : 4 * P + 1);
-            const EmbedRow m = rmeta[ru];
-            const int hi = m.clip_hi > 0.f ? (int)m.clip_hi : 255;
-            uint32_t ids[4], ids2[4];
-            bool bad = false;
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              int b = (int)((cur >> (8 * q4)) & 0xffu);
-              int id = pr < P ? (b & 7) : min(b, hi);
-              if (id >= m.vocab) { bad = true; id = m.vocab - 1; }
-              ids[q4] = (uint32_t)id;
-              int sid = (b >> 3) & 3;
-              if (pr < P) {
-                const int sv = rmeta[3 * P + pr].vocab;
-                if ((b >> 5) != 0 || sid >= sv) { bad = true; sid = sid >= sv ? sv - 1 : sid; }
-              }
-              ids2[q4] = (uint32_t)sid;
+            // (shared-memory copy of the row descriptors whenever it exists: a plain LDS instead of a generic load)
+            const EmbedRow m = R <= 160 ? s_meta[ru] : rowmeta[ru];
+            // the item's four bytes at once (byte-wise SIMD): clip, range check, clamp, then widen to 16-bit ids
+            const uint32_t vmax = (uint32_t)min(m.vocab - 1, 255) * 0x01010101u;
+            uint32_t idv, bad;
+            if (pr < P) {
+              const int sv = R <= 160 ? s_meta[3 * P + pr].vocab : rowmeta[3 * P + pr].vocab;
+              const uint32_t svmax = (uint32_t)min(sv - 1, 255) * 0x01010101u;
+              uint32_t sidv = (cur >> 3) & 0x03030303u;
+              idv = cur & 0x07070707u;
+              bad = (cur & 0xe0e0e0e0u) | __vcmpgtu4(idv, vmax) | __vcmpgtu4(sidv, svmax);
+              sidv = __vminu4(sidv, svmax);
+              *reinterpret_cast<uint2*>(&s_ids[(3 * P + pr) * kTileM + 4 * g]) =
+                  make_uint2(__byte_perm(sidv, 0u, 0x4140), __byte_perm(sidv, 0u, 0x4342));
+            } else {
+              const uint32_t hi4 = (m.clip_hi > 0.f ? (uint32_t)min((int)m.clip_hi, 255) : 255u) * 0x01010101u;
+              idv = __vminu4(cur, hi4);
+              bad = __vcmpgtu4(idv, vmax);
             }
+            idv = __vminu4(idv, vmax);
             if (bad) atomicOr(status, 1);
-            *reinterpret_cast<uint2*>(&s_ids[ru * kTileM + 4 * g]) = make_uint2(ids[0] | (ids[1] << 16), ids[2] | (ids[3] << 16));
-            if (pr < P)
-              *reinterpret_cast<uint2*>(&s_ids[(3 * P + pr) * kTileM + 4 * g]) = make_uint2(ids2[0] | (ids2[1] << 16), ids2[2] | (ids2[3] << 16));
+            *reinterpret_cast<uint2*>(&s_ids[ru * kTileM + 4 * g]) =
+                make_uint2(__byte_perm(idv, 0u, 0x4140), __byte_perm(idv, 0u, 0x4342));
           }
         }
         if (bt < 128) {
@@ -689,7 +759,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
           uint32_t id = 0;
           if (wvalid && g < L4) {
             const EmbedRow m = rmeta[ru];
-            float v = __ldg(reinterpret_cast<const float*>(wbase + pl.sn_off) + ri);
+            float v = reinterpret_cast<const float*>(wbase + pl.sn_off)[ri];
             if (m.clip_hi > 0.f) v = fminf(fmaxf(v, 0.f), m.clip_hi);
             v += (float)m.shift;
             int iv = (int)v;
@@ -780,6 +850,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (packed && bt == 0) mbar_arrive(raw_empty);     // every builder is past its reads of the staged window
       TRACE_ADD(t_ids);
       for (int sl = 0; sl < nslabs; ++sl, ++n) {
         const uint32_t b = n & 1;
@@ -792,26 +863,41 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
         // issued for all of its items before any is used, so their latencies overlap instead of adding up.
         {
           const int r = bt & (kTileM - 1), kc0 = bt >> 7;
-          EmbedCol c0[C::kSlabK];
-          int id[C::kSlabK];
+          uint2 cd[C::kSlabK];
+          uint32_t id[C::kSlabK];
           uint4 val[C::kSlabK];
 #pragma unroll
           for (int j = 0; j < C::kSlabK; ++j)
-            if (j < kh) c0[j] = s_cols[(sl * C::kSlabK * 2 + 2 * j + kc0) * 8];
+            if (j < kh) cd[j] = s_chunk[sl * C::kSlabK * 2 + 2 * j + kc0];
 #pragma unroll
           for (int j = 0; j < C::kSlabK; ++j) {
             id[j] = 0;
-            if (j < kh && c0[j].src_row >= 0) id[j] = s_ids[c0[j].src_row * kTileM + r];
+            if (j < kh && ((cd[j].x >> 16) & 0xff) == 1) id[j] = s_ids[(cd[j].x & 0xffff) * kTileM + r];
           }
 #pragma unroll
           for (int j = 0; j < C::kSlabK; ++j) {
             if (j < kh) {
-              const int kc = sl * C::kSlabK * 2 + 2 * j + kc0;
-              if (c0[j].width == 8 && c0[j].col == 0 && c0[j].src_row >= 0) {
-                val[j] = *reinterpret_cast<const uint4*>(s_tab + c0[j].table_off + id[j] * 8);
-              } else {
-                uint32_t packed[4];
+              const uint32_t kind = (cd[j].x >> 16) & 0xff, src = cd[j].x & 0xffff, off = cd[j].y;
+              if (kind == 1) {
+                val[j] = *reinterpret_cast<const uint4*>(s_tab + off + id[j] * 8);
+              } else if (kind == 3) {
+                if ((cd[j].x >> 24) == 2) {
+                  uint32_t w[4];
 #pragma unroll
+                  for (int q = 0; q < 4; ++q)
+                    w[q] = *reinterpret_cast<const uint32_t*>(s_tab + off + (uint32_t)s_ids[(src + q) * kTileM + r] * 2);
+                  val[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                } else {
+                  const uint2 lo = *reinterpret_cast<const uint2*>(s_tab + off + (uint32_t)s_ids[src * kTileM + r] * 4);
+                  const uint2 hi = *reinterpret_cast<const uint2*>(s_tab + off + (uint32_t)s_ids[(src + 1) * kTileM + r] * 4);
+                  val[j] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+                }
+              } else if (kind == 0) {
+                val[j] = make_uint4(0u, 0u, 0u, 0u);
+              } else {
+                const int kc = sl * C::kSlabK * 2 + 2 * j + kc0;
+                uint32_t packed[4];
+#pragma unroll 1
                 for (int jj = 0; jj < 4; ++jj) {
                   uint32_t pr = 0;
 #pragma unroll
@@ -835,14 +921,15 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
             if (j < kh) dst[(size_t)(2 * j + kc0) * kTileM + r] = val[j];
         }
         fence_proxy_async_smem();
-        mbar_arrive(&a_full[b]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[b]);      // 256 arrivals on one shared-memory word serialise: one per warp
         TRACE_ADD(t_build);
       }
     }
 #ifdef DCB_TRACE
     if (bt == 0 && blockIdx.x < 256) {
       unsigned long long* tr = g_ffn_trace + blockIdx.x * 16;
-      tr[0] = clock64() - t_begin; tr[1] = t_ids; tr[2] = t_aempty; tr[3] = t_build;
+      tr[0] = clock64() - t_begin; tr[1] = t_ids; tr[2] = t_aempty; tr[3] = t_build; tr[6] = t_begin - t_entry;
     }
 #endif
   } else {
@@ -853,38 +940,48 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
     const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t it = 0;
     long long t_accfull = 0, t_epi = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int ti = 0; ti < rounds; ++ti, ++it) {
+      const int tile = tile_of(ti);
+      const bool valid = tile_valid(ti);
       const bool lean = !epi.has_xold && epi.pe_img && !epi.bias && !epi.ln_g && !epi.xb;
       RowPrefetch pf;
-      if (!lean) row_prefetch_start(epi, tile, r, pf);   // positional rows in flight while the GEMM finishes
+      if (!lean && valid) row_prefetch_start(epi, tile, r, pf);   // positional rows in flight while the GEMM finishes
       TRACE_T0();
       mbar_wait(acc_full, it & 1);
       TRACE_ADD(t_accfull);
       tc_fence_after();
       RowStats st{0.f, 1.f};
-      if (lean) row_epilogue_embed_lean(epi, tmem_row, tile, r);
+      if (!valid) {}                                             // the pair's filler round: nothing to store
+      else if (lean) row_epilogue_embed_lean(epi, tmem_row, tile, r);
       else st = row_epilogue_pass1(epi, tmem_row, tile, r, pf);
       tc_fence_before();
-      mbar_arrive(acc_empty);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
       TRACE_ADD(t_epi);
 #ifdef DCB_TRACE
       if (warp == 12 && lane == 0 && blockIdx.x < 256) { unsigned long long* tr = g_ffn_trace + blockIdx.x * 16; tr[4] = t_accfull; tr[5] = t_epi; }
 #endif
-      if (epi.ln_g && epi.xb) row_epilogue_pass2<false>(epi, tile, r, st.mean, st.rstd);
+      if (valid && epi.ln_g && epi.xb) row_epilogue_pass2<false>(epi, tile, r, st.mean, st.rstd);
     }
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();               // no multicast or remote arrive is still under way towards a CTA that exits
+#ifdef DCB_TRACE
+  if (threadIdx.x == 128 && blockIdx.x < 256) g_ffn_trace[blockIdx.x * 16 + 7] = clock64() - t_entry;
+#endif
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
-size_t embed_condense_smem_bytes(int R, int echunks, int table_elems) {
-  const size_t tab = (table_elems * 2 + 127) & ~127, colsb = (echunks * 8 * sizeof(EmbedCol) + 127) & ~(size_t)127;
+size_t embed_condense_smem_bytes(int R, int echunks, int table_elems, int packed_stride) {
+  const size_t tab = (table_elems * 2 + 127) & ~127;
+  const size_t colsb = ((((size_t)echunks * 8 * sizeof(EmbedCol) + 15) & ~(size_t)15) + (size_t)echunks * 8 + 127) & ~(size_t)127;
   const size_t ids = ((size_t)R * kTileM * 2 + 127) & ~(size_t)127;
-  return ((tab + colsb + ids + 1023) & ~(size_t)1023) + 2 * EmbCfg::kASlabBytes + 2 * EmbCfg::kBSlabBytes + 256;
+  const size_t raw = ((size_t)packed_stride + 127) & ~(size_t)127;      // 0 for float32 rows
+  return ((tab + colsb + ids + raw + 1023) & ~(size_t)1023) + 2 * EmbCfg::kASlabBytes + 2 * EmbCfg::kBSlabBytes + 256;
 }
 
 // =====================================================================================
@@ -2796,10 +2893,12 @@ bool launch_embed_condense(const float* rows, const uint8_t* packed, const Packe
                            int ntiles, int echunks, const EmbedCol* cols,
                            const EmbedRow* rowmeta, const __nv_bfloat16* tables, int table_elems,
                            const __nv_bfloat16* wc_img, const RowEpi& epi, int* status, cudaStream_t st) {
-  const size_t smem = embed_condense_smem_bytes(R, echunks, table_elems);
+  const size_t smem = embed_condense_smem_bytes(R, echunks, table_elems, packed ? pl.stride : 0);
   if (smem > 225 * 1024) return false;
   if (packed && !embed_condense_reads_packed(L, Lw)) return false;
-  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  int grid = ntiles < num_sms() ? ntiles : num_sms();
+  grid = (grid + 1) & ~1;           // CTA pairs (the kernel's cluster dimension)
+  if (grid > (num_sms() & ~1)) grid = num_sms() & ~1;
   embed_condense_kernel<<<grid, EmbCfg::kThreads, smem, st>>>(rows, packed, pl, R, L, Lw, M, ntiles, echunks, cols, rowmeta,
                                                               tables, table_elems, wc_img, epi, status);
   return true;

@@ -19,7 +19,7 @@ void launch_gemm_row(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int
 void launch_gemm_qkv(const __nv_bfloat16* a_img, const __nv_bfloat16* b_img, int ntiles,
                      __nv_bfloat16* qkv_img, cudaStream_t st);
 // fused embedding + condenser (+pos-enc, residual image, next operand); false if it does not fit smem
-size_t embed_condense_smem_bytes(int R, int echunks, int table_elems);
+size_t embed_condense_smem_bytes(int R, int echunks, int table_elems, int packed_stride);
 // `packed` != null: read the packed rows (include/dcb200.h) instead of `rows`; only when embed_condense_reads_packed().
 bool embed_condense_reads_packed(int L, int Lw);
 bool launch_embed_condense(const float* rows, const uint8_t* packed, const PackedLayout& pl, int R, int L, int Lw, int M,

@@ -230,6 +230,17 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
       : "memory");
 }
 
+__device__ __forceinline__ void umma_commit_multicast_warp(uint64_t* bar, uint16_t cta_mask) {   // warp-collective form
+  dcb_jitter_warp();
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------- CTA pairs (cta_group::2)
 // TMEM alloc / dealloc for a CTA pair: the same warp of BOTH CTAs executes it with the same smem offset.
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_holder, uint32_t ncols) {

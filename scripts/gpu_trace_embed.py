@@ -8,7 +8,8 @@ from deepconsensus_b200 import params as P, weights as W, synthetic, engine
 p = P.synthetic_params(20, 120); w = W.init_weights(p, seed=1)
 B = 1024
 rows = synthetic.make_rows(p, B, seed=7)
-lib = engine._load(os.path.join(os.path.dirname(engine.library_path()), "libdcb200_trace.so"))
+libname = [a for a in sys.argv[1:] if a.endswith(".so")] or ["libdcb200_trace.so"]
+lib = engine._load(os.path.join(os.path.dirname(engine.library_path()), libname[0]))
 m = engine.B200Model(p, w, max_batch=B, library=lib)
 packed = "--packed" in sys.argv
 pk = m.pack_rows(rows)
@@ -18,7 +19,7 @@ print("packed rows" if packed else "float32 rows")
 buf = (ctypes.c_uint64 * (256 * 16))()
 lib.dcb_debug_trace(buf, 256 * 16)
 a = np.array(buf[:], dtype=np.float64).reshape(256, 16)[1:148:2]   # odd blocks: the stack kernel's issuer writes even blocks only
-names = ["builder_total", "ids_phase", "wait_a_empty", "build", "epi_wait_acc_full", "epi_body"]
+names = ["builder_total", "ids_phase", "wait_a_empty", "build", "epi_wait_acc_full", "epi_body", "prologue (entry -> builders start)", "kernel total (entry -> exit)"]
 for i, nme in enumerate(names):
     col = a[:, i]
     print("%-18s mean %10.0f  per tile %8.0f" % (nme, col.mean(), col.mean() / 7))
