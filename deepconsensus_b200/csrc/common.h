@@ -138,8 +138,9 @@ struct HeadParams {
   const float* ln_b;
   const float* wfc;      // [280][5]
   const float* bfc;      // [5]
-  const float* gw8;      // [280][8]: gamma_c * Wfc[c][j] for j < 5, zero padded (head_kernel; precomputed at load time)
-  const float* ab;       // [16]: A_j = sum_c gamma_c Wfc[c][j] at 0..4, B_j = sum_c beta_c Wfc[c][j] at 8..12
+  const float* gw8;      // [280][8]: gamma_c * Wfc[c][j] for j < 5, then b2_c of the last layer (fused head), zero padded
+  const float* ab;       // [32]: A_j = sum_c gamma_c Wfc[c][j] at 0..4, B_j = sum_c beta_c Wfc[c][j] at 8..12; fused head:
+                         // H_j = sum_c b2_c gamma_c Wfc[c][j] at 16..20, sum b2 at 24, sum b2^2 at 25
   uint8_t* bases;        // [M] ASCII ' ATCG'
   uint8_t* quals;        // [M] Phred+33
   float* probs;          // [M][5] or null

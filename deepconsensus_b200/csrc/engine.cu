@@ -17,6 +17,10 @@
 #include "../../include/dcb200_debug.h"
 #include "kernels.h"
 
+#ifndef DCB_FUSE_HEAD_DEFAULT
+#define DCB_FUSE_HEAD_DEFAULT 1
+#endif
+
 using namespace dcb;
 
 namespace {
@@ -75,8 +79,9 @@ struct dcb_engine {
   bool fuse_oproj = true;
   bool fuse_embed = true;
   bool fuse_qa = true;
-  bool fuse_head = false;  // head in the tail of the stack kernel: measured 1 % SLOWER than the separate kernel (the five
-                           // 280-long dot products per token are LDS-bound and the tensor pipe idles meanwhile); DCB_FUSE_HEAD=1
+  bool fuse_head = DCB_FUSE_HEAD_DEFAULT != 0;   // head in the tail of the stack kernel (one pipelined pass over the row, the
+                           // gamma * Wfc table in the idle staging area): +1.7 % against the separate head_kernel, and the
+                           // residual image is never written back.  DCB_FUSE_HEAD=0 (developer build): head_kernel
   bool stack = true;   // whole encoder stack in one launch (stack_pair_kernel) when the configuration allows it
   bool qkv2 = false;   // measured: not faster than gemm_kernel<3,QKV> (both sit on the per-SM L2 port), kept as an option
   bool fused_last = false;
@@ -461,6 +466,7 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
   // ---- encoder layers
   const int ff = c.filter_size;
   e->layers.assign(c.num_hidden_layers, LayerDev());
+  std::vector<float> last_b2(kD, 0.f);   // output bias of the last layer's FFN (ReZero gain folded in), for the fused head
   for (int n_ = 0; n_ < c.num_hidden_layers; ++n_) {
     LayerDev& ld = e->layers[n_];
     char pre[128];
@@ -666,6 +672,8 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
     }
     if ((rc = upload(e, &ld.b1, std::vector<float>(b1, b1 + ff)))) return rc;
     if ((rc = upload(e, &ld.b2, pad288(b2, alpha1)))) return rc;
+    last_b2.assign(kD, 0.f);
+    for (int k = 0; k < kD; ++k) last_b2[k] = b2[k] * alpha1;      // what the stack kernel adds to Y after this layer
   }
   // ---- head
   {
@@ -679,14 +687,22 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
     if ((rc = upload(e, &e->d_bfc, std::vector<float>(bb, bb + kVocab)))) return rc;
     // head_kernel folds the final LayerNorm into the fc1 sums (one pass over the row): logits_j = rstd * (sum_c y_c g_c W_cj
     // - mean_y * A_j) + B_j + bfc_j.  The products are formed here once, in float32 in the same order the kernel used to.
-    std::vector<float> gw8((size_t)kD * 8, 0.f), ab(16, 0.f);
-    for (int cc = 0; cc < kD; ++cc)
+    // The fused tail of the stack kernel works on Y = x - b2 (b2 of the last layer joins here): column 5 of the table and
+    // H_j, sum b2, sum b2^2 carry it (stack_kernel.cuh, fused head).
+    std::vector<float> gw8((size_t)kD * 8, 0.f), ab(32, 0.f);
+    for (int cc = 0; cc < kD; ++cc) {
       for (int j = 0; j < kVocab; ++j) gw8[(size_t)cc * 8 + j] = g[cc] * w[cc * kVocab + j];
-    for (int j = 0; j < kVocab; ++j) {
-      float a = 0.f, bsum = 0.f;
-      for (int cc = 0; cc < kD; ++cc) { a += g[cc] * w[cc * kVocab + j]; bsum += b[cc] * w[cc * kVocab + j]; }
-      ab[j] = a; ab[8 + j] = bsum;
+      gw8[(size_t)cc * 8 + 5] = last_b2[cc];
     }
+    for (int j = 0; j < kVocab; ++j) {
+      float a = 0.f, bsum = 0.f, h = 0.f;
+      for (int cc = 0; cc < kD; ++cc) {
+        a += g[cc] * w[cc * kVocab + j]; bsum += b[cc] * w[cc * kVocab + j];
+        h += last_b2[cc] * (g[cc] * w[cc * kVocab + j]);
+      }
+      ab[j] = a; ab[8 + j] = bsum; ab[16 + j] = h;
+    }
+    for (int cc = 0; cc < kD; ++cc) { ab[24] += last_b2[cc]; ab[25] += last_b2[cc] * last_b2[cc]; }
     if ((rc = upload(e, &e->d_head_gw8, gw8))) return rc;
     if ((rc = upload(e, &e->d_head_ab, ab))) return rc;
   }

@@ -870,6 +870,14 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
       }
 
       // ---- after the last layer
+      float4 gwreg[3];                                   // fused head: this thread's share of the gamma * Wfc | b2 table,
+      if (HP.bases != nullptr) {                         // fetched while the last GEMM2 drains
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int idx = (int)threadIdx.x - 128 + i * 256;
+          gwreg[i] = idx < kD * 2 ? __ldg(reinterpret_cast<const float4*>(HP.gw8) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       SW(y_full, k_y & 1, 917); ++k_y;
       tc_fence_after();
       const float* __restrict__ b2 = P.b2[NL - 1];
@@ -895,67 +903,71 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
         }
       } else {
         // ---- fused head (encoder_stack.py:197, networks.py:342,238, quick_inference.py:377-414): final LayerNorm of
-        // Y + b2, the five fc1 logits, then head_finish.  Two threads per row: statistics and partial logits are
-        // exchanged through the (now idle) staging area, which also holds gamma | beta | Wfc for broadcast reads.
-        float* sG = reinterpret_cast<float*>(sS + 8192);          // [288] gamma, [288] beta, [280*5] Wfc
-        float* sBt = sG + kDP;
-        float* sW = sBt + kDP;
-        for (int i = threadIdx.x - 128; i < kD; i += 256) { sG[i] = __ldg(HP.ln_g + i); sBt[i] = __ldg(HP.ln_b + i); }
-        for (int i = threadIdx.x - 128; i < kD * kVocab; i += 256) sW[i] = __ldg(HP.wfc + i);
-        float s1 = 0.f, s2 = 0.f, shift = 0.f;
-#pragma unroll 1
-        for (int cb = 0; cb < 9; ++cb) {
-          uint32_t acc[16];
-          tmem_ld16(tmem_row + C::kTmemY + (cb0 + cb) * 16, acc);
-          tmem_ld_wait();
+        // v = Y + b2, the five fc1 logits, then head_finish -- in ONE pass over the row, as head_kernel does it:
+        //   logits_j = rstd * (sum_k (v_k - mean) g_k W_kj) + B_j + bfc_j,  v_k - shift = y_k + b2_k  (y = Y - shift), so with
+        //   T_j = sum y_k gW_kj,  S1 = sum y,  S2 = sum y^2,  BB = sum y_k b2_k  (the row's two halves added up)
+        //   m = (S1 + SB) / n,  var = (S2 + 2 BB + SBB) / n - m^2,  logits_j = rstd * (T_j + H_j - m A_j) + B_j
+        // (A, B, H, SB, SBB: per-model constants in HP.ab; gW | b2 per column in HP.gw8, staged in the idle staging area).
+        float* sShift = reinterpret_cast<float*>(sS);                       // [128]
+        float4* sGW = reinterpret_cast<float4*>(sS + 8192);                 // [280][2]
+        float* sPart = reinterpret_cast<float*>(sS + 8192 + kD * 32);       // [128][8] + [128] partial sums of the upper half
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int idx = (int)threadIdx.x - 128 + i * 256;
+          if (idx < kD * 2) sGW[idx] = gwreg[i];
+        }
+        const uint32_t ycol = tmem_row + C::kTmemY + cb0 * 16;
+        uint32_t a[16], b[16];
+        tmem_ld16(ycol, a);
+        tmem_ld_wait();
+        if (!halfsel) sShift[r] = __uint_as_float(a[0]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // shift of the row published, table staged
+        const float shift = sShift[r];
+        float s1 = 0.f, s2 = 0.f, bb = 0.f, t[kVocab];
+#pragma unroll
+        for (int j = 0; j < kVocab; ++j) t[j] = 0.f;
+        auto accum = [&](const uint32_t (&acc)[16], int cb) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int col = (cb0 + cb) * 16 + i;
             if (col < kD) {
-              const float v = __uint_as_float(acc[i]) + __ldg(b2 + col);
-              if (cb == 0 && i == 0) shift = v;
-              const float dlt = v - shift;
-              s1 += dlt;
-              s2 += dlt * dlt;
+              const float y = __uint_as_float(acc[i]) - shift;
+              const float4 w0 = sGW[col * 2], w1 = sGW[col * 2 + 1];          // 16-byte broadcast reads
+              s1 += y;
+              s2 = fmaf(y, y, s2);
+              t[0] = fmaf(y, w0.x, t[0]); t[1] = fmaf(y, w0.y, t[1]); t[2] = fmaf(y, w0.z, t[2]);
+              t[3] = fmaf(y, w0.w, t[3]); t[4] = fmaf(y, w1.x, t[4]);
+              bb = fmaf(y, w1.y, bb);
             }
           }
-        }
-        sStat[halfsel * kTileM + r] = make_float4(shift, s1, s2, 0.f);
-        asm volatile("bar.sync 1, 256;" ::: "memory");     // also: gamma / beta / Wfc staged
-        const float4 o = sStat[(1 - halfsel) * kTileM + r];
-        const float n_me = halfsel ? (float)(kD - 144) : 144.f, n_o = halfsel ? 144.f : (float)(kD - 144);
-        const float mean = (n_me * shift + s1 + n_o * o.x + o.y) * (1.f / kD);
-        const float d_me = mean - shift, d_o = mean - o.x;
-        const float ss = (s2 - 2.f * d_me * s1 + n_me * d_me * d_me) + (o.z - 2.f * d_o * o.y + n_o * d_o * d_o);
-        const float rstd = rsqrtf(fmaxf(ss * (1.f / kD), 0.f) + 1e-6f);
-        float lg[kVocab];
-#pragma unroll
-        for (int j = 0; j < kVocab; ++j) lg[j] = 0.f;
+        };
 #pragma unroll 1
-        for (int cb = 0; cb < 9; ++cb) {
-          uint32_t acc[16];
-          tmem_ld16(tmem_row + C::kTmemY + (cb0 + cb) * 16, acc);
+        for (int cb = 0; cb < 8; cb += 2) {
           tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int col = (cb0 + cb) * 16 + i;
-            if (col < kD) {
-              const float z = (__uint_as_float(acc[i]) + __ldg(b2 + col) - mean) * rstd * sG[col] + sBt[col];
-#pragma unroll
-              for (int j = 0; j < kVocab; ++j) lg[j] = fmaf(z, sW[col * kVocab + j], lg[j]);
-            }
-          }
+          tmem_ld16(ycol + (cb + 1) * 16, b);
+          accum(a, cb);
+          tmem_ld_wait();
+          tmem_ld16(ycol + (cb + 2) * 16, a);
+          accum(b, cb + 1);
         }
-        asm volatile("bar.sync 2, 256;" ::: "memory");     // everyone has read the statistics
-        float* sL = reinterpret_cast<float*>(sS);          // partial logits of the upper column half: [128][8]
+        tmem_ld_wait();
+        accum(a, 8);
         if (halfsel) {
-#pragma unroll
-          for (int j = 0; j < kVocab; ++j) sL[r * 8 + j] = lg[j];
+          *reinterpret_cast<float4*>(sPart + r * 8) = make_float4(t[0], t[1], t[2], t[3]);
+          *reinterpret_cast<float4*>(sPart + r * 8 + 4) = make_float4(t[4], s1, s2, bb);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (!halfsel && valid && goff + r < L) {
+          const float4 p0 = *reinterpret_cast<const float4*>(sPart + r * 8), p1 = *reinterpret_cast<const float4*>(sPart + r * 8 + 4);
+          t[0] += p0.x; t[1] += p0.y; t[2] += p0.z; t[3] += p0.w; t[4] += p1.x;
+          s1 += p1.y; s2 += p1.z; bb += p1.w;
+          const float m = (s1 + __ldg(HP.ab + 24)) * (1.f / kD);
+          const float var = fmaxf((s2 + 2.f * bb + __ldg(HP.ab + 25)) * (1.f / kD) - m * m, 0.f);
+          const float rstd = rsqrtf(var + 1e-6f);
+          float lg[kVocab];
 #pragma unroll
-          for (int j = 0; j < kVocab; ++j) lg[j] += sL[r * 8 + j];
+          for (int j = 0; j < kVocab; ++j)
+            lg[j] = rstd * (t[j] + __ldg(HP.ab + 16 + j) - m * __ldg(HP.ab + j)) + __ldg(HP.ab + 8 + j);
           // window-aligned layout: tile == window (kWide: tile pair == window), row == position
           head_finish(HP, lg, kWide ? (size_t)(tile >> 1) * L + goff + r : (size_t)tile * L + r);
         }
