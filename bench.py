@@ -496,7 +496,8 @@ def main():
   if prof["fused_oproj"] == 2:
     pairs = Lp * (2 * wdw + 1) - wdw * (wdw + 1)
     per_token = p.num_hidden_layers * (8.0 * d * d + 4.0 * d * ff + 4.0 * pairs * d / Lp)
-    kname = "stack_pair_kernel (all %d layers: QKV + banded attention + out-proj + FFN, residual in TMEM)" % p.num_hidden_layers
+    kname = ("stack_pair_kernel (all %d layers: QKV + banded attention + out-proj + FFN, residual in TMEM; final LayerNorm, fc1 "
+             "and the quality epilogue in its tail -- their flops are not counted)" % p.num_hidden_layers)
   else:
     per_token = 4.0 * d * ff + (2.0 * d * d if prof["fused_oproj"] else 0.0)
     kname = "ffn_pair_kernel<fused out-proj>" if prof["fused_oproj"] else "ffn_pair_kernel"

@@ -117,6 +117,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 // the same offset in each of them.
 __device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src,
                                                    uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  dcb_jitter();
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
       "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),

@@ -43,8 +43,10 @@ for tag, env, kw in (("stack kernel (rezero)", {}, {}),
     t0 = time.time()
     bad = 0
     ms = []
+    pk = m.pack_rows(rows)
     for i in range(n):
-      got = m.forward(rows, want_logits=True)
+      # the one-kernel path alternates between float32 rows and packed rows (staged by bulk copy in the embedding kernel)
+      got = m.forward_packed(pk, want_logits=True) if (not env and i % 2) else m.forward(rows, want_logits=True)
       ms.append(m.last_ms)
       if env:
         ok = np.array_equal(got["logits"], first["logits"]) if i else True     # per-layer path: self-consistency

@@ -9,7 +9,8 @@ w = W.init_weights(p, seed=1)
 B = 1024
 rows = synthetic.make_rows(p, B, seed=7)
 # DCB_OUT=libdcb200_trace.so DCB_EXTRA_FLAGS=-DDCB_TRACE bash deepconsensus_b200/csrc/build.sh
-lib = engine._load(os.path.join(os.path.dirname(engine.library_path()), "libdcb200_trace.so"))
+libname = [a for a in sys.argv[1:] if a.endswith(".so")] or ["libdcb200_trace.so"]
+lib = engine._load(os.path.join(os.path.dirname(engine.library_path()), libname[0]))
 m = engine.B200Model(p, w, max_batch=B, library=lib)
 for _ in range(3): m.forward(rows)
 print("device ms", m.last_ms)
