@@ -128,6 +128,7 @@ struct StackParams {
   // bf16(x - shift), gamma is folded into rows 0..279, cs = column sums of the rounded folded weights, bw = beta^T W
   // (+ b1 for W1), dmean = mean - shift; the accumulator is (LN(x) W + bw) / rstd and its reader multiplies by rstd.
   int deferred_ln;
+  float b2_mean[kMaxLayers];         // mean over the 280 columns of b2 (the row pass moves its centring shift by it)
   int num_layers;
   int ff;
 };

@@ -35,6 +35,7 @@ struct LayerDev {
   __nv_bfloat16* wo = nullptr;    // [36][288][8]
   uint8_t* wffn = nullptr;        // per ff chunk: [36][128][8] then [16][288][8]
   uint8_t* wffn2 = nullptr;       // CTA-pair image: per (chunk, rank): [36][64][8] then [16][144][8]
+  float b2_mean = 0.f;            // mean of b2 over its 280 columns (stack kernel, deferred LayerNorm)
   uint8_t* wffn2s = nullptr;      // the stack kernel's copy: b1 / deferred-LayerNorm terms in the padding rows (common.h, StackParams)
   uint8_t* wo2 = nullptr;         // CTA-pair out-proj image: per rank [36][144][8]
   float* b1 = nullptr;            // [ff]
@@ -674,6 +675,9 @@ int dcb_load_weights(dcb_engine* e, const dcb_tensor* tensors, int32_t n) {
     if ((rc = upload(e, &ld.b2, pad288(b2, alpha1)))) return rc;
     last_b2.assign(kD, 0.f);
     for (int k = 0; k < kD; ++k) last_b2[k] = b2[k] * alpha1;      // what the stack kernel adds to Y after this layer
+    ld.b2_mean = 0.f;
+    for (int k = 0; k < kD; ++k) ld.b2_mean += last_b2[k];
+    ld.b2_mean /= (float)kD;
   }
   // ---- head
   {
@@ -1001,7 +1005,7 @@ static int submit_impl(dcb_engine* e, const float* rows, const uint8_t* packed, 
       for (int n_ = 0; n_ < c.num_hidden_layers; ++n_) {
         const LayerDev& ld = e->layers[n_];
         sp.wq3[n_] = ld.wq3; sp.wo2[n_] = ld.wo2; sp.wffn2[n_] = ld.wffn2s;
-        sp.b2[n_] = ld.b2;
+        sp.b2[n_] = ld.b2; sp.b2_mean[n_] = ld.b2_mean;
       }
       HeadParams hs{};
       if (e->fuse_head) { hs = make_head(); }

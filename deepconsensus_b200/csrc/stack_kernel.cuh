@@ -473,6 +473,12 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
     __nv_bfloat16* sV = sK + kTileM * kS;
     float4* sStat = reinterpret_cast<float4*>(sS);   // [2][128] LayerNorm partial statistics
     const int cb0 = halfsel * 9;                  // this thread's 9 column blocks (of 16) of Y
+    auto bar_red_or_workers = [&](bool pred) -> bool {   // OR of `pred` over the 256 worker threads (named barrier 1)
+      uint32_t any;
+      asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %1, 0;\n\tbar.red.or.pred p, 1, 256, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(any) : "r"((uint32_t)pred) : "memory");
+      return any != 0;
+    };
     auto arrive_leader = [&](uint64_t* bar) {     // one arrive per warp on the leader's barrier
       __syncwarp();
       if (lane == 0) {
@@ -493,7 +499,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
     // Centring on the previous mean keeps |x - shift| ~ |x - mean|, so the bf16 rounding error is that of the normalised
     // activations whatever the row's offset.
     float ln_shift = 0.f, ln_rstd = 1.f;
-    auto row_pass = [&](const float* __restrict__ bias, const bool ln, const bool first) {
+    auto row_pass = [&](const float* __restrict__ bias, const float bias_mean, const bool ln, const bool first) {
       const uint32_t ycol = tmem_row + C::kTmemY + cb0 * 16;
       if (ln && first) {
         float s1 = 0.f;
@@ -520,11 +526,13 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
       }
       uint4* arow = reinterpret_cast<uint4*>(sA) + r;
       float s1 = 0.f, s2 = 0.f;
+      const float* __restrict__ bias_now = bias;          // added (and stored back) by the first sweep only
+      if (ln && bias) ln_shift += bias_mean;              // the row's mean moves by the mean of the bias that joins here
       auto emit = [&](uint32_t (&acc)[16], int cb) {
-        if (bias) {
+        if (bias_now) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + (cb0 + cb) * 16) + i);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_now + (cb0 + cb) * 16) + i);
             acc[4 * i + 0] = __float_as_uint(__uint_as_float(acc[4 * i + 0]) + b4.x);
             acc[4 * i + 1] = __float_as_uint(__uint_as_float(acc[4 * i + 1]) + b4.y);
             acc[4 * i + 2] = __float_as_uint(__uint_as_float(acc[4 * i + 2]) + b4.z);
@@ -544,7 +552,10 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
         arow[(size_t)((cb0 + cb) * 2 + 1) * kTileM] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
                                                                  pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
       };
-      {
+      float dmean = 0.f, sd = 1.f;
+#pragma unroll 1
+      for (int sweep = 0; sweep < 2; ++sweep) {
+        s1 = 0.f; s2 = 0.f;
         uint32_t a[16], b[16];
         tmem_ld16(ycol, a);
 #pragma unroll 1
@@ -558,16 +569,25 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
         }
         tmem_ld_wait();
         emit(a, 8);
-      }
-      if (bias) tmem_st_wait();
-      float dmean = 0.f, sd = 1.f;
-      if (ln) {
+        if (bias_now) { tmem_st_wait(); bias_now = nullptr; }
+        if (!ln) break;
         // statistics of (x - shift) over the row's two halves; the staging area is idle until a_ready is signalled
-        sStat[halfsel * kTileM + r] = make_float4(s1, s2, 0.f, 0.f);
+        float4* slot = sStat + (sweep ? 4 : 0) * kTileM;
+        slot[halfsel * kTileM + r] = make_float4(s1, s2, 0.f, 0.f);
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float4 o = sStat[(1 - halfsel) * kTileM + r];
+        const float4 o = slot[(1 - halfsel) * kTileM + r];
         dmean = (s1 + o.x) * (1.f / kD);                                  // mean - shift
-        sd = sqrtf(fmaxf((s2 + o.y) * (1.f / kD) - dmean * dmean, 0.f) + 1e-6f);
+        const float var = fmaxf((s2 + o.y) * (1.f / kD) - dmean * dmean, 0.f);
+        sd = sqrtf(var + 1e-6f);
+        if (sweep) break;
+        // Guard: the tile was rounded around `shift`.  If a row's mean has moved by more than its standard deviation since
+        // the previous pass, |x - shift| is no longer ~ |x - mean| and the bf16 rounding would cost precision: every
+        // worker then sweeps once more, the rows concerned centred on their exact mean (CTA-wide vote; rare).
+        const bool far = dmean * dmean > var;
+        if (!bar_red_or_workers(far)) break;
+        if (far) ln_shift += dmean;
+      }
+      if (ln) {
         ln_rstd = 1.f / sd;
         ln_shift += dmean;                                                // this pass's mean: the next pass's shift
       }
@@ -615,7 +635,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
           SW(y_full, k_y & 1, 912); ++k_y;
           tc_fence_after();
         }
-        { TRACE_T0(); row_pass(n > 0 ? P.b2[n - 1] : nullptr, ln, n == 0); TRACE_ADD(w_rowpass); }
+        { TRACE_T0(); row_pass(n > 0 ? P.b2[n - 1] : nullptr, n > 0 ? P.b2_mean[n - 1] : 0.f, ln, n == 0); TRACE_ADD(w_rowpass); }
 
         for (int h = 0; h < kHeads; ++h) {
           TRACE_T0();
@@ -829,7 +849,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
         tc_fence_after();
 
         // ---- P5: operand tile of the FFN
-        { TRACE_T0(); row_pass(nullptr, ln, false); TRACE_ADD(w_rowpass); }
+        { TRACE_T0(); row_pass(nullptr, 0.f, ln, false); TRACE_ADD(w_rowpass); }
 
         // ---- hidden-chunk epilogue: H (+b1, ReLU) -> bf16 -> shared memory operand of GEMM2
         for (int c = 0; c < nchunks; ++c, ++nchunk) {

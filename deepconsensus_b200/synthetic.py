@@ -60,3 +60,18 @@ def make_rows(params: params_lib.Params, batch: int, seed: int = 20240921,
     rows[:, bq[0]] = np.where(ccs_ids == 0, -1.0, q)
   rows[:, sn[0]:sn[1]] = rng.uniform(3.9, 13.0, size=(batch, 4, 1)).astype(np.float32)
   return rows[..., None]
+
+
+def mean_drift_weights(params: params_lib.Params, weights, w2_offset: float = 0.1, b2_offset: float = 15.0,
+                       wo_offset: float = 0.2):
+  """A copy of `weights` whose sub-layer outputs carry a large common-mode component (a constant added to the attention
+  output kernel, the FFN output kernel and the FFN output bias of every layer): the residual rows' mean runs away from
+  zero while their spread stays put.  LayerNorm removes it in exact arithmetic; an engine that rounds operands around a
+  stale mean does not (tests of the stack kernel's re-centring guard)."""
+  out = dict(weights)
+  for n in range(params.num_hidden_layers):
+    pre = "model/encoder_stack/layers/%d" % n
+    out[pre + "/1/layer/output_dense_layer/kernel"] = weights[pre + "/1/layer/output_dense_layer/kernel"] + np.float32(w2_offset)
+    out[pre + "/1/layer/output_dense_layer/bias"] = weights[pre + "/1/layer/output_dense_layer/bias"] + np.float32(b2_offset)
+    out[pre + "/0/layer/output_dense_layer/kernel"] = weights[pre + "/0/layer/output_dense_layer/kernel"] + np.float32(wo_offset)
+  return out

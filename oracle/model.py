@@ -154,18 +154,27 @@ def band_mask(length: int, attn_win_size: Optional[int]) -> torch.Tensor:
 class DeferredLN:
   """emulate="bf16", pre-LayerNorm models: the engine's deferred normalisation (stack_kernel.cuh, row_pass).
 
-  The tensor-core operand is bf16(x - shift) with shift = the row's mean at the previous sub-layer (the exact mean for
-  the first one); gamma is folded into the weight rows before rounding; the rank-1 terms -(mean - shift) * colsum and
+  The tensor-core operand is bf16(x - shift) with shift = the row's mean at the previous sub-layer (+ the mean of a bias
+  that joined since; the exact mean for the first one, and for any row whose mean moved by more than its standard deviation); gamma is folded into the weight rows before rounding; the rank-1 terms -(mean - shift) * colsum and
   (beta @ W + bias) / rstd ride in the operand's eight padding columns as bf16 hi / lo pairs; the accumulator is
   multiplied by rstd when it is read.
   """
 
+  guard = True     # tests switch the re-centring guard off to show what it protects against
+
   def __init__(self, h2: torch.Tensor, shift: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
     mean = h2.mean(-1, keepdim=True)
     self.shift = mean if shift is None else shift
-    self.d = h2 - self.shift
-    self.dmean = self.d.mean(-1, keepdim=True)
-    var = ((self.d * self.d).mean(-1, keepdim=True) - self.dmean * self.dmean).clamp_min(0.0)
+
+    def stats():
+      d = h2 - self.shift
+      dmean = d.mean(-1, keepdim=True)
+      return d, dmean, ((d * d).mean(-1, keepdim=True) - dmean * dmean).clamp_min(0.0)
+    self.d, self.dmean, var = stats()
+    far = self.dmean * self.dmean > var          # the row's mean moved by more than its standard deviation: the engine
+    if self.guard and bool(far.any()):           # sweeps again with those rows centred on their exact mean
+      self.shift = torch.where(far, self.shift + self.dmean, self.shift)
+      self.d, self.dmean, var = stats()
     self.sd = torch.sqrt(var + 1e-6)
     self.next_shift = self.shift + self.dmean
     self.gamma, self.beta = gamma, beta
@@ -302,6 +311,8 @@ def forward(rows: np.ndarray, params: params_lib.Params, w: weights_lib.Weights,
         if emulate == "bf16" and not params.rezero:
           dln = DeferredLN(h.reshape(B * L, d), shift, _t(w[spre + "/layer_norm/gamma"]), _t(w[spre + "/layer_norm/beta"]))
           shift = dln.next_shift
+          if fn == "ffn":      # the FFN's output bias joins the residual at the next row pass: the shift moves by its mean
+            shift = shift + _t(w[spre + "/layer/output_dense_layer/bias"]).mean()
         gain = alpha if emulate else 1.0     # engine folds alpha into Wo / W2 / b2
         if fn == "attn":
           out = attention(y, spre + "/layer", params, w, emulate, gain, inter, dln)

@@ -126,6 +126,30 @@ def test_layernorm_bq_5_layers_L100(engine_mod):
   _check(engine_mod, p, weights_lib.init_weights(p, seed=3), synthetic.make_rows(p, 7, seed=4), cal_str="10,0.9,1.5")
 
 
+def test_prelayernorm_rows_whose_mean_runs_away(engine_mod):
+  """Deferred LayerNorm of the stack kernel (operands rounded around the row's previous mean): sub-layer outputs with a
+  large common-mode component move the mean by many standard deviations per sub-layer.  The kernel's guard re-centres
+  those rows; without it the logit error is 0.09 on this case (oracle emulation with the guard off,
+  tests/test_oracle_model.py), with it the usual 0.02-0.03."""
+  p = params_lib.synthetic_params(20, 100, use_ccs_bq=True, num_hidden_layers=3, rezero=False)
+  w = synthetic.mean_drift_weights(p, weights_lib.init_weights(p, seed=5))
+  rows = synthetic.make_rows(p, 6, seed=6)
+  cal = calibration.parse_calibration_string(CAL)
+  model = engine_mod.B200Model(p, w, max_batch=6, calibration=cal)
+  out = model.forward(rows, want_probs=True, want_logits=True)
+  strict = model.forward(rows, want_probs=True, want_logits=True, strict=True)
+  model.close()
+  ref = omodel.forward(rows, p, w)
+  emu = omodel.forward(rows, p, w, emulate="bf16")
+  refd = _ref_dict(ref["logits"], ref["probs"], cal)
+  _epilogue_exact(out, cal)
+  # float32 itself is coarser here (row means of ~175 against a spread of ~2): the strict path's summation order shows
+  assert np.abs(strict["logits"] - ref["logits"]).max() < 2e-3
+  _assert_default(out, refd, "mean drift, default vs fp32 oracle")
+  assert np.abs(out["logits"] - ref["logits"]).max() < 0.05
+  assert np.abs(out["logits"] - emu["logits"]).max() < 0.04
+
+
 def test_c5_shape_P32_L200(engine_mod):
   p = params_lib.synthetic_params(32, 200)
   _check(engine_mod, p, weights_lib.init_weights(p, seed=5), synthetic.make_rows(p, 5, seed=6), cal_str="skip")

@@ -70,6 +70,25 @@ def test_bf16_emulation_is_close_to_fp32():
   assert 1e-4 < np.abs(a - b).max() < 0.15
 
 
+def test_deferred_layernorm_emulation_recentres_rows_whose_mean_ran_away():
+  """emulate="bf16" mirrors the stack kernel's deferred LayerNorm: operands are rounded around the row's previous mean, and a
+  row whose mean moved by more than its standard deviation is rounded again around its exact mean.  With sub-layer outputs
+  that carry a large common-mode component the guard is what keeps the bf16 error at its usual size."""
+  p = params_lib.synthetic_params(20, 100, use_ccs_bq=True, num_hidden_layers=3, rezero=False)
+  w = synthetic.mean_drift_weights(p, weights_lib.init_weights(p, seed=5))
+  rows = synthetic.make_rows(p, 4, seed=6)
+  out = omodel.forward(rows, p, w, return_intermediates=True)
+  resid = out["intermediates"]["ffn_2"]
+  assert abs(resid.mean(-1)).mean() > 30 * resid.std(-1).mean()          # the rows' mean dwarfs their spread
+  with_guard = np.abs(omodel.forward(rows, p, w, emulate="bf16")["logits"] - out["logits"]).max()
+  try:
+    omodel.DeferredLN.guard = False
+    without = np.abs(omodel.forward(rows, p, w, emulate="bf16")["logits"] - out["logits"]).max()
+  finally:
+    omodel.DeferredLN.guard = True
+  assert with_guard < 0.04 and without > 2 * with_guard, (with_guard, without)
+
+
 def test_postprocess_matches_quick_inference_semantics():
   probs = np.array([[[0.1, 0.6, 0.1, 0.1, 0.1], [1.0, 0, 0, 0, 0], [0.25, 0.25, 0.2, 0.2, 0.1], [0.0, 0.0, 0.0, 0.5, 0.5]]], np.float32)
   y, q = opost.quality_from_probs(probs, 93, None)
