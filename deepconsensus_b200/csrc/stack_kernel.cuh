@@ -493,37 +493,14 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
     //
     // Pre-LayerNorm models: the normalisation is DEFERRED so that Y is read from TMEM once, not twice (common.h,
     // StackParams::deferred_ln).  The operand tile is bf16(x - shift) with shift = the row's exact mean at the PREVIOUS row
-    // pass (the first pass of a tile takes one extra pass for it); the weights carry gamma in rows 0..279 and the column
+    // pass (for the first pass of a tile: summed while the tile is loaded); the weights carry gamma in rows 0..279 and the column
     // sums / beta^T W (+ b1) in the padding rows 280..287, against which this pass writes -(mean - shift) and 1 / rstd as
     // bf16 hi / lo pairs.  The accumulator then holds (LN(x) W + bw) / rstd and its reader multiplies by ln_rstd.
     // Centring on the previous mean keeps |x - shift| ~ |x - mean|, so the bf16 rounding error is that of the normalised
     // activations whatever the row's offset.
     float ln_shift = 0.f, ln_rstd = 1.f;
-    auto row_pass = [&](const float* __restrict__ bias, const float bias_mean, const bool ln, const bool first) {
+    auto row_pass = [&](const float* __restrict__ bias, const float bias_mean, const bool ln) {
       const uint32_t ycol = tmem_row + C::kTmemY + cb0 * 16;
-      if (ln && first) {
-        float s1 = 0.f;
-        auto sum = [&](uint32_t (&acc)[16], int cb) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) s1 += ((cb0 + cb) * 16 + i < kD) ? __uint_as_float(acc[i]) : 0.f;
-        };
-        uint32_t a[16], b[16];
-        tmem_ld16(ycol, a);
-#pragma unroll 1
-        for (int cb = 0; cb < 8; cb += 2) {
-          tmem_ld_wait();
-          tmem_ld16(ycol + (cb + 1) * 16, b);
-          sum(a, cb);
-          tmem_ld_wait();
-          tmem_ld16(ycol + (cb + 2) * 16, a);
-          sum(b, cb + 1);
-        }
-        tmem_ld_wait();
-        sum(a, 8);
-        sStat[2 * kTileM + halfsel * kTileM + r] = make_float4(s1, 0.f, 0.f, 0.f);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        ln_shift = (s1 + sStat[2 * kTileM + (1 - halfsel) * kTileM + r].x) * (1.f / kD);
-      }
       uint4* arow = reinterpret_cast<uint4*>(sA) + r;
       float s1 = 0.f, s2 = 0.f;
       const float* __restrict__ bias_now = bias;          // added (and stored back) by the first sweep only
@@ -614,17 +591,24 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
       const bool valid = tile_raw < ntiles;
       const int tile = min(tile_raw, ntiles - 1);
       float4* xrow = reinterpret_cast<float4*>(xg + (size_t)tile * x_image_elems()) + r;
-      // ---- Y <- x (this thread's half row)
+      // ---- Y <- x (this thread's half row); pre-LayerNorm models: the row's mean on the way, as the first centring shift
+      float xsum = 0.f;
 #pragma unroll 3
       for (int cb = 0; cb < 9; ++cb) {
         uint32_t v[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 x4 = xrow[(size_t)((cb0 + cb) * 4 + i) * kTileM];
+          const float4 x4 = xrow[(size_t)((cb0 + cb) * 4 + i) * kTileM];     // padding columns of the image are zero
+          xsum += (x4.x + x4.y) + (x4.z + x4.w);
           v[4 * i + 0] = __float_as_uint(x4.x); v[4 * i + 1] = __float_as_uint(x4.y);
           v[4 * i + 2] = __float_as_uint(x4.z); v[4 * i + 3] = __float_as_uint(x4.w);
         }
         tmem_st16(tmem_row + C::kTmemY + (cb0 + cb) * 16, v);
+      }
+      if (P.deferred_ln) {
+        sStat[2 * kTileM + halfsel * kTileM + r] = make_float4(xsum, 0.f, 0.f, 0.f);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        ln_shift = (xsum + sStat[2 * kTileM + (1 - halfsel) * kTileM + r].x) * (1.f / kD);
       }
       tmem_st_wait();
 
@@ -635,7 +619,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
           SW(y_full, k_y & 1, 912); ++k_y;
           tc_fence_after();
         }
-        { TRACE_T0(); row_pass(n > 0 ? P.b2[n - 1] : nullptr, n > 0 ? P.b2_mean[n - 1] : 0.f, ln, n == 0); TRACE_ADD(w_rowpass); }
+        { TRACE_T0(); row_pass(n > 0 ? P.b2[n - 1] : nullptr, n > 0 ? P.b2_mean[n - 1] : 0.f, ln); TRACE_ADD(w_rowpass); }
 
         for (int h = 0; h < kHeads; ++h) {
           TRACE_T0();
@@ -849,7 +833,7 @@ stack_pair_kernel(float* __restrict__ xg, int ntiles, int L, int win, const __gr
         tc_fence_after();
 
         // ---- P5: operand tile of the FFN
-        { TRACE_T0(); row_pass(nullptr, 0.f, ln, false); TRACE_ADD(w_rowpass); }
+        { TRACE_T0(); row_pass(nullptr, 0.f, ln); TRACE_ADD(w_rowpass); }
 
         // ---- hidden-chunk epilogue: H (+b1, ReLU) -> bf16 -> shared memory operand of GEMM2
         for (int c = 0; c < nchunks; ++c, ++nchunk) {
