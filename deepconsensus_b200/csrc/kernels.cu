@@ -287,14 +287,18 @@ __device__ __forceinline__ RowStats row_epilogue_pass1(const RowEpi& e, uint32_t
 // Lean form of the row epilogue for the embedding / condenser GEMM in front of the one-kernel stack: no residual
 // input, no bias, no LayerNorm, no bf16 operand image -- x = acc + positional table (image order), nothing else.
 // A small loop body (the general function carries every predicated variant and stalls on instruction fetch).
-__device__ __forceinline__ void row_epilogue_embed_lean(const RowEpi& e, uint32_t tmem_row_base, int tile, int r) {
+// The 288 accumulator columns come from two 144-column TMEM regions (col0: columns 0..143, col1: 144..287); `free0` is
+// arrived on (one lane per warp) as soon as the first region has been read, so the next tile's UMMAs may overwrite it
+// while the second half of this tile is still being stored.
+__device__ __forceinline__ void row_epilogue_embed_lean(const RowEpi& e, uint32_t tmem_row_base, int tile, int r,
+                                                        uint32_t col0, uint32_t col1, uint64_t* free0) {
   float4* xrow = reinterpret_cast<float4*>(e.x + (size_t)tile * x_image_elems()) + r;
   const float4* pi = reinterpret_cast<const float4*>(e.pe_img) + r;
   // two register buffers: the tcgen05.ld and the positional rows of block cb + 1 are in flight while block cb is stored
   uint32_t a[16], b[16];
   float4 pa[4], pb[4];
   auto fetch = [&](uint32_t (&acc)[16], float4 (&p)[4], int cb) {
-    tmem_ld16(tmem_row_base + cb * 16, acc);
+    tmem_ld16(tmem_row_base + (cb < kNC / 16 ? col0 + cb * 16 : col1 + (cb - kNC / 16) * 16), acc);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #ifdef DCB_EXP_NOPE
@@ -323,12 +327,18 @@ __device__ __forceinline__ void row_epilogue_embed_lean(const RowEpi& e, uint32_
 #pragma unroll 1
   for (int cb = 0; cb < kDP / 16; cb += 2) {
     tmem_ld_wait();
+    if (cb == kNC / 16 - 1) {             // block 8 = the last one of the first region is in registers
+      tc_fence_before();
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(free0);
+    }
     fetch(b, pb, cb + 1);
     emit(a, pa, cb);
     tmem_ld_wait();
     if (cb + 2 < kDP / 16) fetch(a, pa, cb + 2);
     emit(b, pb, cb + 1);
   }
+  static_assert((kNC / 16 - 1) % 2 == 0, "the first region ends on an even block");
 }
 
 // =====================================================================================
@@ -504,7 +514,11 @@ struct EmbCfg {
   static constexpr int kSlabK = 5;                                   // k-steps per A slab / B stage
   static constexpr int kASlabBytes = kSlabK * 2 * kTileM * 16;       // 20480
   static constexpr int kBSlabBytes = kSlabK * 2 * kDP * 16;          // 46080
-  static constexpr int kThreads = 512;   // 4 warpgroups: {producer, UMMA, 2 idle}, 2 x builders, row epilogue
+  static constexpr int kBuilders = 384;  // builder threads (12 warps: their id / slab phases are latency-bound, 0.3 IPC per
+                                         // scheduler with 8 warps -- more warps, not more work per warp, is what helps)
+  static constexpr int kChunkGroups = kBuilders / kTileM;              // 3: thread = (row, chunk group)
+  static constexpr int kItems = (2 * kSlabK + kChunkGroups - 1) / kChunkGroups;   // 4 chunks per thread and slab at most
+  static constexpr int kThreads = 128 + kBuilders + 128;   // {producer, UMMA, 2 service warps}, builders, row epilogue
   static constexpr int kTmemCols = 512;
 };
 
@@ -545,6 +559,12 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 10);
   uint64_t* raw_full = bars + 11;   // bulk copy -> builders
   uint64_t* raw_empty = bars + 12;  // builders -> copy issuer
+  // Accumulator: three 144-column TMEM regions; a tile's two column halves take regions (2 it) % 3 and (2 it + 1) % 3 of
+  // the CTA's it-th tile, so the region the epilogue reads LAST is not needed by the next tile and the one it reads FIRST is
+  // released half way through -- the next tile's UMMAs start under the second half of the epilogue (lean epilogue only;
+  // the general row epilogue keeps regions 0 and 1 and releases both at its end).
+  uint64_t* reg_free = bars + 13;   // [3] epilogue -> UMMA issuer
+  const bool lean = !epi.has_xold && epi.pe_img && !epi.bias && !epi.ln_g && !epi.xb;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ksteps = echunks / 2;
   const int nslabs = (ksteps + C::kSlabK - 1) / C::kSlabK;
@@ -559,7 +579,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 8);     // one arrive per builder warp
+      mbar_init(&a_full[i], C::kBuilders / 32);     // one arrive per builder warp
       mbar_init(&a_empty[i], 1);
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 2);    // the UMMA warps of both CTAs of the pair
@@ -567,7 +587,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
     mbar_init(raw_full, 1);
     mbar_init(raw_empty, 1);
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 4);        // one arrive per epilogue warp
+    for (int i = 0; i < 3; ++i) mbar_init(&reg_free[i], 4);   // one arrive per epilogue warp
     mbar_fence_init();
   }
   // tables (the blob is padded to 8 elements per table, the device allocation is 256-byte aligned) and column
@@ -633,9 +653,15 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
     // ------------------------------------------------------------- UMMA issuer (whole warp, elected lane issues)
     {
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, kNC);
-      uint32_t n = 0, it = 0;
+      uint32_t n = 0, it = 0, par = 0;      // par: bit r = parity of region r's acquisitions
       for (int ti = 0; ti < rounds; ++ti, ++it) {
-        mbar_wait(acc_empty, (it & 1) ^ 1);
+        const uint32_t rot = lean ? it : 0u;
+        const uint32_t jr[2] = {(2 * rot) % 3, (2 * rot + 1) % 3};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          mbar_wait(&reg_free[jr[j]], ((par >> jr[j]) & 1) ^ 1);
+          par ^= 1u << jr[j];
+        }
         tc_fence_after();
         for (int sl = 0; sl < nslabs; ++sl, ++n) {
           const uint32_t b = n & 1;
@@ -650,7 +676,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const uint64_t bdesc = make_kc16_desc(sb + kk * (2 * kDP * 16) + j * kNC * 16, kDP * 16, 128);
-              umma_bf16_ss_warp(tmem_base + j * kNC, adesc, bdesc, idesc, (sl | kk) != 0);
+              umma_bf16_ss_warp(tmem_base + jr[j] * kNC, adesc, bdesc, idesc, (sl | kk) != 0);
             }
           }
           umma_commit_warp(&a_empty[b]);
@@ -688,9 +714,9 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
       mbar_wait(acc_full, it & 1);
     }
    }
-  } else if (warp < 12) {
-    setmaxnreg_dec<72>();
-    // ------------------------------------------------------------- builders (256 threads)
+  } else if (warp < 4 + C::kBuilders / 32) {
+    setmaxnreg_dec<80>();
+    // ------------------------------------------------------------- builders (384 threads)
     const int bt = threadIdx.x - 128;   // 0..255
     uint32_t n = 0;
     long long t_ids = 0, t_aempty = 0, t_build = 0;
@@ -700,7 +726,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
       TRACE_T0();
       // every slab of the previous tile has been built (program order), but its last reads of s_ids
       // happen in other builder threads: synchronise the builders before overwriting the ids
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(C::kBuilders) : "memory");
       if (packed) {
         // Packed rows (include/dcb200.h; launcher guarantees Lw == kTileM and L % 4 == 0): the window is
         // [3P+1+bq][L] bytes + four SN floats.  Item = (plane row pr, 4 consecutive positions) = one 32-bit load; a
@@ -711,9 +737,9 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
         const uint8_t* wbase = s_raw;
         const uint32_t* base32 = reinterpret_cast<const uint32_t*>(wbase);
         const int P = pl.P, PR = 3 * P + 1 + pl.bq, L4 = L >> 2;
-        const int nitems = (PR * 32 + 255) / 256;
+        const int nitems = (PR * 32 + C::kBuilders - 1) / C::kBuilders;
         auto load_item = [&](int k) -> uint32_t {
-          const int item = bt + k * 256;
+          const int item = bt + k * C::kBuilders;
           const int pr = item >> 5, g = item & 31;
           if (k < nitems && pr < PR && wvalid && g < L4) return base32[pr * L4 + g];
           return 0u;
@@ -723,7 +749,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
         for (int k = 0; k < nitems; ++k) {
           const uint32_t cur = f0;
           f0 = f1; f1 = f2; f2 = load_item(k + 3);
-          const int item = bt + k * 256;
+          const int item = bt + k * C::kBuilders;
           const int pr = item >> 5, g = item & 31;
           if (pr < PR) {
             // reference row this plane feeds (a base|strand byte feeds two)
@@ -774,9 +800,9 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
         // exposed memory latency instead of six dependent batches), a warp reads 512 contiguous bytes.
         const bool wvalid = (size_t)tile * kTileM < (size_t)M;
         const float4* base4 = reinterpret_cast<const float4*>(rows + (size_t)(wvalid ? tile : 0) * R * L);
-        const int nitems = (R * 32 + 255) / 256;
+        const int nitems = (R * 32 + C::kBuilders - 1) / C::kBuilders;
         auto load_item = [&](int k) -> float4 {
-          const int item = bt + k * 256;
+          const int item = bt + k * C::kBuilders;
           const int ru = item >> 5, g = item & 31;
           if (k < nitems && ru < R && wvalid && 4 * g < L) return __ldg(base4 + ((size_t)ru * L + 4 * g) / 4);
           return make_float4(0.f, 0.f, 0.f, 0.f);
@@ -789,7 +815,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
         for (int k = 0; k < nitems; ++k) {
           const float4 cur = f0;
           f0 = f1; f1 = f2; f2 = load_item(k + 3);
-          const int item = bt + k * 256;
+          const int item = bt + k * C::kBuilders;
           const int ru = item >> 5, g = item & 31;
           if (ru < R) {
             const EmbedRow m = rmeta[ru];
@@ -814,23 +840,24 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
           }
         }
       } else {
-        // thread = (token r, input rows rr0, rr0+2, ...): 8 independent global loads in flight per batch
+        // thread = (token r, input rows rr0, rr0 + G, ...; G = 3 row groups): 8 independent global loads in flight per batch
+        constexpr int G = C::kChunkGroups;
         const int r = bt & (kTileM - 1), rr0 = bt >> 7;
         const int tok = tile * kTileM + r;
         const int bw0 = tok / Lw, l0 = tok - bw0 * Lw;
         const bool tvalid = tok < M && l0 < L;      // layout padding (l >= L) embeds to id 0 everywhere
         const int bw = tvalid ? bw0 : 0, l = tvalid ? l0 : 0;
         const float* base = rows + (size_t)bw * R * L + l;
-        for (int rr = rr0; rr < R; rr += 16) {
+        for (int rr = rr0; rr < R; rr += 8 * G) {
           float f[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int ru = rr + 2 * u;
+            const int ru = rr + G * u;
             f[u] = (tvalid && ru < R) ? __ldg(base + (size_t)ru * L) : 0.f;
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int ru = rr + 2 * u;
+            const int ru = rr + G * u;
             if (ru < R) {
               int id = 0;
               if (tvalid) {
@@ -849,7 +876,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
           }
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(C::kBuilders) : "memory");
       if (packed && bt == 0) mbar_arrive(raw_empty);     // every builder is past its reads of the staged window
       TRACE_ADD(t_ids);
       for (int sl = 0; sl < nslabs; ++sl, ++n) {
@@ -858,25 +885,25 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
         mbar_wait(&a_empty[b], ((n >> 1) & 1) ^ 1);
         TRACE_ADD(t_aempty);
         uint4* dst = reinterpret_cast<uint4*>(sAslab + b * C::kASlabBytes);
-        // A thread builds one 16-byte chunk for each of the slab's kh k-steps (items idx = bt + 256 j: chunk kcl = j*2 +
-        // bt/128, row r = bt%128).  The three dependent shared-memory reads (column descriptor -> id -> table row) are
+        // A thread builds up to four of the slab's 2 kh 16-byte chunks for its row (chunk kcl = 3 j + bt / 128, row r =
+        // bt % 128).  The three dependent shared-memory reads (column descriptor -> id -> table row) are
         // issued for all of its items before any is used, so their latencies overlap instead of adding up.
         {
           const int r = bt & (kTileM - 1), kc0 = bt >> 7;
-          uint2 cd[C::kSlabK];
-          uint32_t id[C::kSlabK];
-          uint4 val[C::kSlabK];
+          uint2 cd[C::kItems];
+          uint32_t id[C::kItems];
+          uint4 val[C::kItems];
 #pragma unroll
-          for (int j = 0; j < C::kSlabK; ++j)
-            if (j < kh) cd[j] = s_chunk[sl * C::kSlabK * 2 + 2 * j + kc0];
+          for (int j = 0; j < C::kItems; ++j)
+            if (C::kChunkGroups * j + kc0 < 2 * kh) cd[j] = s_chunk[sl * C::kSlabK * 2 + C::kChunkGroups * j + kc0];
 #pragma unroll
-          for (int j = 0; j < C::kSlabK; ++j) {
+          for (int j = 0; j < C::kItems; ++j) {
             id[j] = 0;
-            if (j < kh && ((cd[j].x >> 16) & 0xff) == 1) id[j] = s_ids[(cd[j].x & 0xffff) * kTileM + r];
+            if (C::kChunkGroups * j + kc0 < 2 * kh && ((cd[j].x >> 16) & 0xff) == 1) id[j] = s_ids[(cd[j].x & 0xffff) * kTileM + r];
           }
 #pragma unroll
-          for (int j = 0; j < C::kSlabK; ++j) {
-            if (j < kh) {
+          for (int j = 0; j < C::kItems; ++j) {
+            if (C::kChunkGroups * j + kc0 < 2 * kh) {
               const uint32_t kind = (cd[j].x >> 16) & 0xff, src = cd[j].x & 0xffff, off = cd[j].y;
               if (kind == 1) {
                 val[j] = *reinterpret_cast<const uint4*>(s_tab + off + id[j] * 8);
@@ -895,7 +922,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
               } else if (kind == 0) {
                 val[j] = make_uint4(0u, 0u, 0u, 0u);
               } else {
-                const int kc = sl * C::kSlabK * 2 + 2 * j + kc0;
+                const int kc = sl * C::kSlabK * 2 + C::kChunkGroups * j + kc0;
                 uint32_t packed[4];
 #pragma unroll 1
                 for (int jj = 0; jj < 4; ++jj) {
@@ -917,8 +944,8 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
             }
           }
 #pragma unroll
-          for (int j = 0; j < C::kSlabK; ++j)
-            if (j < kh) dst[(size_t)(2 * j + kc0) * kTileM + r] = val[j];
+          for (int j = 0; j < C::kItems; ++j)
+            if (C::kChunkGroups * j + kc0 < 2 * kh) dst[(size_t)(C::kChunkGroups * j + kc0) * kTileM + r] = val[j];
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -933,7 +960,7 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
     }
 #endif
   } else {
-    setmaxnreg_inc<216>();
+    setmaxnreg_inc<184>();   // 640 threads start with 96 registers: the service warps release 128 x 40, the builders 384 x 16 = 128 x 88
     // ------------------------------------------------------------- row epilogue (4 warps)
     const int q = warp & 3;
     const int r = q * 32 + lane;
@@ -943,7 +970,8 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
     for (int ti = 0; ti < rounds; ++ti, ++it) {
       const int tile = tile_of(ti);
       const bool valid = tile_valid(ti);
-      const bool lean = !epi.has_xold && epi.pe_img && !epi.bias && !epi.ln_g && !epi.xb;
+      const uint32_t rot = lean ? it : 0u;
+      const uint32_t j0 = (2 * rot) % 3, j1 = (2 * rot + 1) % 3;
       RowPrefetch pf;
       if (!lean && valid) row_prefetch_start(epi, tile, r, pf);   // positional rows in flight while the GEMM finishes
       TRACE_T0();
@@ -951,15 +979,19 @@ embed_condense_kernel(const float* __restrict__ rows, const uint8_t* __restrict_
       TRACE_ADD(t_accfull);
       tc_fence_after();
       RowStats st{0.f, 1.f};
+      bool first_released = false;
       if (!valid) {}                                             // the pair's filler round: nothing to store
-      else if (lean) row_epilogue_embed_lean(epi, tmem_row, tile, r);
+      else if (lean) { row_epilogue_embed_lean(epi, tmem_row, tile, r, j0 * kNC, j1 * kNC, &reg_free[j0]); first_released = true; }
       else st = row_epilogue_pass1(epi, tmem_row, tile, r, pf);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
+      if (lane == 0) {
+        if (!first_released) mbar_arrive(&reg_free[j0]);
+        mbar_arrive(&reg_free[j1]);
+      }
       TRACE_ADD(t_epi);
 #ifdef DCB_TRACE
-      if (warp == 12 && lane == 0 && blockIdx.x < 256) { unsigned long long* tr = g_ffn_trace + blockIdx.x * 16; tr[4] = t_accfull; tr[5] = t_epi; }
+      if (q == 0 && lane == 0 && blockIdx.x < 256) { unsigned long long* tr = g_ffn_trace + blockIdx.x * 16; tr[4] = t_accfull; tr[5] = t_epi; }
 #endif
       if (valid && epi.ln_g && epi.xb) row_epilogue_pass2<false>(epi, tile, r, st.mean, st.rstd);
     }
