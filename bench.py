@@ -217,6 +217,9 @@ def main():
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--batch", type=int, default=WORKLOAD["batch_per_gpu"])
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--nccl-scatter", action="store_true",
+                  help="N > 1: also time the step fed by ONE reader rank over NCCL (BASELINE configs[3]; secondary record, "
+                       "profiles/r02_bench_{2,4,8}gpu.json were produced with it)")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3)
 
@@ -435,8 +438,11 @@ def main():
   # ---- BASELINE configs[3]: the same step fed by ONE reader rank over NCCL (grouped send/recv of packed chunks,
   # double-buffered; results gathered back) instead of every rank holding its own shard.  Secondary record: the
   # natural split for this path is the replica form above (no data-path collective).
+  # Opt-in (--nccl-scatter): of three 8-GPU runs of this record one ended in an unexplained "unspecified launch failure" on
+  # one receiving rank (not reproduced in 3000 overlapped steps on 2 GPUs, scripts/gpu_scatter_stress.py),
+  # and a secondary record must not be able to take the primary line down with it.
   scatter_info = None
-  if world > 1:
+  if world > 1 and args.nccl_scatter:
     from deepconsensus_b200 import parallel as parallel_lib
     feeder = parallel_lib.ScatterFeeder(packed_bytes, 2 * B * L, reader=0, device=torch.device("cuda", local))
     step_rows = None
