@@ -58,7 +58,9 @@ CALIBRATION = "0,1.197654,-0.99781"   # the fixture params.json's dc_calibration
 def config_dict(world: int, batch: int):
   """The `config` of the JSON line -- identical for the engine arm and the --impl reference arm."""
   return dict(WORKLOAD, batch_per_gpu=batch, global_batch=batch * world,
-              parallelism="dp%d (independent shards)" % world)
+              parallelism="dp%d (independent shards)" % world,
+              l2="inputs larger than L2: the timed steps rotate over resident packed batches spanning > 126 MB of addresses, and "
+                 "every step streams the 151 MB fp32 residual image through L2 (details under `timing`)")
 
 
 def cpu_threads() -> int:
